@@ -1,0 +1,166 @@
+/*
+ * elas_b200.h -- C ABI of the B200 (sm_100a) dense-stereo hot path.
+ *
+ * This is the drop-in boundary for the path that libelas's
+ *     void Elas::process(uint8_t* I1, uint8_t* I2, float* D1, float* D2, const int32_t* dims)
+ * (reference libelas/src/elas.h:165, implementation libelas/src/elas.cpp:32-170) runs per frame
+ * inside stereomapper's StereoThread::run (reference stereomapper/stereothread.cpp:76-114).
+ *
+ * Plain C: pointers, sizes and PODs only.  No CUDA, torch or C++ types cross this boundary.
+ * Every entry point returns 0 on success, ELAS_B200_E_FEW_SUPPORT (1) when fewer than three
+ * support points were found (D1/D2 are then filled with -10, the reference leaves them
+ * untouched: elas.cpp:69-75), and a negative ELAS_B200_E_* code on a runtime error.
+ * There is no CPU fallback behind this ABI: without a usable CUDA device every compute entry
+ * point fails with ELAS_B200_E_NO_DEVICE.
+ */
+#ifndef ELAS_B200_H_
+#define ELAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELAS_B200_OK               0
+#define ELAS_B200_E_FEW_SUPPORT    1   /* elas.cpp:69-75 */
+#define ELAS_B200_E_NO_DEVICE     -1
+#define ELAS_B200_E_CUDA          -2
+#define ELAS_B200_E_BAD_ARG       -3
+#define ELAS_B200_E_UNSUPPORTED   -4
+#define ELAS_B200_E_NO_STAGE      -5
+
+/* Presets of Elas::parameters (elas.h:56, :93-118, :121-146). */
+#define ELAS_B200_ROBOTICS   0
+#define ELAS_B200_MIDDLEBURY 1
+
+/*
+ * POD mirror of Elas::parameters (elas.h:59-85): same 23 fields in the same order, the four
+ * C++ bools widened to int32 so the layout is the same from C, C++, Python ctypes and cgo.
+ */
+typedef struct elas_b200_params {
+    int32_t disp_min;               /* elas.h:61 */
+    int32_t disp_max;               /* elas.h:62 */
+    float   support_threshold;      /* elas.h:63 */
+    int32_t support_texture;        /* elas.h:64 */
+    int32_t candidate_stepsize;     /* elas.h:65 */
+    int32_t incon_window_size;      /* elas.h:66 */
+    int32_t incon_threshold;        /* elas.h:67 */
+    int32_t incon_min_support;      /* elas.h:68 */
+    int32_t add_corners;            /* elas.h:69 (bool) */
+    int32_t grid_size;              /* elas.h:70 */
+    float   beta;                   /* elas.h:71 */
+    float   gamma;                  /* elas.h:72 */
+    float   sigma;                  /* elas.h:73 */
+    float   sradius;                /* elas.h:74 */
+    int32_t match_texture;          /* elas.h:75 */
+    int32_t lr_threshold;           /* elas.h:76 */
+    float   speckle_sim_threshold;  /* elas.h:77 */
+    int32_t speckle_size;           /* elas.h:78 */
+    int32_t ipol_gap_width;         /* elas.h:79 */
+    int32_t filter_median;          /* elas.h:80 (bool) */
+    int32_t filter_adaptive_mean;   /* elas.h:81 (bool) */
+    int32_t postprocess_only_left;  /* elas.h:82 (bool) */
+    int32_t subsampling;            /* elas.h:83 (bool) */
+} elas_b200_params;
+
+/* Fills *p with the ROBOTICS or MIDDLEBURY preset (elas.h:88-147). */
+void elas_b200_default_params(elas_b200_params* p, int32_t setting);
+
+/* The parameter set stereomapper's StereoThread::run uses (stereothread.cpp:76-80):
+ * ROBOTICS + postprocess_only_left=1, filter_adaptive_mean=1, support_texture=30. */
+void elas_b200_stereomapper_params(elas_b200_params* p);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. The synchronous drop-in call: what a replacement Elas::process binds (elas.h:165).
+ *    Host pointers; I1/I2 are uint8 rows of dims[2] bytes, dims = {width, height, bytes/line};
+ *    D1/D2 are dense float maps of width x height (width/2 x height/2 with subsampling),
+ *    both non-null.  Caller owns all buffers before and after; nothing is retained.
+ *    Safe to call from any thread (stereomapper starts a new QThread per frame): the device
+ *    context is cached per (device, width, height, parameter block) and guarded by a mutex.
+ * ------------------------------------------------------------------------------------------ */
+int32_t elas_b200_process(const elas_b200_params* p,
+                          const uint8_t* I1, const uint8_t* I2,
+                          float* D1, float* D2, const int32_t dims[3]);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Persistent context for throughput: frames are independent (a fresh Elas object per frame,
+ *    stereothread.cpp:113), so a context owns n_slots frame slots, each with its own CUDA
+ *    stream, device buffers, pinned staging and a host worker for the sequential middle stage
+ *    (lattice filters + Delaunay + plane fit).  No per-frame allocation.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct elas_b200_ctx elas_b200_ctx;
+
+int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                         int32_t width, int32_t height, int32_t n_slots);
+void    elas_b200_destroy(elas_b200_ctx* ctx);
+
+/* One frame through one slot, synchronous, host buffers (same contract as elas_b200_process). */
+int32_t elas_b200_process_ctx(elas_b200_ctx* ctx, int32_t slot,
+                              const uint8_t* I1, const uint8_t* I2,
+                              float* D1, float* D2, int32_t bytes_per_line);
+
+/* n frames pipelined over all slots.  Host buffers; images are tightly strided by
+ * bytes_per_line; I1[i], I2[i], D1[i], D2[i] address frame i.  Host<->device copies are part
+ * of the call.  status[i] (optional) receives the per-frame return code. */
+int32_t elas_b200_process_batch(elas_b200_ctx* ctx, int32_t n,
+                                const uint8_t* const* I1, const uint8_t* const* I2,
+                                float* const* D1, float* const* D2,
+                                int32_t bytes_per_line, int32_t* status);
+
+/* Same, but all four buffers per frame are DEVICE pointers on the context's device (images with
+ * pitch bytes_per_line, disparity maps dense): nothing but the 37 KB candidate lattice and the
+ * support/triangle tables crosses PCIe.  Used by the HBM-resident throughput measurement. */
+int32_t elas_b200_process_batch_device(elas_b200_ctx* ctx, int32_t n,
+                                       const uint8_t* const* dI1, const uint8_t* const* dI2,
+                                       float* const* dD1, float* const* dD2,
+                                       int32_t bytes_per_line, int32_t* status);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Introspection for parity tests and the bench (not used by stereomapper).
+ * ------------------------------------------------------------------------------------------ */
+
+/* When enabled, each stage's output of the NEXT frame run through `slot` is kept on the host and
+ * can be read back by name.  Names and element types:
+ *   "desc1","desc2"      u8  [H][W][16]   descriptor.cpp:88-120 (border = 0)
+ *   "dcan_raw"           i16 [Hc][Wc]     elas.cpp:471-493 (before the lattice filters)
+ *   "dcan"               i16 [Hc][Wc]     elas.cpp:496-502
+ *   "support"            i32 [n][3]       elas.cpp:505-517 (u,v,d)
+ *   "tri1","tri2"        i32 [t][3]       elas.cpp:534-600
+ *   "planes1","planes2"  f32 [t][6]       elas.cpp:605-680 (t1a,t1b,t1c,t2a,t2b,t2c)
+ *   "grid1","grid2"      i32 [gh][gw][dmax+2]  elas.cpp:684-780 (expanded to the reference layout)
+ *   "D1_raw","D2_raw"    f32 [H][W]       elas.cpp:960-1118
+ *   "D1_lr","D2_lr"      f32              elas.cpp:1122-1204
+ *   "D1_seg","D2_seg"    f32              elas.cpp:1208-1326
+ *   "D1_gap","D2_gap"    f32              elas.cpp:1330-1530
+ *   "D1_mean","D2_mean"  f32              elas.cpp:1535-1754
+ */
+int32_t elas_b200_stage_capture(elas_b200_ctx* ctx, int32_t slot, int32_t enable);
+int64_t elas_b200_stage_bytes(elas_b200_ctx* ctx, int32_t slot, const char* name);
+int32_t elas_b200_stage_read(elas_b200_ctx* ctx, int32_t slot, const char* name,
+                             void* dst, int64_t capacity_bytes);
+
+/* Number of CUDA kernels launched by this context since creation (bench: gpu_launches). */
+int64_t elas_b200_launch_count(elas_b200_ctx* ctx);
+
+/* Device time of the last frame run through `slot`, per stage, in milliseconds (CUDA events on
+ * the slot's stream).  names_out/ms_out hold up to `cap` entries; returns the entry count.
+ * Timing must have been switched on with elas_b200_stage_timing(ctx, 1). */
+int32_t elas_b200_stage_timing(elas_b200_ctx* ctx, int32_t enable);
+int32_t elas_b200_stage_times(elas_b200_ctx* ctx, int32_t slot,
+                              const char** names_out, float* ms_out, int32_t cap);
+
+/* Bench hook: runs only the dense matching kernel (left+right, elas.cpp:960-1118) `iters` times
+ * on the tables left in `slot` by the last frame and returns the mean milliseconds per launch
+ * (CUDA events on the slot's stream; flush_l2 != 0 rewrites a >L2-sized buffer between
+ * launches, outside the timed span).  Negative on error. */
+float   elas_b200_time_matching(elas_b200_ctx* ctx, int32_t slot, int32_t iters, int32_t flush_l2);
+
+/* Library / device description (static string, never freed). */
+const char* elas_b200_version(void);
+int32_t     elas_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELAS_B200_H_ */
