@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/s of the dense-stereo hot path (Elas::process) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one batch of B synthetic 1242x375 stereo pairs (d_max 255, stereomapper's parameter
+set: BASELINE.json configs[1]) per GPU through the whole path.  Frames are independent, so they are
+sharded over ranks with no data-path collective (weak scaling: B pairs per GPU per step); the only
+collective is one NCCL broadcast of the parameter block at start-up.
+
+Printed JSON (rank 0, one line):
+  value      pairs/s, whole job, inputs/outputs resident in HBM (elas_b200_process_batch_device)
+  e2e        pairs/s through the C ABI with PINNED HOST buffers (elas_b200_process_batch): the
+             host->device copies of both images and device->host copies of both disparity maps are
+             inside the timed region
+  roofline   matching kernel (K7, elas.cpp:960-1118): algorithmic bytes / CUDA-event time per launch
+             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the unmodified reference libelas (oracle/_ref, -O3 -msse3) on the host cores of this
+             box, one process per core, bounded sample
+--impl reference times only that CPU arm and prints the same line shape with "impl": "reference".
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+W, H, DMAX = 1242, 375, 255           # BASELINE.json configs[1]
+WORKLOAD = f"synthetic {W}x{H} random-texture stereo pairs, d_max={DMAX}, stereomapper parameter set"
+METRIC = "stereo pairs/sec @1242x375 d_max=255"
+
+
+def algorithmic_bytes_matching(w, h, dmax, grid_size=20):
+    """B_match = 72*N + 8*gw*gh*(dmax+2) bytes per stereo pair (both directions)."""
+    gw, gh = -(-w // grid_size), -(-h // grid_size)
+    return 72 * w * h + 8 * gw * gh * (dmax + 2)
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md): nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the unmodified reference (oracle/_ref), one PROCESS per core (Triangle keeps file-scope
+# state, triangle.cpp:541-550, so threads would race)
+# ------------------------------------------------------------------------------------------------
+_cpu_state = {}
+
+
+def _cpu_init(kind):
+    import checkers
+    _cpu_state["impl"] = checkers.RefElas() if kind == "reference" else checkers.OracleElas()
+    _cpu_state["params"] = checkers.stereomapper(DMAX)
+
+
+def _cpu_work(args):
+    seed, n = args
+    import synth
+    L, R, _ = synth.synthetic_pair(W, H, DMAX, seed)
+    impl, p = _cpu_state["impl"], _cpu_state["params"]
+    t0 = time.perf_counter()
+    for _ in range(n):
+        rc, D1, D2 = impl.process(L, R, p)
+    return time.perf_counter() - t0, int((D1 >= 0).sum())
+
+
+def cpu_kind():
+    import checkers
+    return "reference" if checkers.have_ref() else "port"
+
+
+class CpuArm:
+    """A pool of one worker process per host core, each with the checker library loaded."""
+
+    def __init__(self):
+        self.kind = cpu_kind()
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
+        self.pool.map(_cpu_work, [(0, 1)] * self.cores)      # load libraries, touch memory
+
+    def run(self, pairs_per_core):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_work, [(s, pairs_per_core) for s in range(self.cores)], chunksize=1)
+        dt = time.perf_counter() - t0
+        return self.cores * pairs_per_core / dt, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    arm = CpuArm()
+    per_core = args.cpu_pairs_per_core
+    for _ in range(args.warmup):
+        arm.run(1)
+    t_total, pairs = 0.0, 0
+    for _ in range(args.steps):
+        rate, dt = arm.run(per_core)
+        t_total += dt
+        pairs += arm.cores * per_core
+    arm.close()
+    value = pairs / t_total
+    sample = f"{arm.cores} processes x {per_core} pairs per step, {args.steps} steps, Elas::process only"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": arm.cores * per_core, "host_cores": arm.cores},
+        "cpu_baseline": {"value": round(value, 3), "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled through the batch")
+    ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = from host core count)")
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import elas_b200
+    import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # the one collective of the path: rank 0's parameter block to every rank (NCCL broadcast)
+    params = elas_b200.stereomapper(DMAX)
+    blob = torch.frombuffer(bytearray(bytes(params)), dtype=torch.uint8).to(dev)
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    params = elas_b200.Params.from_buffer_copy(bytes(blob.cpu().numpy().tobytes()))
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    slots = args.slots or max(2, min(16, cores // max(world, 1)))
+    B = args.batch
+    bpl = W + 15 - (W - 1) % 16
+
+    # synthetic inputs: `distinct` seeded pairs per rank, cycled to fill the batch
+    pairs = [synth.synthetic_pair(W, H, DMAX, seed=1000 * rank + i)[:2] for i in range(args.distinct)]
+    h_I = torch.zeros((B, 2, H, bpl), dtype=torch.uint8).pin_memory()
+    for i in range(B):
+        L, R = pairs[i % args.distinct]
+        h_I[i, 0, :, :W] = torch.from_numpy(L)
+        h_I[i, 1, :, :W] = torch.from_numpy(R)
+    h_D = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
+    d_I = h_I.to(dev)
+    d_D = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # 4x the 126 MB L2
+
+    def ptrs(t, k):
+        return [t[i, k].data_ptr() for i in range(B)]
+
+    engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank)
+
+    def step_device():
+        return engine.process_batch_ptrs(ptrs(d_I, 0), ptrs(d_I, 1), ptrs(d_D, 0), ptrs(d_D, 1), bpl, device=True)
+
+    def step_host():
+        return engine.process_batch_ptrs(ptrs(h_I, 0), ptrs(h_I, 1), ptrs(h_D, 0), ptrs(h_D, 1), bpl, device=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        """K steps, each bracketed by CUDA events on the current stream (which is idle, so an event
+        completes when recorded and the pair spans all slot streams of the step); L2 flushed between."""
+        total_ms, bad = 0.0, 0
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            status = step_fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            bad += sum(1 for s in status if s != 0)
+        return total_ms, bad
+
+    # warm-up (both paths), then the two timed regions
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_host()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = engine.launch_count()
+    ms_dev, bad_dev = timed(step_device, args.steps)
+    launches = engine.launch_count() - launches0
+    barrier()
+    ms_host, bad_host = timed(step_host, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # parity guard inside the bench: device-resident and host paths must give identical maps
+    same = bool(torch.equal(d_D.cpu(), h_D))
+
+    t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_host_max = float(t[0]), float(t[1])
+
+    # roofline of the matching kernel: isolated launches cycling over all slots' tables (their
+    # combined descriptors exceed L2), CUDA events on the launching stream, L2 flushed first
+    k7_ms = engine.time_matching(iters=max(20, 2 * slots), flush_l2=True)
+    peak, peak_src = measured_hbm_peak()
+    b_match = algorithmic_bytes_matching(W, H, DMAX)
+    achieved = b_match / (k7_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            arm = CpuArm()
+            rate, dt = arm.run(args.cpu_pairs_per_core)
+            cpu = {"value": round(rate, 3), "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind,
+                   "sample": f"{arm.cores} processes x {args.cpu_pairs_per_core} pairs, Elas::process only, {dt:.1f} s wall"}
+            arm.close()
+        total_pairs = world * B * args.steps
+        line = {
+            "metric": METRIC, "value": round(total_pairs / (ms_dev_max * 1e-3), 2), "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_dev_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "slots_per_gpu": slots,
+                       "distinct_pairs": args.distinct, "l2": "512 MiB buffer rewritten between timed steps",
+                       "parallelism": f"frame-sharded x{world}, one NCCL broadcast of the parameter block",
+                       "host_cores": cores},
+            "e2e": {"value": round(total_pairs / (ms_host_max * 1e-3), 2), "unit": "pairs/s",
+                    "h2d_bytes_per_step": B * 2 * W * H, "d2h_bytes_per_step": B * 2 * W * H * 4,
+                    "ms_per_step": round(ms_host_max / args.steps, 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right in one launch)",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},
+        }
+        print(json.dumps(line), flush=True)
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,16 @@ int64_t elas_b200_stage_bytes(elas_b200_ctx* ctx, int32_t slot, const char* name
 int32_t elas_b200_stage_read(elas_b200_ctx* ctx, int32_t slot, const char* name,
                              void* dst, int64_t capacity_bytes);
 
+/* The host middle stage on its own (no device needed): in-place lattice filters
+ * (elas.cpp:174-279), support list (:505-523), Triangle-compatible Delaunay of both point sets
+ * (:534-600) and disparity planes (:605-680).  dcan is the candidate lattice [Hc][Wc] as K2
+ * produces it (filtered in place).  Outputs hold up to support_cap / tri_cap entries; counts are
+ * returned through n_out = {n_support, n_tri1, n_tri2}.  Returns 0, or ELAS_B200_E_FEW_SUPPORT. */
+int32_t elas_b200_host_stage(const elas_b200_params* p, int32_t width, int32_t height, int16_t* dcan,
+                             int32_t* support, int32_t support_cap,
+                             int32_t* tri1, int32_t* tri2, float* planes1, float* planes2,
+                             int32_t tri_cap, int32_t n_out[3]);
+
 /* Number of CUDA kernels launched by this context since creation (bench: gpu_launches). */
 int64_t elas_b200_launch_count(elas_b200_ctx* ctx);
 

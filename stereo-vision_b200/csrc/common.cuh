@@ -1,0 +1,96 @@
+// Shared device/host definitions of the B200 dense-stereo path.
+// Vocabulary follows the reference (libelas/src/elas.{h,cpp}): descriptors, candidate lattice,
+// support points, triangles, disparity planes, candidate grid, disparity maps.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/elas_b200.h"
+
+namespace elasb {
+
+constexpr int kInvalid = -10;        // elas.cpp:977-980: disparity maps are pre-filled with -10
+
+// Everything a kernel needs to know about one frame geometry + parameter block.
+struct FrameGeom {
+    int W, H;            // image size (dims[0], dims[1])
+    int bpl;             // padded image pitch, elas.cpp:37
+    int Dw, Dh;          // disparity map size (W/2 x H/2 with subsampling, elas.h:83-85)
+    int step;            // candidate lattice stride (5, or 6 with subsampling, elas.cpp:453-457)
+    int Wc, Hc;          // candidate lattice size, elas.cpp:460-463
+    int gw, gh;          // candidate grid size, elas.cpp:98-99
+    int gwords;          // 32-bit words per grid cell bitmask = ceil((disp_max+1)/32)
+    int dn;              // disp_max + 1 (number of disparities, elas.cpp:819)
+    int plane_radius;    // elas.cpp:993
+};
+
+// One triangle of one image, prepared by the host stage in the reference's own float arithmetic
+// (elas.cpp:1006-1072): edge lines v = a*u + b, integer corner columns, plane and validity.
+struct __align__(16) TriRaster {
+    float ACa, ACb, ABa, ABb;
+    float BCa, BCb, pa, pb;
+    float pc;
+    int   uA, uB, uC;       // (int32_t)A_u, (int32_t)B_u, (int32_t)C_u after the sort by u
+    int   valid;            // |plane_a| < 0.7 && |plane_d| < 0.7 (elas.cpp:1072)
+    int   pad0, pad1, pad2;
+};
+static_assert(sizeof(TriRaster) == 64, "TriRaster is one 64-byte record");
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned sad16(const uint4& a, const uint4& b)
+{
+    // VABSDIFF4.U8.ACC x4: sum of |a_i - b_i| over 16 bytes (_mm_sad_epu8 both halves, elas.cpp:787-789)
+    unsigned s = 0;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.x), "r"(b.x));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.y), "r"(b.y));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.z), "r"(b.z));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.w), "r"(b.w));
+    return s;
+}
+
+// sum |desc[i] - 128| (elas.cpp:358-362, :851-855)
+__device__ __forceinline__ unsigned texture16(const uint4& a)
+{
+    const uint4 mid = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    return sad16(a, mid);
+}
+#endif  // __CUDACC__
+
+// ---- kernel launchers (one translation unit each) --------------------------------------------
+// K1  Sobel + descriptor, both images (filter.cpp:408-416, descriptor.cpp:48-121)
+void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const uint8_t* img2,
+                       uint4* desc1, uint4* desc2, cudaStream_t s);
+// K2  support matching on the candidate lattice, forward + reverse (elas.cpp:322-445, :471-493)
+void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
+                    const uint4* desc2, int16_t* dcan, cudaStream_t s);
+// K6  candidate grid as per-cell disparity bitmasks, both images (elas.cpp:684-780)
+void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
+                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, cudaStream_t s);
+// triangle-id maps: scan conversion with last-writer-wins (elas.cpp:1074-1114)
+void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
+                   const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s);
+// K7  dense matching, both images (elas.cpp:814-955, :960-1118)
+void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
+                     const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
+                     const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
+                     const uint32_t* grid2, const int32_t* prior, float* D1, float* D2, cudaStream_t s);
+size_t matching_smem_bytes(const FrameGeom& g);
+// K8  left/right consistency (elas.cpp:1122-1204)
+void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
+                     float* O1, float* O2, cudaStream_t s);
+// K9  speckle removal (elas.cpp:1208-1326)
+void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
+                     int32_t* size, cudaStream_t s);
+// K10 gap interpolation (elas.cpp:1330-1530)
+void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, cudaStream_t s);
+// K11 adaptive mean (elas.cpp:1535-1754)
+void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp,
+                          cudaStream_t s);
+// K12 median (elas.cpp:1758-1838)
+void launch_median(const FrameGeom& g, float* D, float* tmp, cudaStream_t s);
+
+// number of kernel launches issued through the launchers above (process-wide, relaxed)
+long long launches_issued();
+void count_launch(int n = 1);
+
+}  // namespace elasb

@@ -1,0 +1,692 @@
+// C ABI (include/elas_b200.h) + per-device context of the B200 dense-stereo path.
+//
+// A context owns `n_slots` frame slots.  A slot is everything one frame needs -- a CUDA stream, all
+// device buffers (images, descriptors, lattice, tables, triangle-id maps, disparity maps, scratch),
+// pinned host mirrors of the small tables and a HostStage -- allocated once: nothing is allocated
+// per frame (the reference mallocs ~20 buffers per Elas::process call).  Frames are independent
+// (stereothread.cpp:113 builds a fresh Elas per frame), so slots run concurrently: one host worker
+// per slot drives   GPU phase A (copy-in, K1 descriptors, K2 support search, lattice copy-out)
+//                -> host stage (lattice filters, Delaunay, planes; host_stage.cc)
+//                -> GPU phase B (tables in, grid, triangle-id maps, K7 matching, K8-K12, copy-out)
+// and the GPU overlaps the phases of different slots.
+#include <atomic>
+#include <condition_variable>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "host_stage.h"
+
+namespace elasb {
+
+static std::atomic<long long> g_launches{0};
+long long launches_issued() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace elasb
+
+using namespace elasb;
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t err__ = (expr);                                                                \
+        if (err__ != cudaSuccess) {                                                                \
+            std::fprintf(stderr, "elas_b200: %s failed at %s:%d: %s\n", #expr, __FILE__, __LINE__, \
+                         cudaGetErrorString(err__));                                               \
+            return ELAS_B200_E_CUDA;                                                               \
+        }                                                                                          \
+    } while (0)
+
+namespace {
+
+struct StageTimer {
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;   // event recorded AFTER the named stage
+    cudaEvent_t begin = nullptr;
+    std::vector<std::pair<std::string, float>> last;          // (stage, ms)
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    // device
+    uint8_t* d_img[2] = {nullptr, nullptr};
+    uint4* d_desc[2] = {nullptr, nullptr};
+    int16_t* d_dcan = nullptr;
+    int32_t* d_support = nullptr;
+    TriRaster* d_tri[2] = {nullptr, nullptr};
+    uint32_t* d_grid_scratch = nullptr;
+    uint32_t* d_grid[2] = {nullptr, nullptr};
+    int32_t* d_map[2] = {nullptr, nullptr};
+    float* d_raw[2] = {nullptr, nullptr};      // K7 output
+    float* d_D[2] = {nullptr, nullptr};        // after the L/R check and post-processing
+    float* d_tmp = nullptr;                    // two planes of scratch
+    int32_t* d_parent = nullptr;
+    int32_t* d_size = nullptr;
+    // pinned host
+    int16_t* h_dcan = nullptr;
+    int32_t* h_support = nullptr;
+    TriRaster* h_tri[2] = {nullptr, nullptr};
+    // host stage + tables of the last frame (kept for elas_b200_time_matching)
+    HostStage host;
+    int n_tri[2] = {0, 0};
+    bool tables_valid = false;
+    // introspection
+    bool capture = false;
+    std::map<std::string, std::vector<uint8_t>> stages;
+    StageTimer timer;
+};
+
+}  // namespace
+
+struct elas_b200_ctx {
+    int device = 0;
+    elas_b200_params p{};
+    FrameGeom g{};
+    int support_cap = 0, tri_cap = 0;
+    int32_t* d_prior = nullptr;
+    void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
+    size_t flush_bytes = 0;
+    bool timing = false;
+    long long launches_at_create = 0;
+    std::vector<std::unique_ptr<Slot>> slots;
+
+    // worker pool: one thread per slot, fed by process_batch
+    struct Job {
+        int n = 0;
+        const uint8_t* const* I1 = nullptr; const uint8_t* const* I2 = nullptr;
+        float* const* D1 = nullptr; float* const* D2 = nullptr;
+        int bpl = 0; bool device_io = false; int32_t* status = nullptr;
+        std::atomic<int> next{0}, done{0}, worst{0};
+        int active = 0;                      // workers currently holding this job (guarded by mu)
+    };
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    Job* job = nullptr;
+    uint64_t job_seq = 0;
+    bool stopping = false;
+    std::mutex batch_mu;                     // one batch at a time
+};
+
+namespace {
+
+FrameGeom make_geom(const elas_b200_params& p, int W, int H)
+{
+    FrameGeom g{};
+    g.W = W; g.H = H;
+    g.bpl = W + 15 - (W - 1) % 16;                                         // elas.cpp:37
+    g.Dw = p.subsampling ? W / 2 : W;
+    g.Dh = p.subsampling ? H / 2 : H;
+    g.step = p.candidate_stepsize + (p.subsampling ? p.candidate_stepsize % 2 : 0);   // :453-457
+    g.Wc = (W + g.step - 1) / g.step;                                      // :462-463
+    g.Hc = (H + g.step - 1) / g.step;
+    g.gw = (int)std::ceil((float)W / (float)p.grid_size);                  // :98-99
+    g.gh = (int)std::ceil((float)H / (float)p.grid_size);
+    g.dn = p.disp_max + 1;
+    g.gwords = (g.dn + 31) / 32;
+    g.plane_radius = (int)std::fmax((float)std::ceil(p.sigma * p.sradius), 2.0f);     // :993
+    return g;
+}
+
+// prior table, elas.cpp:984-992 (float exp/log, as the reference's C++ overloads resolve them)
+std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
+{
+    std::vector<int32_t> P(dn);
+    const float two_sigma_squared = 2 * p.sigma * p.sigma;
+    for (int dd = 0; dd < dn; dd++) {
+        const float tmp = -std::log(p.gamma + std::exp(-dd * dd / two_sigma_squared)) + std::log(p.gamma);
+        P[dd] = (int32_t)(tmp / p.beta);
+    }
+    return P;
+}
+
+void free_slot(Slot& s)
+{
+    for (int k = 0; k < 2; k++) {
+        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]);
+        cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
+        cudaFreeHost(s.h_tri[k]);
+    }
+    cudaFree(s.d_dcan); cudaFree(s.d_support); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
+    cudaFree(s.d_parent); cudaFree(s.d_size);
+    cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_support);
+    for (auto& m : s.timer.marks) cudaEventDestroy(m.second);
+    if (s.timer.begin) cudaEventDestroy(s.timer.begin);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
+{
+    const FrameGeom& g = c->g;
+    const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
+    const size_t cells = (size_t)g.gw * g.gh * g.gwords;
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
+        CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
+        CK(cudaMalloc(&s.d_desc[k], N * 16));
+        CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
+        CK(cudaMalloc(&s.d_grid[k], cells * 4));
+        CK(cudaMalloc(&s.d_map[k], N * 4));
+        CK(cudaMalloc(&s.d_raw[k], ND * 4));
+        CK(cudaMalloc(&s.d_D[k], ND * 4));
+        CK(cudaMallocHost(&s.h_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
+    }
+    CK(cudaMalloc(&s.d_dcan, (size_t)g.Wc * g.Hc * 2));
+    CK(cudaMalloc(&s.d_support, (size_t)c->support_cap * 12));
+    CK(cudaMalloc(&s.d_grid_scratch, 2 * cells * 4));
+    CK(cudaMalloc(&s.d_tmp, 2 * ND * 4));
+    CK(cudaMalloc(&s.d_parent, ND * 4));
+    CK(cudaMalloc(&s.d_size, ND * 4));
+    CK(cudaMallocHost(&s.h_dcan, (size_t)g.Wc * g.Hc * 2));
+    CK(cudaMallocHost(&s.h_support, (size_t)c->support_cap * 12));
+    return ELAS_B200_OK;
+}
+
+// ---- introspection helpers -------------------------------------------------------------------
+
+int32_t grab(Slot& s, const char* name, const void* dptr, size_t bytes)
+{
+    std::vector<uint8_t>& v = s.stages[name];
+    v.resize(bytes);
+    CK(cudaMemcpyAsync(v.data(), dptr, bytes, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return ELAS_B200_OK;
+}
+
+void grab_host(Slot& s, const char* name, const void* ptr, size_t bytes)
+{
+    std::vector<uint8_t>& v = s.stages[name];
+    v.assign((const uint8_t*)ptr, (const uint8_t*)ptr + bytes);
+}
+
+void mark(elas_b200_ctx* c, Slot& s, const char* name)
+{
+    if (!c->timing) return;
+    cudaEvent_t e = nullptr;
+    for (auto& m : s.timer.marks) if (m.first == name) e = m.second;
+    if (!e) { cudaEventCreate(&e); s.timer.marks.emplace_back(name, e); }
+    cudaEventRecord(e, s.stream);
+}
+
+// expands a per-cell bitmask grid to the reference's int32 [gh][gw][disp_max+2] lists (elas.cpp:754-775)
+std::vector<uint8_t> expand_grid(const FrameGeom& g, const std::vector<uint8_t>& raw)
+{
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(raw.data());
+    const size_t cells = (size_t)g.gw * g.gh;
+    std::vector<uint8_t> out(cells * (g.dn + 1) * 4, 0);
+    int32_t* o = reinterpret_cast<int32_t*>(out.data());
+    for (size_t cidx = 0; cidx < cells; cidx++) {
+        int k = 1;
+        for (int d = 0; d < g.dn; d++)
+            if (bits[cidx * g.gwords + (d >> 5)] >> (d & 31) & 1u) o[cidx * (g.dn + 1) + k++] = d;
+        o[cidx * (g.dn + 1)] = k - 1;
+    }
+    return out;
+}
+
+// ---- one frame through one slot ----------------------------------------------------------------
+
+int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool device_io)
+{
+    // fewer than 3 support points: the reference returns without writing D (elas.cpp:69-75), which
+    // leaves the caller with uninitialised maps; the defined behaviour here is "all invalid".
+    const size_t nd = (size_t)c->g.Dw * c->g.Dh;
+    std::vector<float> fill(nd, (float)kInvalid);
+    const cudaMemcpyKind kind = device_io ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+    CK(cudaMemcpy(D1, fill.data(), nd * 4, kind));
+    CK(cudaMemcpy(D2, fill.data(), nd * 4, kind));
+    return ELAS_B200_OK;
+}
+
+int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I2, float* D1,
+                  float* D2, int bytes_per_line, bool device_io)
+{
+    const FrameGeom& g = c->g;
+    const elas_b200_params& p = c->p;
+    const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
+    cudaStream_t st = s.stream;
+    if (s.capture) s.stages.clear();
+    s.tables_valid = false;
+    if (c->timing) {
+        if (!s.timer.begin) cudaEventCreate(&s.timer.begin);
+        cudaEventRecord(s.timer.begin, st);
+    }
+
+    // ---- phase A: images in, descriptors, support search, lattice out --------------------------
+    // elas.cpp:35-56: W bytes of every row into the 16-byte-aligned zero-padded copy
+    CK(cudaMemcpy2DAsync(s.d_img[0], g.bpl, I1, bytes_per_line, g.W, g.H, cudaMemcpyDefault, st));
+    CK(cudaMemcpy2DAsync(s.d_img[1], g.bpl, I2, bytes_per_line, g.W, g.H, cudaMemcpyDefault, st));
+    mark(c, s, "copy_in");
+    launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
+    mark(c, s, "descriptor");
+    launch_support(g, p, s.d_desc[0], s.d_desc[1], s.d_dcan, st);
+    mark(c, s, "support");
+    CK(cudaMemcpyAsync(s.h_dcan, s.d_dcan, (size_t)g.Wc * g.Hc * 2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s.capture) {
+        if (int32_t rc = grab(s, "desc1", s.d_desc[0], N * 16)) return rc;
+        if (int32_t rc = grab(s, "desc2", s.d_desc[1], N * 16)) return rc;
+        grab_host(s, "dcan_raw", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
+        int32_t lat[2] = {g.Wc, g.Hc};
+        grab_host(s, "lattice_dims", lat, sizeof lat);
+    }
+
+    // ---- host stage ---------------------------------------------------------------------------
+    const int n = s.host.run(g, p, s.h_dcan, s.capture);
+    if (s.capture) {
+        grab_host(s, "dcan_incon", s.host.dcan_incon.data(), s.host.dcan_incon.size() * 2);
+        grab_host(s, "dcan", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
+        grab_host(s, "support", s.host.support.data(), s.host.support.size() * 4);
+    }
+    if (n < 3) {
+        if (int32_t rc = fill_invalid(c, s, D1, D2, device_io)) return rc;
+        return ELAS_B200_E_FEW_SUPPORT;
+    }
+    if (n > c->support_cap) return ELAS_B200_E_BAD_ARG;
+    std::memcpy(s.h_support, s.host.support.data(), (size_t)n * 12);
+    for (int k = 0; k < 2; k++) {
+        s.n_tri[k] = (int)s.host.raster[k].size();
+        if (s.n_tri[k] > c->tri_cap) return ELAS_B200_E_BAD_ARG;
+        std::memcpy(s.h_tri[k], s.host.raster[k].data(), (size_t)s.n_tri[k] * sizeof(TriRaster));
+    }
+    if (s.capture) {
+        grab_host(s, "tri1", s.host.tri[0].data(), s.host.tri[0].size() * 4);
+        grab_host(s, "tri2", s.host.tri[1].data(), s.host.tri[1].size() * 4);
+        grab_host(s, "planes1", s.host.planes[0].data(), s.host.planes[0].size() * 4);
+        grab_host(s, "planes2", s.host.planes[1].data(), s.host.planes[1].size() * 4);
+        int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
+        grab_host(s, "grid_dims", gd, sizeof gd);
+    }
+
+    // ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------
+    if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
+    CK(cudaMemcpyAsync(s.d_support, s.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 2; k++)
+        CK(cudaMemcpyAsync(s.d_tri[k], s.h_tri[k], (size_t)s.n_tri[k] * sizeof(TriRaster), cudaMemcpyHostToDevice, st));
+    mark(c, s, "tables_in");
+    launch_grid(g, p, s.d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], st);
+    mark(c, s, "grid");
+    launch_raster(g, p.subsampling, s.d_tri[0], s.n_tri[0], s.d_tri[1], s.n_tri[1], s.d_map[0], s.d_map[1], st);
+    mark(c, s, "raster");
+    launch_matching(g, p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
+                    s.d_grid[0], s.d_grid[1], c->d_prior, s.d_raw[0], s.d_raw[1], st);
+    mark(c, s, "matching");
+    s.tables_valid = true;
+    if (s.capture) {
+        const size_t cells = (size_t)g.gw * g.gh * g.gwords;
+        if (int32_t rc = grab(s, "grid1_bits", s.d_grid[0], cells * 4)) return rc;
+        if (int32_t rc = grab(s, "grid2_bits", s.d_grid[1], cells * 4)) return rc;
+        if (int32_t rc = grab(s, "D1_raw", s.d_raw[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_raw", s.d_raw[1], ND * 4)) return rc;
+    }
+    launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], st);             // elas.cpp:116
+    mark(c, s, "lr_check");
+    if (s.capture) {
+        if (int32_t rc = grab(s, "D1_lr", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_lr", s.d_D[1], ND * 4)) return rc;
+    }
+    const int n_post = p.postprocess_only_left ? 1 : 2;                                  // elas.cpp:121-159
+    for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st);
+    mark(c, s, "segments");
+    if (s.capture) {
+        if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
+    }
+    for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, st);
+    mark(c, s, "gap");
+    if (s.capture) {
+        if (int32_t rc = grab(s, "D1_gap", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
+    }
+    if (p.filter_adaptive_mean) {
+        for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, st);
+        mark(c, s, "adaptive_mean");
+    }
+    if (s.capture) {
+        if (int32_t rc = grab(s, "D1_mean", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_mean", s.d_D[1], ND * 4)) return rc;
+    }
+    if (p.filter_median) {
+        for (int k = 0; k < n_post; k++) launch_median(g, s.d_D[k], s.d_tmp, st);
+        mark(c, s, "median");
+    }
+    CK(cudaMemcpyAsync(D1, s.d_D[0], ND * 4, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(D2, s.d_D[1], ND * 4, cudaMemcpyDefault, st));
+    mark(c, s, "copy_out");
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (s.capture) {
+        if (int32_t rc = grab(s, "D1", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2", s.d_D[1], ND * 4)) return rc;
+    }
+    if (c->timing) {
+        s.timer.last.clear();
+        cudaEvent_t prev = s.timer.begin;
+        // marks are appended in first-use order, which is pipeline order
+        for (auto& m : s.timer.marks) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, prev, m.second) == cudaSuccess) s.timer.last.emplace_back(m.first, ms);
+            prev = m.second;
+        }
+    }
+    return ELAS_B200_OK;
+}
+
+void worker_main(elas_b200_ctx* c, int slot)
+{
+    cudaSetDevice(c->device);
+    uint64_t seen = 0;
+    for (;;) {
+        elas_b200_ctx::Job* job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->cv_work.wait(lk, [&] { return c->stopping || (c->job && c->job_seq != seen); });
+            if (c->stopping) return;
+            job = c->job;
+            seen = c->job_seq;
+            job->active++;
+        }
+        for (;;) {
+            const int i = job->next.fetch_add(1);
+            if (i >= job->n) break;
+            const int32_t rc = run_frame(c, *c->slots[slot], job->I1[i], job->I2[i], job->D1[i], job->D2[i],
+                                         job->bpl, job->device_io);
+            if (job->status) job->status[i] = rc;
+            if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
+            job->done.fetch_add(1);
+        }
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            job->active--;
+            c->cv_done.notify_all();
+        }
+    }
+}
+
+int32_t run_batch(elas_b200_ctx* c, int32_t n, const uint8_t* const* I1, const uint8_t* const* I2,
+                  float* const* D1, float* const* D2, int32_t bpl, int32_t* status, bool device_io)
+{
+    if (!c || n < 0 || !I1 || !I2 || !D1 || !D2 || bpl < c->g.W) return ELAS_B200_E_BAD_ARG;
+    if (n == 0) return ELAS_B200_OK;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    elas_b200_ctx::Job job;
+    job.n = n; job.I1 = I1; job.I2 = I2; job.D1 = D1; job.D2 = D2; job.bpl = bpl;
+    job.device_io = device_io; job.status = status;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->job = &job;
+        c->job_seq++;
+    }
+    c->cv_work.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(c->mu);
+        c->cv_done.wait(lk, [&] { return job.done.load() >= n && job.active == 0; });
+        c->job = nullptr;
+    }
+    return job.worst.load();
+}
+
+// cache of single-slot contexts behind the synchronous drop-in call
+struct CacheKey {
+    int device, W, H;
+    elas_b200_params p;
+    bool operator<(const CacheKey& o) const { return std::memcmp(this, &o, sizeof *this) < 0; }
+};
+std::mutex g_cache_mu;
+std::map<CacheKey, elas_b200_ctx*> g_cache;
+
+}  // namespace
+
+extern "C" {
+
+void elas_b200_default_params(elas_b200_params* p, int32_t setting)
+{
+    // Elas::parameters(setting), elas.h:88-147
+    const bool mb = setting == ELAS_B200_MIDDLEBURY;
+    p->disp_min = 0;                 p->disp_max = 255;
+    p->support_threshold = mb ? 0.95f : 0.85f;
+    p->support_texture = 10;         p->candidate_stepsize = 5;
+    p->incon_window_size = 5;        p->incon_threshold = 5;
+    p->incon_min_support = 5;        p->add_corners = mb ? 1 : 0;
+    p->grid_size = 20;               p->beta = 0.02f;
+    p->gamma = mb ? 5.f : 3.f;       p->sigma = 1.f;
+    p->sradius = mb ? 3.f : 2.f;     p->match_texture = mb ? 0 : 1;
+    p->lr_threshold = 2;             p->speckle_sim_threshold = 1.f;
+    p->speckle_size = 200;           p->ipol_gap_width = mb ? 5000 : 3;
+    p->filter_median = mb ? 1 : 0;   p->filter_adaptive_mean = mb ? 0 : 1;
+    p->postprocess_only_left = mb ? 0 : 1;
+    p->subsampling = 0;
+}
+
+void elas_b200_stereomapper_params(elas_b200_params* p)
+{
+    elas_b200_default_params(p, ELAS_B200_ROBOTICS);     // stereothread.cpp:76-80
+    p->postprocess_only_left = 1;
+    p->filter_adaptive_mean = 1;
+    p->support_texture = 30;
+}
+
+int32_t elas_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* elas_b200_version(void) { return "elas_b200 0.1 (sm_100a; CUDA kernels only, no CPU fallback)"; }
+
+int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                         int32_t width, int32_t height, int32_t n_slots)
+{
+    if (!out || !p || width < 16 || n_slots < 1 || n_slots > 64) return ELAS_B200_E_BAD_ARG;
+    *out = nullptr;
+    if (p->disp_max < 0 || p->disp_max > 4095 || p->grid_size < 1 || p->candidate_stepsize < 1) return ELAS_B200_E_BAD_ARG;
+    // createGrid's diffusion walks from grid row 2 (elas.cpp:732-748): fewer than 3 grid rows is UB there
+    if ((int)std::ceil((float)height / (float)p->grid_size) < 3) return ELAS_B200_E_UNSUPPORTED;
+    if (elas_b200_device_count() <= device || device < 0) return ELAS_B200_E_NO_DEVICE;
+    CK(cudaSetDevice(device));
+    std::unique_ptr<elas_b200_ctx> c(new elas_b200_ctx);
+    c->device = device; c->p = *p;
+    c->g = make_geom(*p, width, height);
+    c->support_cap = c->g.Wc * c->g.Hc + 6;
+    c->tri_cap = 2 * c->support_cap + 8;
+    if (matching_smem_bytes(c->g) > 200 * 1024) return ELAS_B200_E_UNSUPPORTED;
+    std::vector<int32_t> prior = make_prior(*p, c->g.dn);
+    CK(cudaMalloc(&c->d_prior, prior.size() * 4));
+    CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
+    c->launches_at_create = launches_issued();
+    for (int i = 0; i < n_slots; i++) {
+        c->slots.emplace_back(new Slot);
+        if (int32_t rc = alloc_slot(c.get(), *c->slots.back())) {
+            for (auto& s : c->slots) free_slot(*s);
+            cudaFree(c->d_prior);
+            return rc;
+        }
+    }
+    for (int i = 0; i < n_slots; i++) c->workers.emplace_back(worker_main, c.get(), i);
+    *out = c.release();
+    return ELAS_B200_OK;
+}
+
+void elas_b200_destroy(elas_b200_ctx* c)
+{
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->stopping = true;
+    }
+    c->cv_work.notify_all();
+    for (auto& t : c->workers) t.join();
+    cudaSetDevice(c->device);
+    for (auto& s : c->slots) { cudaStreamSynchronize(s->stream); free_slot(*s); }
+    cudaFree(c->d_prior);
+    cudaFree(c->d_flush);
+    delete c;
+}
+
+int32_t elas_b200_process_ctx(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, const uint8_t* I2,
+                              float* D1, float* D2, int32_t bytes_per_line)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !I1 || !I2 || !D1 || !D2 || bytes_per_line < c->g.W)
+        return ELAS_B200_E_BAD_ARG;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    CK(cudaSetDevice(c->device));
+    return run_frame(c, *c->slots[slot], I1, I2, D1, D2, bytes_per_line, false);
+}
+
+int32_t elas_b200_process_batch(elas_b200_ctx* c, int32_t n, const uint8_t* const* I1, const uint8_t* const* I2,
+                                float* const* D1, float* const* D2, int32_t bytes_per_line, int32_t* status)
+{
+    return run_batch(c, n, I1, I2, D1, D2, bytes_per_line, status, false);
+}
+
+int32_t elas_b200_process_batch_device(elas_b200_ctx* c, int32_t n, const uint8_t* const* dI1,
+                                       const uint8_t* const* dI2, float* const* dD1, float* const* dD2,
+                                       int32_t bytes_per_line, int32_t* status)
+{
+    return run_batch(c, n, dI1, dI2, dD1, dD2, bytes_per_line, status, true);
+}
+
+int32_t elas_b200_process(const elas_b200_params* p, const uint8_t* I1, const uint8_t* I2,
+                          float* D1, float* D2, const int32_t dims[3])
+{
+    if (!p || !I1 || !I2 || !D1 || !D2 || !dims) return ELAS_B200_E_BAD_ARG;
+    int device = 0;
+    if (elas_b200_device_count() < 1) return ELAS_B200_E_NO_DEVICE;
+    if (const char* e = std::getenv("ELAS_B200_DEVICE")) device = std::atoi(e);
+    CacheKey key;
+    std::memset(&key, 0, sizeof key);
+    key.device = device; key.W = dims[0]; key.H = dims[1]; key.p = *p;
+    elas_b200_ctx* c = nullptr;
+    std::lock_guard<std::mutex> lk(g_cache_mu);          // one call at a time, from any thread
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+        if (int32_t rc = elas_b200_create(&c, device, p, dims[0], dims[1], 1)) return rc;
+        g_cache[key] = c;
+    } else c = it->second;
+    return elas_b200_process_ctx(c, 0, I1, I2, D1, D2, dims[2]);
+}
+
+int32_t elas_b200_stage_capture(elas_b200_ctx* c, int32_t slot, int32_t enable)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return ELAS_B200_E_BAD_ARG;
+    c->slots[slot]->capture = enable != 0;
+    if (!enable) c->slots[slot]->stages.clear();
+    return ELAS_B200_OK;
+}
+
+static const std::vector<uint8_t>* find_stage(elas_b200_ctx* c, int32_t slot, const char* name, std::vector<uint8_t>& scratch)
+{
+    if (!c || !name || slot < 0 || slot >= (int)c->slots.size()) return nullptr;
+    Slot& s = *c->slots[slot];
+    const std::string n(name);
+    if (n == "grid1" || n == "grid2") {
+        auto it = s.stages.find(n + "_bits");
+        if (it == s.stages.end()) return nullptr;
+        scratch = expand_grid(c->g, it->second);
+        return &scratch;
+    }
+    auto it = s.stages.find(n);
+    return it == s.stages.end() ? nullptr : &it->second;
+}
+
+int64_t elas_b200_stage_bytes(elas_b200_ctx* c, int32_t slot, const char* name)
+{
+    std::vector<uint8_t> scratch;
+    const std::vector<uint8_t>* v = find_stage(c, slot, name, scratch);
+    return v ? (int64_t)v->size() : -1;
+}
+
+int32_t elas_b200_stage_read(elas_b200_ctx* c, int32_t slot, const char* name, void* dst, int64_t cap)
+{
+    std::vector<uint8_t> scratch;
+    const std::vector<uint8_t>* v = find_stage(c, slot, name, scratch);
+    if (!v) return ELAS_B200_E_NO_STAGE;
+    if ((int64_t)v->size() > cap || !dst) return ELAS_B200_E_BAD_ARG;
+    std::memcpy(dst, v->data(), v->size());
+    return ELAS_B200_OK;
+}
+
+int32_t elas_b200_host_stage(const elas_b200_params* p, int32_t width, int32_t height, int16_t* dcan,
+                             int32_t* support, int32_t support_cap, int32_t* tri1, int32_t* tri2,
+                             float* planes1, float* planes2, int32_t tri_cap, int32_t n_out[3])
+{
+    if (!p || !dcan || !support || !tri1 || !tri2 || !planes1 || !planes2 || !n_out) return ELAS_B200_E_BAD_ARG;
+    const FrameGeom g = make_geom(*p, width, height);
+    HostStage hs;
+    const int n = hs.run(g, *p, dcan, false);
+    n_out[0] = n; n_out[1] = (int)hs.tri[0].size() / 3; n_out[2] = (int)hs.tri[1].size() / 3;
+    if (n > support_cap || n_out[1] > tri_cap || n_out[2] > tri_cap) return ELAS_B200_E_BAD_ARG;
+    std::memcpy(support, hs.support.data(), hs.support.size() * 4);
+    if (n < 3) return ELAS_B200_E_FEW_SUPPORT;
+    std::memcpy(tri1, hs.tri[0].data(), hs.tri[0].size() * 4);
+    std::memcpy(tri2, hs.tri[1].data(), hs.tri[1].size() * 4);
+    std::memcpy(planes1, hs.planes[0].data(), hs.planes[0].size() * 4);
+    std::memcpy(planes2, hs.planes[1].data(), hs.planes[1].size() * 4);
+    return ELAS_B200_OK;
+}
+
+int64_t elas_b200_launch_count(elas_b200_ctx* c)
+{
+    return c ? launches_issued() - c->launches_at_create : launches_issued();
+}
+
+int32_t elas_b200_stage_timing(elas_b200_ctx* c, int32_t enable)
+{
+    if (!c) return ELAS_B200_E_BAD_ARG;
+    c->timing = enable != 0;
+    return ELAS_B200_OK;
+}
+
+int32_t elas_b200_stage_times(elas_b200_ctx* c, int32_t slot, const char** names_out, float* ms_out, int32_t cap)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size()) return ELAS_B200_E_BAD_ARG;
+    Slot& s = *c->slots[slot];
+    int n = 0;
+    for (auto& e : s.timer.last) {
+        if (n >= cap) break;
+        // names point into the slot's mark table, stable for the life of the context
+        for (auto& m : s.timer.marks) if (m.first == e.first) names_out[n] = m.first.c_str();
+        ms_out[n] = e.second;
+        n++;
+    }
+    return n;
+}
+
+float elas_b200_time_matching(elas_b200_ctx* c, int32_t slot, int32_t iters, int32_t flush_l2)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || iters < 1) return -1.f;
+    Slot& s = *c->slots[slot];
+    if (!s.tables_valid) return -1.f;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1.f;
+    if (flush_l2 && !c->d_flush) {
+        c->flush_bytes = (size_t)512 << 20;       // 4x the 126 MB L2
+        if (cudaMalloc(&c->d_flush, c->flush_bytes) != cudaSuccess) return -1.f;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double total = 0;
+    for (int i = 0; i < iters; i++) {
+        if (flush_l2) cudaMemsetAsync(c->d_flush, i & 0xff, c->flush_bytes, s.stream);
+        cudaEventRecord(e0, s.stream);
+        launch_matching(c->g, c->p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
+                        s.d_grid[0], s.d_grid[1], c->d_prior, s.d_raw[0], s.d_raw[1], s.stream);
+        cudaEventRecord(e1, s.stream);
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { total = -1; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return total < 0 ? -1.f : (float)(total / iters);
+}
+
+}  // extern "C"

@@ -1,0 +1,573 @@
+// Host middle stage: lattice filters, support list, Triangle-compatible Delaunay, disparity planes,
+// raster records.  See host_stage.h.  Compiled with -ffp-contract=off: the double/float expressions
+// must round exactly as the reference's x86-64 SSE code does.
+#include "host_stage.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace elasb {
+
+// =============================================================================================
+// Triangulator: divide-and-conquer Delaunay with alternating cuts, Triangle-compatible.
+//
+// Structure (triangle.cpp:5638-6217): triangles live in a pool in allocation order; each has three
+// neighbour links (triangle index * 4 + orientation) and three vertices, vertex -1 being the ghost
+// vertex of the "bounding" triangles that surround the hull.  An oriented triangle (t, o) names the
+// edge org->dest with apex opposite.  Merging two hulls converts bounding triangles into real ones
+// and vice versa in place, which is what fixes the output ORDER; tie-breaks are the strict
+// comparisons of mergehulls.  The predicates are exact integer determinants (the reference's
+// adaptive float predicates return exact signs; ELAS coordinates are small integers).
+// =============================================================================================
+
+Triangulator::OTri Triangulator::make()
+{
+    const int t = ntri_++;
+    for (int i = 0; i < 3; i++) { nbr_[3 * t + i] = -1; vtx_[3 * t + i] = -1; }
+    return {t, 0};
+}
+
+int Triangulator::ccw(int a, int b, int c) const
+{
+    const int64_t l = (int64_t)(x_[a] - x_[c]) * (y_[b] - y_[c]);
+    const int64_t r = (int64_t)(y_[a] - y_[c]) * (x_[b] - x_[c]);
+    return (l > r) - (l < r);
+}
+
+int Triangulator::incircle(int a, int b, int c, int d) const
+{
+    const int64_t adx = x_[a] - x_[d], ady = y_[a] - y_[d];
+    const int64_t bdx = x_[b] - x_[d], bdy = y_[b] - y_[d];
+    const int64_t cdx = x_[c] - x_[d], cdy = y_[c] - y_[d];
+    const __int128 det = (__int128)(adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
+                         (__int128)(bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
+                         (__int128)(cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
+    return (det > 0) - (det < 0);
+}
+
+int Triangulator::random(unsigned choices)              // triangle.cpp:4045-4049
+{
+    seed_ = (seed_ * 1366u + 150889u) % 714025u;
+    return (int)(seed_ / (714025u / choices + 1));
+}
+
+bool Triangulator::before(int a, int b, int axis) const
+{
+    const int32_t a1 = axis ? y_[a] : x_[a], a2 = axis ? x_[a] : y_[a];
+    const int32_t b1 = axis ? y_[b] : x_[b], b2 = axis ? x_[b] : y_[b];
+    return a1 < b1 || (a1 == b1 && a2 < b2);
+}
+
+void Triangulator::sort(int* s, int n)                   // vertexsort, triangle.cpp:5446-5499
+{
+    if (n == 2) {
+        if (before(s[1], s[0], 0)) std::swap(s[0], s[1]);
+        return;
+    }
+    const int pivot = s[random((unsigned)n)];
+    int left = -1, right = n;
+    while (left < right) {
+        do { left++; } while (left <= right && before(s[left], pivot, 0));
+        do { right--; } while (left <= right && before(pivot, s[right], 0));
+        if (left < right) std::swap(s[left], s[right]);
+    }
+    if (left > 1) sort(s, left);
+    if (right < n - 2) sort(s + right + 1, n - right - 1);
+}
+
+void Triangulator::median(int* s, int n, int med, int axis)   // vertexmedian, :5513-5569
+{
+    if (n == 2) {
+        if (before(s[1], s[0], axis)) std::swap(s[0], s[1]);
+        return;
+    }
+    const int pivot = s[random((unsigned)n)];
+    int left = -1, right = n;
+    while (left < right) {
+        do { left++; } while (left <= right && before(s[left], pivot, axis));
+        do { right--; } while (left <= right && before(pivot, s[right], axis));
+        if (left < right) std::swap(s[left], s[right]);
+    }
+    if (left > med) median(s, left, med, axis);
+    if (right < med - 1) median(s + right + 1, n - right - 1, med - right - 1, axis);
+}
+
+void Triangulator::alternate(int* s, int n, int axis)     // alternateaxes, :5582-5601
+{
+    const int divider = n >> 1;
+    if (n <= 3) axis = 0;
+    median(s, n, divider, axis);
+    if (n - divider >= 2) {
+        if (divider >= 2) alternate(s, divider, 1 - axis);
+        alternate(s + divider, n - divider, 1 - axis);
+    }
+}
+
+void Triangulator::merge(OTri& farleft, OTri& innerleft, OTri& innerright, OTri& farright, int axis)
+{
+    // mergehulls, triangle.cpp:5638-5934
+    int ild = dest(innerleft), ila = apex(innerleft);
+    int iro = org(innerright), ira = apex(innerright);
+
+    if (axis == 1) {
+        // horizontal cut: re-aim the four hull handles at the bottom-/top-most vertices (:5666-5704)
+        int flp = org(farleft), fla = apex(farleft);
+        int frp = dest(farright);
+        while (y_[fla] < y_[flp]) {
+            farleft = sym(lnext(farleft));
+            flp = fla;
+            fla = apex(farleft);
+        }
+        OTri check = sym(innerleft);
+        int cv = apex(check);
+        while (y_[cv] > y_[ild]) {
+            innerleft = lnext(check);
+            ila = ild;
+            ild = cv;
+            check = sym(innerleft);
+            cv = apex(check);
+        }
+        while (y_[ira] < y_[iro]) {
+            innerright = sym(lnext(innerright));
+            iro = ira;
+            ira = apex(innerright);
+        }
+        check = sym(farright);
+        cv = apex(check);
+        while (y_[cv] > y_[frp]) {
+            farright = lnext(check);
+            frp = cv;
+            check = sym(farright);
+            cv = apex(check);
+        }
+    }
+
+    // lower common tangent (:5706-5726)
+    for (bool changed = true; changed;) {
+        changed = false;
+        if (ccw(ild, ila, iro) > 0) {
+            innerleft = sym(lprev(innerleft));
+            ild = ila;
+            ila = apex(innerleft);
+            changed = true;
+        }
+        if (ccw(ira, iro, ild) > 0) {
+            innerright = sym(lnext(innerright));
+            iro = ira;
+            ira = apex(innerright);
+            changed = true;
+        }
+    }
+
+    OTri leftcand = sym(innerleft), rightcand = sym(innerright);
+    OTri base = make();                                  // bottom bounding triangle (:5731-5738)
+    bond(base, innerleft);
+    base = lnext(base);
+    bond(base, innerright);
+    base = lnext(base);
+    set_org(base, iro);
+    set_dest(base, ild);
+    if (ild == org(farleft)) farleft = lnext(base);      // :5745-5752
+    if (iro == dest(farright)) farright = lprev(base);
+
+    int lowerleft = ild, lowerright = iro;
+    int upperleft = apex(leftcand), upperright = apex(rightcand);
+
+    for (;;) {
+        const bool leftdone = ccw(upperleft, lowerleft, lowerright) <= 0;     // :5765-5768
+        const bool rightdone = ccw(upperright, lowerleft, lowerright) <= 0;
+        if (leftdone && rightdone) {
+            OTri top = make();                           // top bounding triangle (:5771-5780)
+            set_org(top, lowerleft);
+            set_dest(top, lowerright);
+            bond(top, base);
+            top = lnext(top);
+            bond(top, rightcand);
+            top = lnext(top);
+            bond(top, leftcand);
+            if (axis == 1) {
+                // restore the handles to the left-/right-most vertices (:5786-5809)
+                int flp = org(farleft);
+                int frp = dest(farright), fra = apex(farright);
+                OTri check = sym(farleft);
+                int cv = apex(check);
+                while (x_[cv] < x_[flp]) {
+                    farleft = lprev(check);
+                    flp = cv;
+                    check = sym(farleft);
+                    cv = apex(check);
+                }
+                while (x_[fra] > x_[frp]) {
+                    farright = sym(lprev(farright));
+                    frp = fra;
+                    fra = apex(farright);
+                }
+            }
+            return;
+        }
+        if (!leftdone) {
+            // flip away left-hull edges that are not Delaunay w.r.t. the knitting edge (:5813-5859)
+            OTri next = sym(lprev(leftcand));
+            int nextapex = apex(next);
+            if (nextapex >= 0) {
+                bool bad = incircle(lowerleft, lowerright, upperleft, nextapex) > 0;
+                while (bad) {
+                    next = lnext(next);
+                    const OTri topcasing = sym(next);
+                    next = lnext(next);
+                    const OTri sidecasing = sym(next);
+                    bond(next, topcasing);
+                    bond(leftcand, sidecasing);
+                    leftcand = lnext(leftcand);
+                    const OTri outercasing = sym(leftcand);
+                    next = lprev(next);
+                    bond(next, outercasing);
+                    set_org(leftcand, lowerleft);
+                    set_dest(leftcand, -1);
+                    set_apex(leftcand, nextapex);
+                    set_org(next, -1);
+                    set_dest(next, upperleft);
+                    set_apex(next, nextapex);
+                    upperleft = nextapex;
+                    next = sidecasing;
+                    nextapex = apex(next);
+                    bad = nextapex >= 0 && incircle(lowerleft, lowerright, upperleft, nextapex) > 0;
+                }
+            }
+        }
+        if (!rightdone) {
+            // same on the right hull (:5861-5907)
+            OTri next = sym(lnext(rightcand));
+            int nextapex = apex(next);
+            if (nextapex >= 0) {
+                bool bad = incircle(lowerleft, lowerright, upperright, nextapex) > 0;
+                while (bad) {
+                    next = lprev(next);
+                    const OTri topcasing = sym(next);
+                    next = lprev(next);
+                    const OTri sidecasing = sym(next);
+                    bond(next, topcasing);
+                    bond(rightcand, sidecasing);
+                    rightcand = lprev(rightcand);
+                    const OTri outercasing = sym(rightcand);
+                    next = lnext(next);
+                    bond(next, outercasing);
+                    set_org(rightcand, -1);
+                    set_dest(rightcand, lowerright);
+                    set_apex(rightcand, nextapex);
+                    set_org(next, upperright);
+                    set_dest(next, -1);
+                    set_apex(next, nextapex);
+                    upperright = nextapex;
+                    next = sidecasing;
+                    nextapex = apex(next);
+                    bad = nextapex >= 0 && incircle(lowerleft, lowerright, upperright, nextapex) > 0;
+                }
+            }
+        }
+        // choose the next tooth; on co-circular quads the LEFT candidate wins (:5908-5910)
+        if (leftdone || (!rightdone && incircle(upperleft, lowerleft, lowerright, upperright) > 0)) {
+            bond(base, rightcand);
+            base = lprev(rightcand);
+            set_dest(base, lowerleft);
+            lowerright = upperright;
+            rightcand = sym(base);
+            upperright = apex(rightcand);
+        } else {
+            bond(base, leftcand);
+            base = lnext(leftcand);
+            set_org(base, lowerright);
+            lowerleft = upperleft;
+            leftcand = sym(base);
+            upperleft = apex(leftcand);
+        }
+    }
+}
+
+void Triangulator::recurse(int* s, int n, int axis, OTri& farleft, OTri& farright)
+{
+    // divconqrecurse, triangle.cpp:5953-6103
+    if (n == 2) {
+        farleft = make();
+        set_org(farleft, s[0]); set_dest(farleft, s[1]);
+        farright = make();
+        set_org(farright, s[1]); set_dest(farright, s[0]);
+        bond(farleft, farright);
+        farleft = lprev(farleft); farright = lnext(farright);
+        bond(farleft, farright);
+        farleft = lprev(farleft); farright = lnext(farright);
+        bond(farleft, farright);
+        farleft = lprev(farright);
+        return;
+    }
+    if (n == 3) {
+        OTri mid = make(), t1 = make(), t2 = make(), t3 = make();
+        const int area = ccw(s[0], s[1], s[2]);
+        if (area == 0) {
+            set_org(mid, s[0]); set_dest(mid, s[1]);
+            set_org(t1, s[1]);  set_dest(t1, s[0]);
+            set_org(t2, s[2]);  set_dest(t2, s[1]);
+            set_org(t3, s[1]);  set_dest(t3, s[2]);
+            bond(mid, t1); bond(t2, t3);
+            mid = lnext(mid); t1 = lprev(t1); t2 = lnext(t2); t3 = lprev(t3);
+            bond(mid, t3); bond(t1, t2);
+            mid = lnext(mid); t1 = lprev(t1); t2 = lnext(t2); t3 = lprev(t3);
+            bond(mid, t1); bond(t2, t3);
+            farleft = t1;
+            farright = t2;
+        } else {
+            const int p = area > 0 ? s[1] : s[2], q = area > 0 ? s[2] : s[1];
+            set_org(mid, s[0]); set_dest(t1, s[0]); set_org(t3, s[0]);
+            set_dest(mid, p);   set_org(t1, p);     set_dest(t2, p);
+            set_apex(mid, q);   set_org(t2, q);     set_dest(t3, q);
+            bond(mid, t1);
+            mid = lnext(mid);
+            bond(mid, t2);
+            mid = lnext(mid);
+            bond(mid, t3);
+            t1 = lprev(t1); t2 = lnext(t2);
+            bond(t1, t2);
+            t1 = lprev(t1); t3 = lprev(t3);
+            bond(t1, t3);
+            t2 = lnext(t2); t3 = lprev(t3);
+            bond(t2, t3);
+            farleft = t1;
+            farright = area > 0 ? t2 : lnext(farleft);
+        }
+        return;
+    }
+    const int divider = n >> 1;
+    OTri innerleft, innerright;
+    recurse(s, divider, 1 - axis, farleft, innerleft);
+    recurse(s + divider, n - divider, 1 - axis, innerright, farright);
+    merge(farleft, innerleft, innerright, farright, axis);
+}
+
+void Triangulator::run(const int32_t* x, const int32_t* y, int n, std::vector<int32_t>& out)
+{
+    out.clear();
+    if (n < 2) return;
+    x_ = x; y_ = y; seed_ = 1; ntri_ = 0;                 // randomseed reset per call, triangle.cpp:4030
+    const size_t cap = 3 * (size_t)(3 * n + 8);
+    if (nbr_.size() < cap) { nbr_.resize(cap); vtx_.resize(cap); }
+    order_.resize(n);
+    int* s = order_.data();
+    for (int i = 0; i < n; i++) s[i] = i;
+    sort(s, n);                                           // :6178
+    int m = 0;                                            // duplicates: keep the first (:6180-6196)
+    for (int j = 1; j < n; j++)
+        if (!(x[s[m]] == x[s[j]] && y[s[m]] == y[s[j]])) s[++m] = s[j];
+    m++;
+    const int divider = m >> 1;                           // :6197-6206
+    if (m - divider >= 2) {
+        if (divider >= 2) alternate(s, divider, 1);
+        alternate(s + divider, m - divider, 1);
+    }
+    if (m < 2) return;
+    OTri hullleft, hullright;
+    recurse(s, m, 0, hullleft, hullright);                // :6213
+    // removeghosts (:6105-6148) frees exactly the triangles holding the ghost vertex; writeelements
+    // (:7834-7853) then walks the pool in allocation order, corners (org, dest, apex) at orientation 0
+    out.reserve((size_t)ntri_ * 3);
+    for (int t = 0; t < ntri_; t++) {
+        const int a = vtx_[3 * t + 1], b = vtx_[3 * t + 2], c = vtx_[3 * t];
+        if (a < 0 || b < 0 || c < 0) continue;
+        out.push_back(a); out.push_back(b); out.push_back(c);
+    }
+}
+
+// =============================================================================================
+// lattice filters, planes, raster records
+// =============================================================================================
+namespace {
+
+// removeInconsistentSupportPoints, elas.cpp:174-209 (in place, u outer / v inner: every decision
+// sees the invalidations made before it)
+void remove_inconsistent(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
+{
+    const int win = p.incon_window_size;
+    for (int u = 0; u < Wc; u++)
+        for (int v = 0; v < Hc; v++) {
+            const int d = D[v * Wc + u];
+            if (d < 0) continue;
+            int support = 0;
+            const int u_lo = std::max(u - win, 0), u_hi = std::min(u + win, Wc - 1);
+            const int v_lo = std::max(v - win, 0), v_hi = std::min(v + win, Hc - 1);
+            for (int v2 = v_lo; v2 <= v_hi; v2++) {
+                const int16_t* row = D + v2 * Wc;
+                for (int u2 = u_lo; u2 <= u_hi; u2++) {
+                    const int d2 = row[u2];
+                    support += d2 >= 0 && std::abs(d - d2) <= p.incon_threshold;
+                }
+            }
+            if (support < p.incon_min_support) D[v * Wc + u] = -1;
+        }
+}
+
+// removeRedundantSupportPoints, elas.cpp:213-279 (in place)
+void remove_redundant(int16_t* D, int Wc, int Hc, int max_dist, int thresh, bool vertical)
+{
+    const int du = vertical ? 0 : 1, dv = vertical ? 1 : 0;
+    for (int u = 0; u < Wc; u++)
+        for (int v = 0; v < Hc; v++) {
+            const int d = D[v * Wc + u];
+            if (d < 0) continue;
+            bool redundant = true;
+            for (int dir = -1; dir <= 1 && redundant; dir += 2) {
+                bool support = false;
+                int u2 = u, v2 = v;
+                for (int j = 0; j < max_dist; j++) {
+                    u2 += dir * du; v2 += dir * dv;
+                    if (u2 < 0 || v2 < 0 || u2 >= Wc || v2 >= Hc) break;
+                    const int d2 = D[v2 * Wc + u2];
+                    if (d2 >= 0 && std::abs(d - d2) <= thresh) { support = true; break; }
+                }
+                if (!support) redundant = false;
+            }
+            if (redundant) D[v * Wc + u] = -1;
+        }
+}
+
+// addCornerSupportPoints, elas.cpp:283-318
+void add_corners(int W, int H, std::vector<int32_t>& sup)
+{
+    const int n = (int)sup.size() / 3;
+    int32_t b[6][3] = {{0, 0, 0}, {0, H - 1, 0}, {W - 1, 0, 0}, {W - 1, H - 1, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < 4; i++) {
+        int best = 10000000;
+        for (int j = 0; j < n; j++) {
+            const int du = b[i][0] - sup[3 * j], dv = b[i][1] - sup[3 * j + 1];
+            const int dist = du * du + dv * dv;
+            if (dist < best) { best = dist; b[i][2] = sup[3 * j + 2]; }
+        }
+    }
+    for (int k = 0; k < 2; k++) { b[4 + k][0] = b[2 + k][0] + b[2 + k][2]; b[4 + k][1] = b[2 + k][1]; b[4 + k][2] = b[2 + k][2]; }
+    for (auto& r : b) sup.insert(sup.end(), r, r + 3);
+}
+
+// Matrix::solve for a 3x3 system with one right-hand side (matrix.cpp:414-502): Gauss-Jordan, full
+// pivoting, double precision; false when a pivot is below 1e-20.
+bool solve3(double A[3][3], double b[3])
+{
+    int ipiv[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+        double big = 0.0;
+        int irow = 0, icol = 0;
+        for (int j = 0; j < 3; j++)
+            if (ipiv[j] != 1)
+                for (int k = 0; k < 3; k++)
+                    if (ipiv[k] == 0 && std::fabs(A[j][k]) >= big) { big = std::fabs(A[j][k]); irow = j; icol = k; }
+        ++ipiv[icol];
+        if (irow != icol) {
+            for (int l = 0; l < 3; l++) std::swap(A[irow][l], A[icol][l]);
+            std::swap(b[irow], b[icol]);
+        }
+        if (std::fabs(A[icol][icol]) < 1e-20) return false;
+        const double pivinv = 1.0 / A[icol][icol];
+        A[icol][icol] = 1.0;
+        for (int l = 0; l < 3; l++) A[icol][l] *= pivinv;
+        b[icol] *= pivinv;
+        for (int ll = 0; ll < 3; ll++)
+            if (ll != icol) {
+                const double dum = A[ll][icol];
+                A[ll][icol] = 0.0;
+                for (int l = 0; l < 3; l++) A[ll][l] -= A[icol][l] * dum;
+                b[ll] -= b[icol] * dum;
+            }
+    }
+    return true;
+}
+
+// computeDisparityPlanes, elas.cpp:605-680
+void disparity_planes(const std::vector<int32_t>& sup, const std::vector<int32_t>& tri, std::vector<float>& planes)
+{
+    const size_t nt = tri.size() / 3;
+    planes.resize(nt * 6);
+    for (size_t i = 0; i < nt; i++)
+        for (int k = 0; k < 2; k++) {
+            double A[3][3], b[3];
+            for (int c = 0; c < 3; c++) {
+                const int32_t* s = &sup[3 * (size_t)tri[3 * i + c]];
+                A[c][0] = k ? s[0] - s[2] : s[0];
+                A[c][1] = s[1];
+                A[c][2] = 1;
+                b[c] = s[2];
+            }
+            float* o = &planes[6 * i + 3 * k];
+            if (solve3(A, b)) { o[0] = (float)b[0]; o[1] = (float)b[1]; o[2] = (float)b[2]; }
+            else o[0] = o[1] = o[2] = 0.f;
+        }
+}
+
+// per-triangle set-up of computeDisparity, elas.cpp:1006-1072
+void raster_records(const std::vector<int32_t>& sup, const std::vector<int32_t>& tri,
+                    const std::vector<float>& planes, int right_image, std::vector<TriRaster>& out)
+{
+    const size_t nt = tri.size() / 3;
+    out.resize(nt);
+    for (size_t i = 0; i < nt; i++) {
+        const float* pl = &planes[6 * i];
+        TriRaster r{};
+        const float pd = right_image ? pl[0] : pl[3];
+        r.pa = right_image ? pl[3] : pl[0];
+        r.pb = right_image ? pl[4] : pl[1];
+        r.pc = right_image ? pl[5] : pl[2];
+        float tu[3], tv[3];
+        for (int k = 0; k < 3; k++) {
+            const int32_t* s = &sup[3 * (size_t)tri[3 * i + k]];
+            tu[k] = right_image ? (float)(s[0] - s[2]) : (float)s[0];
+            tv[k] = (float)s[1];
+        }
+        for (int j = 0; j < 3; j++)                       // :1043-1053
+            for (int k = 0; k < j; k++)
+                if (tu[k] > tu[j]) { std::swap(tu[j], tu[k]); std::swap(tv[j], tv[k]); }
+        const float Au = tu[0], Av = tv[0], Bu = tu[1], Bv = tv[1], Cu = tu[2], Cv = tv[2];
+        float ABa = 0, ACa = 0, BCa = 0;                  // :1061-1067
+        if ((int32_t)Au != (int32_t)Bu) ABa = (Av - Bv) / (Au - Bu);
+        if ((int32_t)Au != (int32_t)Cu) ACa = (Av - Cv) / (Au - Cu);
+        if ((int32_t)Bu != (int32_t)Cu) BCa = (Bv - Cv) / (Bu - Cu);
+        r.ABa = ABa; r.ACa = ACa; r.BCa = BCa;
+        r.ABb = Av - ABa * Au;
+        r.ACb = Av - ACa * Au;
+        r.BCb = Bv - BCa * Bu;
+        r.uA = (int32_t)Au; r.uB = (int32_t)Bu; r.uC = (int32_t)Cu;
+        r.valid = std::fabs(r.pa) < 0.7 && std::fabs(pd) < 0.7;   // :1072 (float |.| compared in double)
+        out[i] = r;
+    }
+}
+
+}  // namespace
+
+int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages)
+{
+    remove_inconsistent(p, dcan, g.Wc, g.Hc);                     // elas.cpp:496
+    if (keep_stages) dcan_incon.assign(dcan, dcan + (size_t)g.Wc * g.Hc);
+    remove_redundant(dcan, g.Wc, g.Hc, 5, 1, true);               // :501
+    remove_redundant(dcan, g.Wc, g.Hc, 5, 1, false);              // :502
+
+    support.clear();
+    for (int uc = 1; uc < g.Wc; uc++)                             // :505-517, u outer / v inner
+        for (int vc = 1; vc < g.Hc; vc++) {
+            const int d = dcan[vc * g.Wc + uc];
+            if (d >= 0) { support.push_back(uc * g.step); support.push_back(vc * g.step); support.push_back(d); }
+        }
+    if (p.add_corners) add_corners(g.W, g.H, support);            // :520-523
+    n_support = (int)support.size() / 3;
+    for (int k = 0; k < 2; k++) { tri[k].clear(); planes[k].clear(); raster[k].clear(); }
+    if (n_support < 3) return n_support;                          // :69-75
+
+    px_.resize(n_support); py_.resize(n_support);
+    for (int k = 0; k < 2; k++) {                                 // :80-81, :534-559
+        for (int i = 0; i < n_support; i++) {
+            px_[i] = k ? support[3 * i] - support[3 * i + 2] : support[3 * i];
+            py_[i] = support[3 * i + 1];
+        }
+        delaunay_.run(px_.data(), py_.data(), n_support, tri[k]);
+        disparity_planes(support, tri[k], planes[k]);             // :87-88
+        raster_records(support, tri[k], planes[k], k, raster[k]);
+    }
+    return n_support;
+}
+
+}  // namespace elasb

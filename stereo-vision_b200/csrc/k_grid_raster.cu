@@ -1,0 +1,125 @@
+// K6: candidate grid (elas.cpp:684-780) and the triangle-id maps that replace the reference's
+// per-triangle scan conversion (elas.cpp:1003-1115).
+//
+// Grid layout in HBM: the reference stores, per 20x20-pixel cell, a count and an ascending list of
+// candidate disparities as int32[disp_max+2] (1028 B per cell at disp_max 255).  The same set is
+// kept here as a bitmask of disp_max+1 bits per cell (32 B): bit d set <=> d is in the list.  The
+// ascending list order the matching kernel needs is the order of the set bits.  The expansion back to
+// the reference layout (for parity checks) is done on the host by the stage-dump hook.
+#include "common.cuh"
+
+namespace elasb {
+namespace {
+
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// elas.cpp:697-727: every support point marks d-1..d+1 in its cell, for the left image at
+// (u/grid_size, v/grid_size) and for the right image at (floor((u-d)/grid_size), v/grid_size).
+// scratch = two bitmask planes [2][gh*gw][gwords], zeroed before this kernel.
+__global__ void k_grid_scatter(FrameGeom g, elas_b200_params p, const int32_t* __restrict__ support,
+                               int n, uint32_t* __restrict__ scratch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int u = support[3 * i], v = support[3 * i + 1], d = support[3 * i + 2];
+    const int y = floor_div(v, p.grid_size);
+    const int cells = g.gw * g.gh;
+#pragma unroll
+    for (int img = 0; img < 2; img++) {
+        const int x = img ? floor_div(u - d, p.grid_size) : u / p.grid_size;     // :712, :716
+        if (x < 0 || x >= g.gw || y < 0 || y >= g.gh) continue;                   // :721
+        uint32_t* cell = scratch + ((size_t)img * cells + (size_t)y * g.gw + x) * g.gwords;
+        for (int dd = max(d - 1, 0); dd <= min(d + 1, p.disp_max); dd++)          // :703-707
+            atomicOr(cell + (dd >> 5), 1u << (dd & 31));
+    }
+}
+
+// elas.cpp:732-751: the reference walks nine pointers over the flat temp1 array in lock-step, so a
+// cell's "3x3 neighbourhood" is the nine FLAT offsets {-gw-1,-gw,-gw+1,-1,0,1,gw-1,gw,gw+1} (it
+// wraps across row ends) and only flat cells gw+1 .. gw*gh-gw-2 are written; all others stay empty
+// (SURVEY A.7).
+__global__ void k_grid_diffuse(FrameGeom g, const uint32_t* __restrict__ scratch,
+                               uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2)
+{
+    const int cells = g.gw * g.gh;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // (cell, word)
+    if (i >= cells * g.gwords) return;
+    const int c = i / g.gwords, w = i % g.gwords;
+#pragma unroll
+    for (int img = 0; img < 2; img++) {
+        uint32_t m = 0;
+        if (c >= g.gw + 1 && c <= cells - g.gw - 2) {
+            const uint32_t* t = scratch + (size_t)img * cells * g.gwords + w;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) m |= t[(size_t)(c + dy * g.gw + dx) * g.gwords];
+        }
+        (img ? grid2 : grid1)[i] = m;
+    }
+}
+
+// Scan conversion of one triangle per warp (elas.cpp:1074-1114): lanes take the columns u of both
+// halves (A->B, B->C), v runs over the half-open range [min(v1,v2), max(v1,v2)) with
+//   v1 = (uint32_t)(AC_a*u + AC_b),  v2 = (uint32_t)(AB_a*u + AB_b)   (separate mul and add, no FMA;
+// the x86-64 conversion truncates through 64 bits, i.e. trunc toward zero for the values met here).
+// The reference lets later triangles overwrite earlier ones; atomicMax on the triangle index gives
+// the same winner (findMatch's early returns depend on the pixel only, never on the triangle).
+__global__ void __launch_bounds__(256)
+k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int nt1,
+         const TriRaster* __restrict__ tri2, int nt2, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
+{
+    const int lane = threadIdx.x & 31;
+    int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const TriRaster* tri; int32_t* map;
+    if (t < nt1) { tri = tri1 + t; map = map1; }
+    else { t -= nt1; if (t >= nt2) return; tri = tri2 + t; map = map2; }
+    const float ACa = tri->ACa, ACb = tri->ACb;
+    const int uA = tri->uA, uB = tri->uB, uC = tri->uC;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int ua = half ? uB : uA, ub = half ? uC : uB;
+        if (ua == ub) continue;                                                   // :1075, :1096
+        const float ea = half ? tri->BCa : tri->ABa, eb = half ? tri->BCb : tri->ABb;
+        for (int u = max(ua, 0) + lane; u < min(ub, g.W); u += 32) {              // :1077, :1098
+            if (subsampling && (u & 1)) continue;
+            const float fu = (float)u;
+            const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(ACa, fu), ACb));    // :1081, :1102
+            const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(ea, fu), eb));      // :1082, :1103
+            const int lo = max(min(v1, v2), 0), hi = min(max(v1, v2), g.H);
+            for (int v = lo; v < hi; v++) {
+                if (subsampling && (v & 1)) continue;
+                atomicMax(map + (size_t)v * g.W + u, t);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
+                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, cudaStream_t s)
+{
+    const size_t words = (size_t)g.gw * g.gh * g.gwords;
+    cudaMemsetAsync(scratch, 0, 2 * words * sizeof(uint32_t), s);
+    if (n_support > 0) {
+        k_grid_scatter<<<(n_support + 127) / 128, 128, 0, s>>>(g, p, support, n_support, scratch);
+        count_launch();
+    }
+    k_grid_diffuse<<<(int)((words + 255) / 256), 256, 0, s>>>(g, scratch, grid1, grid2);
+    count_launch();
+}
+
+void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
+                   const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s)
+{
+    const size_t bytes = (size_t)g.W * g.H * sizeof(int32_t);
+    cudaMemsetAsync(map1, 0xFF, bytes, s);      // -1 = not covered by any triangle
+    cudaMemsetAsync(map2, 0xFF, bytes, s);
+    const int total = nt1 + nt2;
+    if (total <= 0) return;
+    k_raster<<<(total + 7) / 8, 256, 0, s>>>(g, subsampling, tri1, nt1, tri2, nt2, map1, map2);
+    count_launch();
+}
+
+}  // namespace elasb
