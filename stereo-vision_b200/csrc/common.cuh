@@ -27,12 +27,10 @@ struct FrameGeom {
 // One triangle of one image, prepared by the host stage in the reference's own float arithmetic
 // (elas.cpp:1006-1072): edge lines v = a*u + b, integer corner columns, plane and validity.
 struct __align__(16) TriRaster {
-    float ACa, ACb, ABa, ABb;
-    float BCa, BCb, pa, pb;
-    float pc;
-    int   uA, uB, uC;       // (int32_t)A_u, (int32_t)B_u, (int32_t)C_u after the sort by u
-    int   valid;            // |plane_a| < 0.7 && |plane_d| < 0.7 (elas.cpp:1072)
-    int   pad0, pad1, pad2;
+    float ACa, ACb, ABa, ABb;                 // 16 B: edge lines A-C and A-B
+    float BCa, BCb; int uA, uB;               // 16 B: edge line B-C, (int32_t)A_u, (int32_t)B_u after the sort by u
+    float pa, pb, pc; int valid;              // 16 B: plane of this image; valid = |plane_a| < 0.7 && |plane_d| < 0.7 (elas.cpp:1072)
+    int   uC, pad0, pad1, pad2;               // 16 B: (int32_t)C_u
 };
 static_assert(sizeof(TriRaster) == 64, "TriRaster is one 64-byte record");
 
@@ -74,7 +72,7 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
                      const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
                      const uint32_t* grid2, const int32_t* prior, float* D1, float* D2, cudaStream_t s);
-size_t matching_smem_bytes(const FrameGeom& g);
+size_t matching_smem_bytes(const FrameGeom& g, int grid_size);
 // K8  left/right consistency (elas.cpp:1122-1204)
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
                      float* O1, float* O2, cudaStream_t s);

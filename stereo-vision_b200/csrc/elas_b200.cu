@@ -487,7 +487,9 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
 {
     if (!out || !p || width < 16 || n_slots < 1 || n_slots > 64) return ELAS_B200_E_BAD_ARG;
     *out = nullptr;
-    if (p->disp_max < 0 || p->disp_max > 4095 || p->grid_size < 1 || p->candidate_stepsize < 1) return ELAS_B200_E_BAD_ARG;
+    if (p->disp_max < 0 || p->disp_max > 4095 || p->disp_min > p->disp_max || p->candidate_stepsize < 1) return ELAS_B200_E_BAD_ARG;
+    // the matching kernel divides by grid_size with a 32-bit reciprocal (exact for u, grid_size < 65536)
+    if (p->grid_size < 2 || p->grid_size > 4096 || width >= 65536 || height >= 65536) return ELAS_B200_E_UNSUPPORTED;
     // createGrid's diffusion walks from grid row 2 (elas.cpp:732-748): fewer than 3 grid rows is UB there
     if ((int)std::ceil((float)height / (float)p->grid_size) < 3) return ELAS_B200_E_UNSUPPORTED;
     if (elas_b200_device_count() <= device || device < 0) return ELAS_B200_E_NO_DEVICE;
@@ -497,7 +499,7 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
     c->g = make_geom(*p, width, height);
     c->support_cap = c->g.Wc * c->g.Hc + 6;
     c->tri_cap = 2 * c->support_cap + 8;
-    if (matching_smem_bytes(c->g) > 200 * 1024) return ELAS_B200_E_UNSUPPORTED;
+    if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));

@@ -104,6 +104,62 @@ void Triangulator::alternate(int* s, int n, int axis)     // alternateaxes, :558
     }
 }
 
+// Fast path for the vertex order.  vertexsort + alternateaxes are randomised, but without duplicate
+// points every comparison is between distinct keys, so the array they produce is unique: the set
+// split at each level is fixed by the keys and the leaves (<= 3 vertices) end up sorted by x.  That
+// arrangement is built here from two counting-sorted id lists (by (x,y) and by (y,x)) with stable
+// partitions, k-d-tree style: O(n log n) sequential passes instead of ~55 unpredictable indirect
+// comparisons per vertex.  Returns false (caller falls back to the literal quicksort/quickselect,
+// whose pivot sequence decides which duplicate survives) when two points coincide.
+bool Triangulator::presorted_order(int n)
+{
+    int32_t xmin = x_[0], xmax = x_[0], ymin = y_[0], ymax = y_[0];
+    for (int i = 1; i < n; i++) {
+        xmin = std::min(xmin, x_[i]); xmax = std::max(xmax, x_[i]);
+        ymin = std::min(ymin, y_[i]); ymax = std::max(ymax, y_[i]);
+    }
+    const int64_t rx = (int64_t)xmax - xmin + 1, ry = (int64_t)ymax - ymin + 1;
+    if (rx > (1 << 22) || ry > (1 << 22)) return false;
+    sx_.resize(n); sy_.resize(n); tmp_.resize(n); side_.resize(n);
+    // stable counting sort of ids 0..n-1 by key
+    auto counting = [&](const int* in, int* out, const int32_t* key, int32_t kmin, int64_t range) {
+        count_.assign((size_t)range + 1, 0);
+        for (int i = 0; i < n; i++) count_[key[in[i]] - kmin + 1]++;
+        for (int64_t k = 0; k < range; k++) count_[k + 1] += count_[k];
+        for (int i = 0; i < n; i++) out[count_[key[in[i]] - kmin]++] = in[i];
+    };
+    int* ids = order_.data();
+    for (int i = 0; i < n; i++) ids[i] = i;
+    counting(ids, tmp_.data(), y_, ymin, ry);            // by y, then stably by x  => (x, y)
+    counting(tmp_.data(), sx_.data(), x_, xmin, rx);
+    counting(ids, tmp_.data(), x_, xmin, rx);            // by x, then stably by y  => (y, x)
+    counting(tmp_.data(), sy_.data(), y_, ymin, ry);
+    for (int i = 1; i < n; i++)
+        if (x_[sx_[i]] == x_[sx_[i - 1]] && y_[sx_[i]] == y_[sx_[i - 1]]) return false;
+    arrange(sx_.data(), sy_.data(), n, 0, ids);
+    return true;
+}
+
+// xs / ys: the same n ids sorted by (x,y) / (y,x).  Writes the alternating-cut order to out[0..n).
+void Triangulator::arrange(int* xs, int* ys, int n, int axis, int* out)
+{
+    if (n <= 3) {                                         // leaves are sorted by x (triangle.cpp:5587-5591)
+        for (int i = 0; i < n; i++) out[i] = xs[i];
+        return;
+    }
+    const int divider = n >> 1;
+    int* primary = axis ? ys : xs;
+    int* other = axis ? xs : ys;
+    for (int i = 0; i < divider; i++) side_[primary[i]] = 0;
+    for (int i = divider; i < n; i++) side_[primary[i]] = 1;
+    int* t = tmp_.data() + (other - (axis ? sx_.data() : sy_.data()));    // scratch window matching this range
+    int l = 0, r = divider;
+    for (int i = 0; i < n; i++) { const int id = other[i]; if (side_[id]) t[r++] = id; else t[l++] = id; }
+    for (int i = 0; i < n; i++) other[i] = t[i];
+    arrange(xs, ys, divider, 1 - axis, out);
+    arrange(xs + divider, ys + divider, n - divider, 1 - axis, out + divider);
+}
+
 void Triangulator::merge(OTri& farleft, OTri& innerleft, OTri& innerright, OTri& farright, int axis)
 {
     // mergehulls, triangle.cpp:5638-5934
@@ -353,16 +409,19 @@ void Triangulator::run(const int32_t* x, const int32_t* y, int n, std::vector<in
     if (nbr_.size() < cap) { nbr_.resize(cap); vtx_.resize(cap); }
     order_.resize(n);
     int* s = order_.data();
-    for (int i = 0; i < n; i++) s[i] = i;
-    sort(s, n);                                           // :6178
-    int m = 0;                                            // duplicates: keep the first (:6180-6196)
-    for (int j = 1; j < n; j++)
-        if (!(x[s[m]] == x[s[j]] && y[s[m]] == y[s[j]])) s[++m] = s[j];
-    m++;
-    const int divider = m >> 1;                           // :6197-6206
-    if (m - divider >= 2) {
-        if (divider >= 2) alternate(s, divider, 1);
-        alternate(s + divider, m - divider, 1);
+    int m = n;
+    if (!presorted_order(n)) {
+        for (int i = 0; i < n; i++) s[i] = i;
+        sort(s, n);                                       // :6178
+        m = 0;                                            // duplicates: keep the first (:6180-6196)
+        for (int j = 1; j < n; j++)
+            if (!(x[s[m]] == x[s[j]] && y[s[m]] == y[s[j]])) s[++m] = s[j];
+        m++;
+        const int divider = m >> 1;                       // :6197-6206
+        if (m - divider >= 2) {
+            if (divider >= 2) alternate(s, divider, 1);
+            alternate(s + divider, m - divider, 1);
+        }
     }
     if (m < 2) return;
     OTri hullleft, hullright;
@@ -383,26 +442,29 @@ void Triangulator::run(const int32_t* x, const int32_t* y, int n, std::vector<in
 namespace {
 
 // removeInconsistentSupportPoints, elas.cpp:174-209 (in place, u outer / v inner: every decision
-// sees the invalidations made before it)
+// sees the invalidations made before it).  The reference counts all valid neighbours within the
+// (2*win+1)^2 lattice window whose disparity differs by <= incon_threshold and invalidates the
+// point when the count is below incon_min_support; only that comparison is observable, so the
+// count stops as soon as it reaches incon_min_support (rows nearest the centre are visited first).
 void remove_inconsistent(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
 {
-    const int win = p.incon_window_size;
-    for (int u = 0; u < Wc; u++)
+    const int win = p.incon_window_size, need = p.incon_min_support, thr = p.incon_threshold;
+    for (int u = 0; u < Wc; u++) {
+        const int u_lo = std::max(u - win, 0), u_hi = std::min(u + win, Wc - 1);
         for (int v = 0; v < Hc; v++) {
             const int d = D[v * Wc + u];
             if (d < 0) continue;
+            const int lo = std::max(d - thr, 0), hi = d + thr;
             int support = 0;
-            const int u_lo = std::max(u - win, 0), u_hi = std::min(u + win, Wc - 1);
-            const int v_lo = std::max(v - win, 0), v_hi = std::min(v + win, Hc - 1);
-            for (int v2 = v_lo; v2 <= v_hi; v2++) {
+            for (int k = 0; k <= 2 * win && support < need; k++) {
+                const int v2 = v + ((k & 1) ? (k + 1) / 2 : -(k / 2));      // v, v+1, v-1, v+2, v-2, ...
+                if (v2 < 0 || v2 >= Hc) continue;
                 const int16_t* row = D + v2 * Wc;
-                for (int u2 = u_lo; u2 <= u_hi; u2++) {
-                    const int d2 = row[u2];
-                    support += d2 >= 0 && std::abs(d - d2) <= p.incon_threshold;
-                }
+                for (int u2 = u_lo; u2 <= u_hi; u2++) support += row[u2] >= lo && row[u2] <= hi;
             }
-            if (support < p.incon_min_support) D[v * Wc + u] = -1;
+            if (support < need) D[v * Wc + u] = -1;
         }
+    }
 }
 
 // removeRedundantSupportPoints, elas.cpp:213-279 (in place)

@@ -46,12 +46,15 @@ private:
     void sort(int* s, int n);
     void median(int* s, int n, int med, int axis);
     void alternate(int* s, int n, int axis);
+    bool presorted_order(int n);
+    void arrange(int* xs, int* ys, int n, int axis, int* out);
     void merge(OTri& farleft, OTri& innerleft, OTri& innerright, OTri& farright, int axis);
     void recurse(int* s, int n, int axis, OTri& farleft, OTri& farright);
 
     const int32_t* x_ = nullptr;
     const int32_t* y_ = nullptr;
-    std::vector<int> nbr_, vtx_, order_;
+    std::vector<int> nbr_, vtx_, order_, sx_, sy_, tmp_, count_;
+    std::vector<uint8_t> side_;
     int ntri_ = 0;
     uint64_t seed_ = 1;
 };

@@ -5,36 +5,38 @@
 // image.  Here the scan conversion has already produced a triangle-id map per image (k_raster), so
 // the work is a flat per-pixel pass.
 //
-// Decomposition: one CTA per (image row v, column segment).  Both matching directions of a row
-// read the SAME two descriptor rows (left image: own = desc1, other = desc2; right image: the
-// reverse), so the CTA stages the desc1 strip and the desc2 strip of row clamp(v,2,H-3)
-// (elas.cpp:834) in shared memory ONCE -- two TMA bulk copies (cp.async.bulk, contiguous
-// 16 B/pixel rows) completing on one mbarrier -- and then produces the D1 and the D2 pixels of the
-// segment from shared memory.  Every candidate SAD is an LDS.128 + 4 VABSDIFF4.  HBM sees each
-// descriptor byte about once per row (segments overlap by disp_max columns), the triangle-id maps
-// once and the two output rows once.
+// Decomposition: one CTA per (image row v, column segment of ~420 pixels).  Both matching
+// directions of a row read the SAME two descriptor rows (left image: own = desc1, other = desc2;
+// right image: the reverse), so the CTA stages the desc1 strip and the desc2 strip of row
+// clamp(v,2,H-3) (elas.cpp:834) in shared memory ONCE -- two TMA bulk copies (cp.async.bulk,
+// contiguous 16 B/pixel rows) completing on one mbarrier -- and then produces the D1 and the D2
+// pixels of the segment from shared memory.  While the copies are in flight the warps turn the
+// candidate-grid bitmasks of the ~22 cells under the segment into short ascending disparity lists in
+// shared memory.  Every candidate SAD is then an LDS.128 + 4 VABSDIFF4.  HBM sees each descriptor
+// byte about once per row (neighbouring segments overlap by disp_max columns, absorbed by L2), the
+// triangle-id maps once and the two output rows once.
 //
 // Per pixel (findMatch): candidates = the grid cell's disparities OUTSIDE the plane window in
 // ascending order (cost = SAD), then the plane window d_plane-r..d_plane+r ascending
 // (cost = SAD + prior if the triangle is valid); strict '<' keeps the first minimum (elas.cpp:790,805).
-// The grid cell is a bitmask (see k_grid_raster.cu): ascending order = ascending set bits.
 #include "common.cuh"
 
 namespace elasb {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kSingleSegMax = 1600;     // rows up to this width are one segment
-constexpr int kSegTarget = 1024;        // wider rows are cut into ~equal segments of about this size
+constexpr int kThreads = 128;
+constexpr int kSegTarget = 448;         // rows wider than this are cut into ~equal segments
+constexpr int kListCap = 48;            // candidates per cell kept as a list; fuller cells use the bitmask path
+constexpr int kPriorCap = 16;
 
 struct SegPlan { int nseg, segw; };
 
-__host__ __device__ inline SegPlan plan_segments(int W)
+inline SegPlan plan_segments(int W)
 {
     SegPlan s;
-    if (W <= kSingleSegMax) { s.nseg = 1; s.segw = W; return s; }
     s.nseg = (W + kSegTarget - 1) / kSegTarget;
     s.segw = ((W + s.nseg - 1) / s.nseg + 31) & ~31;
+    s.nseg = (W + s.segw - 1) / s.segw;
     return s;
 }
 
@@ -72,7 +74,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 struct MatchArgs {
     FrameGeom g;
     int disp_max, match_texture, grid_size, subsampling;
-    int nseg, segw;
+    int segw, max_cells;
+    uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
     const uint4* desc[2];
     const TriRaster* tri[2];
     const int32_t* map[2];
@@ -81,11 +84,32 @@ struct MatchArgs {
     float* D[2];
 };
 
+// rare path: a cell holding more than kListCap candidates is scanned from its bitmask in global memory
+__device__ __noinline__ void scan_cell_bitmask(const uint32_t* __restrict__ cell, int gwords, int dlo, int dhi,
+                                               int u, int img, int W, const uint4& own,
+                                               const uint4* __restrict__ oth_strip, int oth_lo,
+                                               int& min_val, int& min_d)
+{
+    for (int w = 0; w < gwords; w++) {
+        uint32_t m = __ldg(cell + w);
+        while (m) {
+            const int d = 32 * w + __ffs(m) - 1;
+            m &= m - 1;
+            if (d >= dlo && d <= dhi) continue;
+            const int uw = img ? u + d : u - d;
+            if (uw < 2 || uw >= W - 2) continue;
+            const int val = (int)sad16(own, oth_strip[uw - oth_lo]);
+            if (val < min_val) { min_val = val; min_d = d; }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_matching(const __grid_constant__ MatchArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_prior[kPriorCap];
 
     const FrameGeom& g = a.g;
     const int v = blockIdx.y;
@@ -94,11 +118,15 @@ k_matching(const __grid_constant__ MatchArgs a)
     // strip 0 = desc1 columns [s0lo, s0hi), strip 1 = desc2 columns [s1lo, s1hi)
     const int s0lo = x0, s0hi = min(x1 + a.disp_max, g.W);
     const int s1lo = max(x0 - a.disp_max, 0), s1hi = x1;
+    const int strip_cap = min(a.segw + a.disp_max, g.W);
     uint4* strip0 = reinterpret_cast<uint4*>(smem_raw);
-    uint4* strip1 = strip0 + (s0hi - s0lo);
+    uint4* strip1 = strip0 + strip_cap;
+    uint16_t* lists = reinterpret_cast<uint16_t*>(strip1 + strip_cap);    // [2][max_cells][kListCap]
+    int* counts = reinterpret_cast<int*>(lists + 2 * a.max_cells * kListCap);   // [2][max_cells]
 
     const int vrow = max(min(v, g.H - 3), 2);                              // elas.cpp:834
     if (threadIdx.x == 0) mbar_init(&bar, 1);
+    if (threadIdx.x < kPriorCap) s_prior[threadIdx.x] = threadIdx.x < g.dn ? __ldg(a.prior + threadIdx.x) : 0;
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t b0 = (uint32_t)(s0hi - s0lo) * 16u, b1 = (uint32_t)(s1hi - s1lo) * 16u;
@@ -107,9 +135,40 @@ k_matching(const __grid_constant__ MatchArgs a)
         tma_bulk_g2s(strip1, a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
     }
 
-    const int n = x1 - x0;
+    // candidate lists of the cells under this segment (elas.cpp:873-874), one (image, cell) per warp pass
     const int gy = v / a.grid_size;                                        // elas.cpp:867
-    const int window = 2;
+    const int c0 = x0 / a.grid_size, c1 = (x1 - 1) / a.grid_size, ncell = c1 - c0 + 1;
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int job = warp; job < 2 * ncell; job += kThreads / 32) {
+            const int img = job >= ncell, c = img ? job - ncell : job;
+            const uint32_t* cell = a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords;
+            uint16_t* list = lists + (img * a.max_cells + c) * kListCap;
+            int total = 0;
+            for (int w0 = 0; w0 < g.gwords; w0 += 32) {
+                const uint32_t m = (w0 + lane < g.gwords) ? __ldg(cell + w0 + lane) : 0u;
+                const int cnt = __popc(m);
+                int incl = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                int pos = total + incl - cnt;
+                uint32_t mm = m;
+                while (mm) {
+                    if (pos < kListCap) list[pos] = (uint16_t)(32 * (w0 + lane) + __ffs(mm) - 1);
+                    pos++;
+                    mm &= mm - 1;
+                }
+                total += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) counts[img * a.max_cells + c] = total <= kListCap ? total : -1;
+        }
+    }
+    __syncthreads();
+
+    const int n = x1 - x0;
     bool waited = false;
 
     // items 0..n-1: left image pixels, n..2n-1: right image pixels
@@ -121,48 +180,45 @@ k_matching(const __grid_constant__ MatchArgs a)
         if (!waited) { mbar_wait(&bar, 0); waited = true; }
 
         float out = (float)kInvalid;                                       // elas.cpp:977-980
-        if (t >= 0 && u >= window && u < g.W - window) {                   // elas.cpp:828
+        if (t >= 0 && u >= 2 && u < g.W - 2) {                             // elas.cpp:828
             const uint4* own_strip = img ? strip1 : strip0;
             const uint4* oth_strip = img ? strip0 : strip1;
             const int own_lo = img ? s1lo : s0lo, oth_lo = img ? s0lo : s1lo;
             const uint4 own = own_strip[u - own_lo];
             if ((int)texture16(own) >= a.match_texture) {                  // elas.cpp:851-859
-                const TriRaster* tr = a.tri[img] + t;
-                const float pa = __ldg(&tr->pa), pb = __ldg(&tr->pb), pc = __ldg(&tr->pc);
-                const int valid = __ldg(&tr->valid);
+                // plane (a,b,c) and validity of the covering triangle: one 16-byte load
+                const float4 pl = __ldg(reinterpret_cast<const float4*>(&a.tri[img][t].pa));
+                const int valid = __float_as_int(pl.w);
                 // elas.cpp:861: (int32_t)(plane_a*u + plane_b*v + plane_c), evaluated left to right
                 const int d_plane = __float2int_rz(
-                    __fadd_rn(__fadd_rn(__fmul_rn(pa, (float)u), __fmul_rn(pb, (float)v)), pc));
+                    __fadd_rn(__fadd_rn(__fmul_rn(pl.x, (float)u), __fmul_rn(pl.y, (float)v)), pl.z));
                 const int dlo = max(d_plane - g.plane_radius, 0);
                 const int dhi = min(d_plane + g.plane_radius, g.dn - 1);
-                const uint32_t* cell = a.grid[img] + ((size_t)gy * g.gw + u / a.grid_size) * g.gwords;
+                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - c0;          // u / grid_size - c0
 
                 int min_val = 10000, min_d = -1;                           // elas.cpp:878-879
                 // (i) grid candidates outside the plane window, ascending (elas.cpp:890-903, :919-932)
-                for (int w = 0; w < g.gwords; w++) {
-                    uint32_t m = __ldg(cell + w);
-                    // clear bits d in [dlo, dhi]
-                    const int lo = dlo - 32 * w, hi = dhi - 32 * w;
-                    if (hi >= 0 && lo < 32 && lo <= hi) {
-                        const uint32_t upto_hi = hi >= 31 ? 0xffffffffu : ((2u << hi) - 1u);
-                        const uint32_t below_lo = lo <= 0 ? 0u : ((1u << lo) - 1u);
-                        m &= ~(upto_hi & ~below_lo);
-                    }
-                    while (m) {
-                        const int d = 32 * w + __ffs(m) - 1;
-                        m &= m - 1;
+                const int cnt = counts[img * a.max_cells + c];
+                if (cnt >= 0) {
+                    const uint16_t* list = lists + (img * a.max_cells + c) * kListCap;
+                    for (int i = 0; i < cnt; i++) {
+                        const int d = list[i];
+                        if (d >= dlo && d <= dhi) continue;
                         const int uw = img ? u + d : u - d;
-                        if (uw < window || uw >= g.W - window) continue;
+                        if (uw < 2 || uw >= g.W - 2) continue;
                         const int val = (int)sad16(own, oth_strip[uw - oth_lo]);
                         if (val < min_val) { min_val = val; min_d = d; }
                     }
+                } else {
+                    scan_cell_bitmask(a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords, g.gwords, dlo, dhi,
+                                      u, img, g.W, own, oth_strip, oth_lo, min_val, min_d);
                 }
                 // (ii) the plane window with the prior (elas.cpp:904-913, :934-943)
                 for (int d = dlo; d <= dhi; d++) {
                     const int uw = img ? u + d : u - d;
-                    if (uw < window || uw >= g.W - window) continue;
+                    if (uw < 2 || uw >= g.W - 2) continue;
                     int val = (int)sad16(own, oth_strip[uw - oth_lo]);
-                    if (valid) val += __ldg(a.prior + abs(d - d_plane));
+                    if (valid) val += s_prior[abs(d - d_plane)];
                     if (val < min_val) { min_val = val; min_d = d; }
                 }
                 out = min_d >= 0 ? (float)min_d : -1.0f;                   // elas.cpp:947-954
@@ -174,15 +230,20 @@ k_matching(const __grid_constant__ MatchArgs a)
     if (!waited) mbar_wait(&bar, 0);     // never leave with a bulk copy in flight
 }
 
+int max_cells_per_segment(const FrameGeom& g, int grid_size, int segw) { return (segw + grid_size - 1) / grid_size + 1; }
+
+size_t smem_bytes_for(const FrameGeom& g, int grid_size)
+{
+    const SegPlan s = plan_segments(g.W);
+    const int dmax = g.dn - 1;
+    const size_t strip = (size_t)((s.segw + dmax) < g.W ? (s.segw + dmax) : g.W);
+    const size_t cells = (size_t)max_cells_per_segment(g, grid_size, s.segw);
+    return 2 * strip * 16 + 2 * cells * kListCap * 2 + 2 * cells * 4;
+}
+
 }  // namespace
 
-size_t matching_smem_bytes(const FrameGeom& g)
-{
-    SegPlan s = plan_segments(g.W);
-    const int dmax = g.dn - 1;
-    size_t l0 = (size_t)min(s.segw + dmax, g.W), l1 = (size_t)min(s.segw + dmax, g.W);
-    return (l0 + l1) * 16;
-}
+size_t matching_smem_bytes(const FrameGeom& g, int grid_size) { return smem_bytes_for(g, grid_size); }
 
 void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
@@ -190,17 +251,18 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
                      const uint32_t* grid2, const int32_t* prior, float* D1, float* D2, cudaStream_t s)
 {
     static bool attr_set = false;
-    const size_t smem = matching_smem_bytes(g);
-    if (!attr_set || smem > 48 * 1024) {
+    if (!attr_set) {
         cudaFuncSetAttribute(k_matching, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    SegPlan sp = plan_segments(g.W);
+    const SegPlan sp = plan_segments(g.W);
     MatchArgs a;
     a.g = g;
     a.disp_max = p.disp_max; a.match_texture = p.match_texture; a.grid_size = p.grid_size;
     a.subsampling = p.subsampling;
-    a.nseg = sp.nseg; a.segw = sp.segw;
+    a.segw = sp.segw;
+    a.max_cells = max_cells_per_segment(g, p.grid_size, sp.segw);
+    a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;
     a.desc[0] = desc1; a.desc[1] = desc2;
     a.tri[0] = tri1; a.tri[1] = tri2;
     a.map[0] = map1; a.map[1] = map2;
@@ -208,7 +270,7 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.prior = prior;
     a.D[0] = D1; a.D[1] = D2;
     dim3 grid(sp.nseg, g.H, 1);
-    k_matching<<<grid, kThreads, smem, s>>>(a);
+    k_matching<<<grid, kThreads, smem_bytes_for(g, p.grid_size), s>>>(a);
     count_launch();
 }
 

@@ -35,12 +35,28 @@ __global__ void k_lr_check(int Dw, int Dh, int subsampling, float lr_threshold,
 // K9  speckle removal, elas.cpp:1208-1326.  The reference flood-fills 4-connected segments in
 // which neighbouring valid pixels differ by <= speckle_sim_threshold and invalidates segments with
 // fewer than speckle_size pixels.  Segments are the connected components of a symmetric relation,
-// so the result does not depend on traversal order: union-find over the pixel lattice.
+// so the result does not depend on traversal order.  Run-based labelling:
+//   rows:   every maximal horizontal run of connected pixels becomes one union-find node (its first
+//           pixel); the other pixels of the run point at it and are never touched again
+//   merge:  vertically connected pixel pairs union their runs; a pair is skipped when its left
+//           neighbour pair already joins the same two runs
+//   count:  each run adds its length to its root once (and stops adding once the root is known to be
+//           large enough -- only "size < speckle_size" is ever asked)
+//   apply:  pixel -> run -> root -> size
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool seg_conn(float a, float b, float thr)
+{
+    return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr;                    // :1281, :1285
+}
+
 __device__ __forceinline__ int uf_find(int32_t* parent, int x)
 {
     int p = parent[x];
-    while (p != x) { x = p; p = parent[x]; }
+    while (p != x) {
+        const int gp = parent[p];
+        if (gp != p) parent[x] = gp;       // path halving; parents only ever move towards the root
+        x = p; p = gp;
+    }
     return x;
 }
 
@@ -57,38 +73,71 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
     }
 }
 
-__global__ void k_seg_init(int n, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+// one CTA per row: parent[pixel] = index of the first pixel of its run (-1 for invalid pixels)
+__global__ void __launch_bounds__(256)
+k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { parent[i] = i; size[i] = 0; }
+    __shared__ int warp_last[8];
+    __shared__ int carry_s;
+    const int v = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* row = D + (size_t)v * Dw;
+    const int base = v * Dw;
+    if (threadIdx.x == 0) carry_s = -1;
+    __syncthreads();
+    for (int u0 = 0; u0 < Dw; u0 += 256) {
+        const int u = u0 + threadIdx.x;
+        const float d = u < Dw ? row[u] : -1.f;
+        const float dl = (u > 0 && u < Dw) ? row[u - 1] : -1.f;
+        const bool valid = d >= 0.f;
+        const bool start = valid && !seg_conn(dl, d, thr);
+        const unsigned starts = __ballot_sync(0xffffffffu, start);
+        const unsigned upto = starts & (0xffffffffu >> (31 - lane));
+        int last = upto ? u0 + (warp << 5) + 31 - __clz(upto) : -1;      // most recent start in this warp
+        if (lane == 31) warp_last[warp] = last;
+        __syncthreads();
+        const int carry = carry_s;
+        if (last < 0) {
+            for (int w = warp - 1; w >= 0 && last < 0; w--) last = warp_last[w];
+            if (last < 0) last = carry;
+        }
+        if (u < Dw) { parent[base + u] = valid ? base + last : -1; size[base + u] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = last >= 0 ? last : carry;     // runs never span an invalid pixel
+        __syncthreads();
+    }
 }
 
-__global__ void k_seg_link(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
+__global__ void k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+    if (u >= Dw || v + 1 >= Dh) return;
+    const int a = v * Dw + u, b = a + Dw;
+    const float da = D[a], db = D[b];
+    if (!seg_conn(da, db, thr)) return;
+    bool a_start = true, b_start = true;
+    if (u > 0) {
+        const float la = D[a - 1], lb = D[b - 1];
+        a_start = !seg_conn(la, da, thr);
+        b_start = !seg_conn(lb, db, thr);
+        if (!a_start && !b_start && seg_conn(la, lb, thr)) return;   // the pair to the left joins the same runs
+    }
+    uf_union(parent, a_start ? a : parent[a], b_start ? b : parent[b]);
+}
+
+__global__ void k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
+                            int32_t* parent, int32_t* size)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= Dw || v >= Dh) return;
     const int a = v * Dw + u;
     const float d = D[a];
-    if (!(d >= 0.f)) return;                                                        // :1281
-    if (u + 1 < Dw) {
-        const float e = D[a + 1];
-        if (e >= 0.f && fabsf(__fsub_rn(d, e)) <= thr) uf_union(parent, a, a + 1);  // :1285
-    }
-    if (v + 1 < Dh) {
-        const float e = D[a + Dw];
-        if (e >= 0.f && fabsf(__fsub_rn(d, e)) <= thr) uf_union(parent, a, a + Dw);
-    }
-}
-
-__global__ void k_seg_count(int n, const float* __restrict__ D, int32_t* parent, int32_t* size)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n && D[i] >= 0.f;
-    int root = -1;
-    if (valid) { root = uf_find(parent, i); parent[i] = root; }
-    // one atomic per distinct root per warp: most of the image is a handful of large segments
-    const unsigned peers = __match_any_sync(0xffffffffu, root);
-    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(size + root, __popc(peers));
+    if (!(d >= 0.f)) return;
+    if (u + 1 < Dw && seg_conn(d, D[a + 1], thr)) return;             // not the last pixel of its run
+    const bool is_start = !(u > 0 && seg_conn(D[a - 1], d, thr));
+    const int start = is_start ? a : parent[a];
+    const int root = uf_find(parent, start);
+    parent[start] = root;                                             // every run ends up one hop from its root
+    if (__ldcg(size + root) < speckle) atomicAdd(size + root, a - start + 1);
 }
 
 __global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int32_t* __restrict__ parent,
@@ -97,8 +146,11 @@ __global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float d = D[i];
-    if (d >= 0.f) { if (size[parent[i]] < speckle) D[i] = (float)kInvalid; }          // :1309-1317
-    else if (1 < speckle) D[i] = (float)kInvalid;   // an invalid pixel is a segment of one (:1248-1250)
+    if (d >= 0.f) {
+        int root = parent[i];                      // pixel -> run start -> (usually one hop) -> root
+        for (int up = parent[root]; up != root; up = parent[root]) root = up;
+        if (size[root] < speckle) D[i] = (float)kInvalid;                              // :1309-1317
+    } else if (1 < speckle) D[i] = (float)kInvalid;   // an invalid pixel is a segment of one (:1248-1250)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,28 +206,40 @@ __device__ __forceinline__ float masked_abs(float x)
     return __uint_as_float(__float_as_uint(x) & 0x4F000000u);
 }
 
+// ((q[(0-r)&3] + q[(1-r)&3]) + q[(2-r)&3]) + q[(3-r)&3]: the reference's lane order for a ring that
+// starts r slots in, without dynamically indexed (local-memory) arrays
+__device__ __forceinline__ float ring_sum4(float q0, float q1, float q2, float q3, int r)
+{
+    switch (r & 3) {
+        case 0:  return __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), q2), q3);
+        case 1:  return __fadd_rn(__fadd_rn(__fadd_rn(q3, q0), q1), q2);
+        case 2:  return __fadd_rn(__fadd_rn(__fadd_rn(q2, q3), q0), q1);
+        default: return __fadd_rn(__fadd_rn(__fadd_rn(q1, q2), q3), q0);
+    }
+}
+
 template <int TAPS>
 __device__ __forceinline__ bool mean_window(const float* __restrict__ line, ptrdiff_t stride, int c, float* result)
 {
     constexpr int BACK = TAPS == 8 ? 4 : 2;          // window = [c-BACK, c+TAPS-BACK-1]
     const float xc = line[c * stride];
-    float w[TAPS], f[TAPS];
+    float w[TAPS], f[TAPS];                          // by tap; tap k sits in ring slot (c-BACK+k) % TAPS (:1667, :1590)
 #pragma unroll
     for (int k = 0; k < TAPS; k++) {
-        const int pos = c - BACK + k;
-        const float x = line[pos * stride];
-        const float wk = fmaxf(0.f, __fsub_rn(4.0f, masked_abs(__fsub_rn(x, xc))));
-        const int slot = pos & (TAPS - 1);           // val[u % taps], :1667 / :1590
-        w[slot] = wk;
-        f[slot] = __fmul_rn(x, wk);
+        const float x = line[(c - BACK + k) * stride];
+        w[k] = fmaxf(0.f, __fsub_rn(4.0f, masked_abs(__fsub_rn(x, xc))));
+        f[k] = __fmul_rn(x, w[k]);
     }
     float ws, fs;
     if (TAPS == 8) {
-        ws = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(w[0], w[4]), __fadd_rn(w[1], w[5])), __fadd_rn(w[2], w[6])), __fadd_rn(w[3], w[7]));
-        fs = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(f[0], f[4]), __fadd_rn(f[1], f[5])), __fadd_rn(f[2], f[6])), __fadd_rn(f[3], f[7]));
+        // SSE lane l = slot l + slot l+4 = taps j and j+4 with j = (l - first_slot) & 3
+        const int r = (c - BACK) & 3;
+        ws = ring_sum4(__fadd_rn(w[0], w[4]), __fadd_rn(w[1], w[5]), __fadd_rn(w[2], w[6]), __fadd_rn(w[3], w[7]), r);
+        fs = ring_sum4(__fadd_rn(f[0], f[4]), __fadd_rn(f[1], f[5]), __fadd_rn(f[2], f[6]), __fadd_rn(f[3], f[7]), r);
     } else {
-        ws = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), w[2]), w[3]);
-        fs = __fadd_rn(__fadd_rn(__fadd_rn(f[0], f[1]), f[2]), f[3]);
+        const int r = (c - BACK) & 3;
+        ws = ring_sum4(w[0], w[1], w[2], w[3], r);
+        fs = ring_sum4(f[0], f[1], f[2], f[3], r);
     }
     if (ws > 0.f) {
         const float d = __fdiv_rn(fs, ws);
@@ -266,9 +330,10 @@ void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, in
     const int n = g.Dw * g.Dh;
     int speckle = p.speckle_size;
     if (p.subsampling) speckle = (int)(sqrtf((float)p.speckle_size) * 2);            // :1218
-    k_seg_init<<<(n + 255) / 256, 256, 0, s>>>(n, parent, size);
-    k_seg_link<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, p.speckle_sim_threshold, D, parent);
-    k_seg_count<<<(n + 255) / 256, 256, 0, s>>>(n, D, parent, size);
+    const float thr = p.speckle_sim_threshold;
+    k_seg_rows<<<g.Dh, 256, 0, s>>>(g.Dw, thr, D, parent, size);
+    k_seg_merge<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent);
+    k_seg_count<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size);
     k_seg_apply<<<(n + 255) / 256, 256, 0, s>>>(n, speckle, D, parent, size);
     count_launch(4);
 }

@@ -77,6 +77,7 @@ CASES = [
     ("ragged-333x131", 333, 131, 63, 2, lambda d: checkers.stereomapper(d)),
     ("dmin3", 320, 160, 63, 6, lambda d: checkers.stereomapper(d).copy(disp_min=3)),
     ("dmax-not-multiple-of-32", 400, 180, 100, 9, lambda d: checkers.demo(d)),
+    ("wide-4096x160-d256-ten-segments", 4096, 160, 256, 12, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255", 1242, 375, 255, 0, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255-seed1-demo", 1242, 375, 255, 1, lambda d: checkers.demo(d)),
 ]
