@@ -11,6 +11,10 @@ namespace elasb {
 
 constexpr int kInvalid = -10;        // elas.cpp:977-980: disparity maps are pre-filled with -10
 
+// candidate grid, list form: per cell kGridListStride uint16 = {count, d0, d1, ...} (128 bytes)
+constexpr int kGridListStride = 64;
+constexpr int kGridListCap = kGridListStride - 1;
+
 // Everything a kernel needs to know about one frame geometry + parameter block.
 struct FrameGeom {
     int W, H;            // image size (dims[0], dims[1])
@@ -63,7 +67,8 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
                     const uint4* desc2, int16_t* dcan, cudaStream_t s);
 // K6  candidate grid as per-cell disparity bitmasks, both images (elas.cpp:684-780)
 void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, cudaStream_t s);
+                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                 cudaStream_t s);
 // triangle-id maps: scan conversion with last-writer-wins (elas.cpp:1074-1114)
 void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
                    const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s);
@@ -71,7 +76,8 @@ void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, i
 void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
                      const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
-                     const uint32_t* grid2, const int32_t* prior, float* D1, float* D2, cudaStream_t s);
+                     const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
+                     const int32_t* prior, float* D1, float* D2, cudaStream_t s);
 size_t matching_smem_bytes(const FrameGeom& g, int grid_size);
 // K8  left/right consistency (elas.cpp:1122-1204)
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,

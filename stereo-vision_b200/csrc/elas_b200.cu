@@ -61,7 +61,8 @@ struct Slot {
     int32_t* d_support = nullptr;
     TriRaster* d_tri[2] = {nullptr, nullptr};
     uint32_t* d_grid_scratch = nullptr;
-    uint32_t* d_grid[2] = {nullptr, nullptr};
+    uint32_t* d_grid[2] = {nullptr, nullptr};      // candidate grid, bitmask form [gh*gw][gwords]
+    uint16_t* d_lists[2] = {nullptr, nullptr};     // candidate grid, list form [gh*gw][kGridListStride]
     int32_t* d_map[2] = {nullptr, nullptr};
     float* d_raw[2] = {nullptr, nullptr};      // K7 output
     float* d_D[2] = {nullptr, nullptr};        // after the L/R check and post-processing
@@ -149,7 +150,7 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
 void free_slot(Slot& s)
 {
     for (int k = 0; k < 2; k++) {
-        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]);
+        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
         cudaFreeHost(s.h_tri[k]);
     }
@@ -173,6 +174,7 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
         CK(cudaMalloc(&s.d_desc[k], N * 16));
         CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
+        CK(cudaMalloc(&s.d_lists[k], (size_t)g.gw * g.gh * kGridListStride * 2));
         CK(cudaMalloc(&s.d_map[k], N * 4));
         CK(cudaMalloc(&s.d_raw[k], ND * 4));
         CK(cudaMalloc(&s.d_D[k], ND * 4));
@@ -311,12 +313,12 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     for (int k = 0; k < 2; k++)
         CK(cudaMemcpyAsync(s.d_tri[k], s.h_tri[k], (size_t)s.n_tri[k] * sizeof(TriRaster), cudaMemcpyHostToDevice, st));
     mark(c, s, "tables_in");
-    launch_grid(g, p, s.d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], st);
+    launch_grid(g, p, s.d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], st);
     mark(c, s, "grid");
     launch_raster(g, p.subsampling, s.d_tri[0], s.n_tri[0], s.d_tri[1], s.n_tri[1], s.d_map[0], s.d_map[1], st);
     mark(c, s, "raster");
     launch_matching(g, p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                    s.d_grid[0], s.d_grid[1], c->d_prior, s.d_raw[0], s.d_raw[1], st);
+                    s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1], st);
     mark(c, s, "matching");
     s.tables_valid = true;
     if (s.capture) {
@@ -501,6 +503,9 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
     c->tri_cap = 2 * c->support_cap + 8;
     if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
+    // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15
+    for (int k = 0; k <= c->g.plane_radius && k < c->g.dn; k++)
+        if (prior[k] > 5000 || prior[k] < -5000) return ELAS_B200_E_UNSUPPORTED;
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
     c->launches_at_create = launches_issued();
@@ -680,7 +685,7 @@ float elas_b200_time_matching(elas_b200_ctx* c, int32_t slot, int32_t iters, int
         if (flush_l2) cudaMemsetAsync(c->d_flush, i & 0xff, c->flush_bytes, s.stream);
         cudaEventRecord(e0, s.stream);
         launch_matching(c->g, c->p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                        s.d_grid[0], s.d_grid[1], c->d_prior, s.d_raw[0], s.d_raw[1], s.stream);
+                        s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1], s.stream);
         cudaEventRecord(e1, s.stream);
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { total = -1; break; }
         float ms = 0;

@@ -37,26 +37,39 @@ __global__ void k_grid_scatter(FrameGeom g, elas_b200_params p, const int32_t* _
 // elas.cpp:732-751: the reference walks nine pointers over the flat temp1 array in lock-step, so a
 // cell's "3x3 neighbourhood" is the nine FLAT offsets {-gw-1,-gw,-gw+1,-1,0,1,gw-1,gw,gw+1} (it
 // wraps across row ends) and only flat cells gw+1 .. gw*gh-gw-2 are written; all others stay empty
-// (SURVEY A.7).
+// (SURVEY A.7).  One thread per (image, cell): ORs the nine scratch masks word by word, stores the
+// cell's bitmask and, for the matching kernel, the same set as an ascending uint16 list
+// (elas.cpp:754-775 packs exactly this list): list[0] = count, list[1..] = disparities; a cell with
+// more than kGridListCap candidates gets count 0xFFFF and is read from its bitmask instead.
 __global__ void k_grid_diffuse(FrameGeom g, const uint32_t* __restrict__ scratch,
-                               uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2)
+                               uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
+                               uint16_t* __restrict__ lists1, uint16_t* __restrict__ lists2)
 {
     const int cells = g.gw * g.gh;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // (cell, word)
-    if (i >= cells * g.gwords) return;
-    const int c = i / g.gwords, w = i % g.gwords;
-#pragma unroll
-    for (int img = 0; img < 2; img++) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * cells) return;
+    const int img = i >= cells, c = img ? i - cells : i;
+    uint32_t* bits = (img ? grid2 : grid1) + (size_t)c * g.gwords;
+    uint16_t* list = (img ? lists2 : lists1) + (size_t)c * kGridListStride;
+    const bool written = c >= g.gw + 1 && c <= cells - g.gw - 2;
+    int count = 0;
+    for (int w = 0; w < g.gwords; w++) {
         uint32_t m = 0;
-        if (c >= g.gw + 1 && c <= cells - g.gw - 2) {
+        if (written) {
             const uint32_t* t = scratch + (size_t)img * cells * g.gwords + w;
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
                 for (int dx = -1; dx <= 1; dx++) m |= t[(size_t)(c + dy * g.gw + dx) * g.gwords];
         }
-        (img ? grid2 : grid1)[i] = m;
+        bits[w] = m;
+        while (m) {
+            if (count < kGridListCap) list[1 + count] = (uint16_t)(32 * w + __ffs(m) - 1);
+            count++;
+            m &= m - 1;
+        }
     }
+    list[0] = count <= kGridListCap ? (uint16_t)count : (uint16_t)0xFFFF;
 }
 
 // Scan conversion of one triangle per warp (elas.cpp:1074-1114): lanes take the columns u of both
@@ -98,7 +111,8 @@ k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int n
 }  // namespace
 
 void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, cudaStream_t s)
+                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                 cudaStream_t s)
 {
     const size_t words = (size_t)g.gw * g.gh * g.gwords;
     cudaMemsetAsync(scratch, 0, 2 * words * sizeof(uint32_t), s);
@@ -106,7 +120,8 @@ void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* s
         k_grid_scatter<<<(n_support + 127) / 128, 128, 0, s>>>(g, p, support, n_support, scratch);
         count_launch();
     }
-    k_grid_diffuse<<<(int)((words + 255) / 256), 256, 0, s>>>(g, scratch, grid1, grid2);
+    const int cells2 = 2 * g.gw * g.gh;
+    k_grid_diffuse<<<(cells2 + 127) / 128, 128, 0, s>>>(g, scratch, grid1, grid2, lists1, lists2);
     count_launch();
 }
 

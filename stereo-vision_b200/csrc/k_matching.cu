@@ -26,7 +26,6 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kSegTarget = 448;         // rows wider than this are cut into ~equal segments
-constexpr int kListCap = 48;            // candidates per cell kept as a list; fuller cells use the bitmask path
 constexpr int kPriorCap = 16;
 
 struct SegPlan { int nseg, segw; };
@@ -80,16 +79,26 @@ struct MatchArgs {
     const TriRaster* tri[2];
     const int32_t* map[2];
     const uint32_t* grid[2];
+    const uint16_t* lists[2];
     const int32_t* prior;
     float* D[2];
 };
 
-// rare path: a cell holding more than kListCap candidates is scanned from its bitmask in global memory
-__device__ __noinline__ void scan_cell_bitmask(const uint32_t* __restrict__ cell, int gwords, int dlo, int dhi,
-                                               int u, int img, int W, const uint4& own,
-                                               const uint4* __restrict__ oth_strip, int oth_lo,
-                                               int& min_val, int& min_d)
+// Candidates are ranked by the key (cost << 8 | evaluation order): the minimum key is the lowest cost
+// and, among equal costs, the candidate the reference evaluates first -- its strict '<' (elas.cpp:790,
+// :805) -- so candidates need no sequential compare-and-select chain.  A candidate the reference
+// skips (warped column outside [2, W-2), elas.cpp:896-899, :907-910) gets kSkip added instead of a
+// branch: it can then never beat the initial 10000 (elas.cpp:878).  Costs stay below 2^15.
+constexpr int kSkip = 20000;
+constexpr int kInitKey = (10000 << 8) | 255;
+
+// rare path: a cell holding more than kGridListCap candidates is scanned from its bitmask in global memory
+__device__ __noinline__ int scan_cell_bitmask(const uint32_t* __restrict__ cell, int gwords, int dlo, int dhi,
+                                              int u, int img, int W, uint4 own,
+                                              const uint4* __restrict__ oth, int best)
 {
+    // evaluation order no longer fits the key's 8 bits: keep (cost, d) with the sequential rule
+    int min_val = best >> 8, min_d = -1;
     for (int w = 0; w < gwords; w++) {
         uint32_t m = __ldg(cell + w);
         while (m) {
@@ -98,12 +107,14 @@ __device__ __noinline__ void scan_cell_bitmask(const uint32_t* __restrict__ cell
             if (d >= dlo && d <= dhi) continue;
             const int uw = img ? u + d : u - d;
             if (uw < 2 || uw >= W - 2) continue;
-            const int val = (int)sad16(own, oth_strip[uw - oth_lo]);
+            const int val = (int)sad16(own, oth[img ? d : -d]);
             if (val < min_val) { min_val = val; min_d = d; }
         }
     }
+    return min_d < 0 ? -1 : ((min_val << 16) | min_d);
 }
 
+template <int RADIUS>     // plane_radius (elas.cpp:993); 0 = generic
 __global__ void __launch_bounds__(kThreads)
 k_matching(const __grid_constant__ MatchArgs a)
 {
@@ -115,60 +126,35 @@ k_matching(const __grid_constant__ MatchArgs a)
     const int v = blockIdx.y;
     if (a.subsampling && ((v & 1) || (v >> 1) >= g.Dh)) return;           // elas.cpp:1085
     const int x0 = blockIdx.x * a.segw, x1 = min(x0 + a.segw, g.W);
-    // strip 0 = desc1 columns [s0lo, s0hi), strip 1 = desc2 columns [s1lo, s1hi)
-    const int s0lo = x0, s0hi = min(x1 + a.disp_max, g.W);
-    const int s1lo = max(x0 - a.disp_max, 0), s1hi = x1;
-    const int strip_cap = min(a.segw + a.disp_max, g.W);
+    // strip 0 holds desc1 columns [x0, x0+cap), strip 1 holds desc2 columns [x0-disp_max, x0-disp_max+cap)
+    // (cap = segw + disp_max); only the part inside the image is copied, the rest is never selected
+    const int cap = a.segw + a.disp_max;
+    const int s0org = x0, s1org = x0 - a.disp_max;
     uint4* strip0 = reinterpret_cast<uint4*>(smem_raw);
-    uint4* strip1 = strip0 + strip_cap;
-    uint16_t* lists = reinterpret_cast<uint16_t*>(strip1 + strip_cap);    // [2][max_cells][kListCap]
-    int* counts = reinterpret_cast<int*>(lists + 2 * a.max_cells * kListCap);   // [2][max_cells]
+    uint4* strip1 = strip0 + cap;
+    const uint16_t* lists = reinterpret_cast<const uint16_t*>(strip1 + cap);   // [2][max_cells][kGridListStride]
 
     const int vrow = max(min(v, g.H - 3), 2);                              // elas.cpp:834
+    const int gy = v / a.grid_size;                                        // elas.cpp:867
+    const int c0 = x0 / a.grid_size, c1 = (x1 - 1) / a.grid_size, ncell = c1 - c0 + 1;
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     if (threadIdx.x < kPriorCap) s_prior[threadIdx.x] = threadIdx.x < g.dn ? __ldg(a.prior + threadIdx.x) : 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t b0 = (uint32_t)(s0hi - s0lo) * 16u, b1 = (uint32_t)(s1hi - s1lo) * 16u;
-        mbar_expect_tx(&bar, b0 + b1);
-        tma_bulk_g2s(strip0, a.desc[0] + (size_t)vrow * g.W + s0lo, b0, &bar);
-        tma_bulk_g2s(strip1, a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
+        // four TMA bulk copies on one mbarrier: two descriptor strips, two runs of candidate lists
+        const int s0hi = min(x1 + a.disp_max, g.W), s1lo = max(s1org, 0);
+        const uint32_t b0 = (uint32_t)(s0hi - x0) * 16u, b1 = (uint32_t)(x1 - s1lo) * 16u;
+        const uint32_t bl = (uint32_t)ncell * kGridListStride * 2u;
+        mbar_expect_tx(&bar, b0 + b1 + 2 * bl);
+        tma_bulk_g2s(strip0, a.desc[0] + (size_t)vrow * g.W + x0, b0, &bar);
+        tma_bulk_g2s(strip1 + (s1lo - s1org), a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
+        const size_t cell0 = ((size_t)gy * g.gw + c0) * kGridListStride;
+        tma_bulk_g2s(const_cast<uint16_t*>(lists), a.lists[0] + cell0, bl, &bar);
+        tma_bulk_g2s(const_cast<uint16_t*>(lists) + a.max_cells * kGridListStride, a.lists[1] + cell0, bl, &bar);
     }
-
-    // candidate lists of the cells under this segment (elas.cpp:873-874), one (image, cell) per warp pass
-    const int gy = v / a.grid_size;                                        // elas.cpp:867
-    const int c0 = x0 / a.grid_size, c1 = (x1 - 1) / a.grid_size, ncell = c1 - c0 + 1;
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int job = warp; job < 2 * ncell; job += kThreads / 32) {
-            const int img = job >= ncell, c = img ? job - ncell : job;
-            const uint32_t* cell = a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords;
-            uint16_t* list = lists + (img * a.max_cells + c) * kListCap;
-            int total = 0;
-            for (int w0 = 0; w0 < g.gwords; w0 += 32) {
-                const uint32_t m = (w0 + lane < g.gwords) ? __ldg(cell + w0 + lane) : 0u;
-                const int cnt = __popc(m);
-                int incl = cnt;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += t;
-                }
-                int pos = total + incl - cnt;
-                uint32_t mm = m;
-                while (mm) {
-                    if (pos < kListCap) list[pos] = (uint16_t)(32 * (w0 + lane) + __ffs(mm) - 1);
-                    pos++;
-                    mm &= mm - 1;
-                }
-                total += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) counts[img * a.max_cells + c] = total <= kListCap ? total : -1;
-        }
-    }
-    __syncthreads();
 
     const int n = x1 - x0;
+    const int radius = RADIUS ? RADIUS : g.plane_radius;
     bool waited = false;
 
     // items 0..n-1: left image pixels, n..2n-1: right image pixels
@@ -181,45 +167,70 @@ k_matching(const __grid_constant__ MatchArgs a)
 
         float out = (float)kInvalid;                                       // elas.cpp:977-980
         if (t >= 0 && u >= 2 && u < g.W - 2) {                             // elas.cpp:828
-            const uint4* own_strip = img ? strip1 : strip0;
-            const uint4* oth_strip = img ? strip0 : strip1;
-            const int own_lo = img ? s1lo : s0lo, oth_lo = img ? s0lo : s1lo;
-            const uint4 own = own_strip[u - own_lo];
+            const uint4 own = img ? strip1[u - s1org] : strip0[u - s0org];
             if ((int)texture16(own) >= a.match_texture) {                  // elas.cpp:851-859
                 // plane (a,b,c) and validity of the covering triangle: one 16-byte load
                 const float4 pl = __ldg(reinterpret_cast<const float4*>(&a.tri[img][t].pa));
-                const int valid = __float_as_int(pl.w);
+                const bool valid = __float_as_int(pl.w) != 0;
                 // elas.cpp:861: (int32_t)(plane_a*u + plane_b*v + plane_c), evaluated left to right
                 const int d_plane = __float2int_rz(
                     __fadd_rn(__fadd_rn(__fmul_rn(pl.x, (float)u), __fmul_rn(pl.y, (float)v)), pl.z));
-                const int dlo = max(d_plane - g.plane_radius, 0);
-                const int dhi = min(d_plane + g.plane_radius, g.dn - 1);
-                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - c0;          // u / grid_size - c0
+                const int dlo = max(d_plane - radius, 0);
+                const int dhi = min(d_plane + radius, g.dn - 1);
+                // other image's descriptor at warped column u -+ d is oth[-+d]; the signed step keeps the
+                // inner loops free of the left/right distinction
+                const uint4* oth = img ? strip0 + (u - s0org) : strip1 + (u - s1org);
+                const int step = img ? 1 : -1;
+                // u -+ d inside [2, W-2)  <=>  d in [dmin_ok, dmax_ok]
+                const int dmax_ok = img ? g.W - 3 - u : u - 2;
 
-                int min_val = 10000, min_d = -1;                           // elas.cpp:878-879
+                int best = kInitKey;                                       // elas.cpp:878-879
                 // (i) grid candidates outside the plane window, ascending (elas.cpp:890-903, :919-932)
-                const int cnt = counts[img * a.max_cells + c];
-                if (cnt >= 0) {
-                    const uint16_t* list = lists + (img * a.max_cells + c) * kListCap;
+                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - c0;          // u / grid_size - c0
+                const uint16_t* list = lists + (img * a.max_cells + c) * kGridListStride;
+                const int cnt = list[0];
+                int wide = -1;
+                if (cnt != 0xFFFF) {
                     for (int i = 0; i < cnt; i++) {
-                        const int d = list[i];
+                        const int d = list[1 + i];
                         if (d >= dlo && d <= dhi) continue;
-                        const int uw = img ? u + d : u - d;
-                        if (uw < 2 || uw >= g.W - 2) continue;
-                        const int val = (int)sad16(own, oth_strip[uw - oth_lo]);
-                        if (val < min_val) { min_val = val; min_d = d; }
+                        int val = (int)sad16(own, oth[step * d]);
+                        val += d > dmax_ok ? kSkip : 0;
+                        best = min(best, val * 256 + i);
                     }
                 } else {
-                    scan_cell_bitmask(a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords, g.gwords, dlo, dhi,
-                                      u, img, g.W, own, oth_strip, oth_lo, min_val, min_d);
+                    wide = scan_cell_bitmask(a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords, g.gwords,
+                                             dlo, dhi, u, img, g.W, own, oth, best);
                 }
                 // (ii) the plane window with the prior (elas.cpp:904-913, :934-943)
-                for (int d = dlo; d <= dhi; d++) {
-                    const int uw = img ? u + d : u - d;
-                    if (uw < 2 || uw >= g.W - 2) continue;
-                    int val = (int)sad16(own, oth_strip[uw - oth_lo]);
-                    if (valid) val += s_prior[abs(d - d_plane)];
-                    if (val < min_val) { min_val = val; min_d = d; }
+                if (RADIUS) {
+#pragma unroll
+                    for (int k = -RADIUS; k <= RADIUS; k++) {
+                        const int d = d_plane + k;
+                        const int prior = valid ? s_prior[k < 0 ? -k : k] : 0;
+                        // d outside [0, disp_max] is not part of the loop; reading oth[] stays inside the strips
+                        const int dc = min(max(d, 0), a.disp_max);
+                        int val = (int)sad16(own, oth[step * dc]) + prior;
+                        val += (d < 0 || d > a.disp_max || d > dmax_ok) ? kSkip : 0;
+                        best = min(best, val * 256 + (64 + k + RADIUS));
+                    }
+                } else {
+                    for (int d = dlo; d <= dhi; d++) {
+                        int val = (int)sad16(own, oth[step * d]) + (valid ? s_prior[abs(d - d_plane)] : 0);
+                        val += d > dmax_ok ? kSkip : 0;
+                        best = min(best, val * 256 + (64 + d - (d_plane - radius)));
+                    }
+                }
+                // decode: evaluation order -> disparity
+                int min_d = -1;
+                if (best < kInitKey) {
+                    const int ord = best & 255;
+                    min_d = ord < 64 ? list[1 + ord] : d_plane - radius + (ord - 64);
+                }
+                if (wide >= 0) {
+                    // the bitmask path ran first in evaluation order: it wins ties
+                    const int wval = wide >> 16, wd = wide & 0xFFFF;
+                    if (min_d < 0 || wval <= (best >> 8)) min_d = wd;
                 }
                 out = min_d >= 0 ? (float)min_d : -1.0f;                   // elas.cpp:947-954
             }
@@ -238,7 +249,8 @@ size_t smem_bytes_for(const FrameGeom& g, int grid_size)
     const int dmax = g.dn - 1;
     const size_t strip = (size_t)((s.segw + dmax) < g.W ? (s.segw + dmax) : g.W);
     const size_t cells = (size_t)max_cells_per_segment(g, grid_size, s.segw);
-    return 2 * strip * 16 + 2 * cells * kListCap * 2 + 2 * cells * 4;
+    (void)strip;
+    return 2 * (size_t)(s.segw + dmax) * 16 + 2 * cells * kGridListStride * 2;
 }
 
 }  // namespace
@@ -248,11 +260,14 @@ size_t matching_smem_bytes(const FrameGeom& g, int grid_size) { return smem_byte
 void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
                      const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
-                     const uint32_t* grid2, const int32_t* prior, float* D1, float* D2, cudaStream_t s)
+                     const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
+                     const int32_t* prior, float* D1, float* D2, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_matching, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_matching<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_matching<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_matching<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     const SegPlan sp = plan_segments(g.W);
@@ -267,10 +282,14 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.tri[0] = tri1; a.tri[1] = tri2;
     a.map[0] = map1; a.map[1] = map2;
     a.grid[0] = grid1; a.grid[1] = grid2;
+    a.lists[0] = lists1; a.lists[1] = lists2;
     a.prior = prior;
     a.D[0] = D1; a.D[1] = D2;
     dim3 grid(sp.nseg, g.H, 1);
-    k_matching<<<grid, kThreads, smem_bytes_for(g, p.grid_size), s>>>(a);
+    const size_t smem = smem_bytes_for(g, p.grid_size);
+    if (g.plane_radius == 2)      k_matching<2><<<grid, kThreads, smem, s>>>(a);     // ROBOTICS
+    else if (g.plane_radius == 3) k_matching<3><<<grid, kThreads, smem, s>>>(a);     // MIDDLEBURY
+    else                          k_matching<0><<<grid, kThreads, smem, s>>>(a);
     count_launch();
 }
 
