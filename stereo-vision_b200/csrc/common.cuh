@@ -15,6 +15,10 @@ constexpr int kInvalid = -10;        // elas.cpp:977-980: disparity maps are pre
 constexpr int kGridListStride = 64;
 constexpr int kGridListCap = kGridListStride - 1;
 
+struct FrameGeom;
+// triangle-id maps are int32 [H][map_pitch]: rows padded to 16 bytes so the matching kernel can TMA them
+__host__ __device__ inline int map_pitch_of(int W) { return (W + 3) & ~3; }
+
 // Everything a kernel needs to know about one frame geometry + parameter block.
 struct FrameGeom {
     int W, H;            // image size (dims[0], dims[1])
@@ -57,6 +61,8 @@ __device__ __forceinline__ unsigned texture16(const uint4& a)
     return sad16(a, mid);
 }
 #endif  // __CUDACC__
+
+__host__ __device__ inline int map_pitch(const FrameGeom& g) { return map_pitch_of(g.W); }
 
 // ---- kernel launchers (one translation unit each) --------------------------------------------
 // K1  Sobel + descriptor, both images (filter.cpp:408-416, descriptor.cpp:48-121)

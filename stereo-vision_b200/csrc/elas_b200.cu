@@ -175,7 +175,7 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
         CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
         CK(cudaMalloc(&s.d_lists[k], (size_t)g.gw * g.gh * kGridListStride * 2));
-        CK(cudaMalloc(&s.d_map[k], N * 4));
+        CK(cudaMalloc(&s.d_map[k], (size_t)map_pitch(g) * g.H * 4));
         CK(cudaMalloc(&s.d_raw[k], ND * 4));
         CK(cudaMalloc(&s.d_D[k], ND * 4));
         CK(cudaMallocHost(&s.h_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));

@@ -83,6 +83,7 @@ k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int n
          const TriRaster* __restrict__ tri2, int nt2, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
 {
     const int lane = threadIdx.x & 31;
+    const int pitch = map_pitch(g);
     int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const TriRaster* tri; int32_t* map;
     if (t < nt1) { tri = tri1 + t; map = map1; }
@@ -102,7 +103,7 @@ k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int n
             const int lo = max(min(v1, v2), 0), hi = min(max(v1, v2), g.H);
             for (int v = lo; v < hi; v++) {
                 if (subsampling && (v & 1)) continue;
-                atomicMax(map + (size_t)v * g.W + u, t);
+                atomicMax(map + (size_t)v * pitch + u, t);
             }
         }
     }
@@ -128,7 +129,7 @@ void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* s
 void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
                    const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s)
 {
-    const size_t bytes = (size_t)g.W * g.H * sizeof(int32_t);
+    const size_t bytes = (size_t)map_pitch(g) * g.H * sizeof(int32_t);
     cudaMemsetAsync(map1, 0xFF, bytes, s);      // -1 = not covered by any triangle
     cudaMemsetAsync(map2, 0xFF, bytes, s);
     const int total = nt1 + nt2;

@@ -19,19 +19,27 @@
 // Per pixel (findMatch): candidates = the grid cell's disparities OUTSIDE the plane window in
 // ascending order (cost = SAD), then the plane window d_plane-r..d_plane+r ascending
 // (cost = SAD + prior if the triangle is valid); strict '<' keeps the first minimum (elas.cpp:790,805).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace elasb {
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kSegTarget = 448;         // rows wider than this are cut into ~equal segments
+constexpr int kSegTargetDefault = 448;  // rows wider than this are cut into ~equal segments
 constexpr int kPriorCap = 16;
 
 struct SegPlan { int nseg, segw; };
 
+inline int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 inline SegPlan plan_segments(int W)
 {
+    static const int kSegTarget = env_int("ELAS_B200_K7_SEG", kSegTargetDefault);
     SegPlan s;
     s.nseg = (W + kSegTarget - 1) / kSegTarget;
     s.segw = ((W + s.nseg - 1) / s.nseg + 31) & ~31;
@@ -73,7 +81,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 struct MatchArgs {
     FrameGeom g;
     int disp_max, match_texture, grid_size, subsampling;
-    int segw, max_cells;
+    int segw, max_cells, map_pitch;
     uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
     const uint4* desc[2];
     const TriRaster* tri[2];
@@ -94,27 +102,130 @@ constexpr int kInitKey = (10000 << 8) | 255;
 
 // rare path: a cell holding more than kGridListCap candidates is scanned from its bitmask in global memory
 __device__ __noinline__ int scan_cell_bitmask(const uint32_t* __restrict__ cell, int gwords, int dlo, int dhi,
-                                              int u, int img, int W, uint4 own,
-                                              const uint4* __restrict__ oth, int best)
+                                              int hi_ok, int step, uint4 own, const uint4* __restrict__ oth)
 {
     // evaluation order no longer fits the key's 8 bits: keep (cost, d) with the sequential rule
-    int min_val = best >> 8, min_d = -1;
+    int min_val = 10000, min_d = -1;
     for (int w = 0; w < gwords; w++) {
         uint32_t m = __ldg(cell + w);
         while (m) {
             const int d = 32 * w + __ffs(m) - 1;
             m &= m - 1;
-            if (d >= dlo && d <= dhi) continue;
-            const int uw = img ? u + d : u - d;
-            if (uw < 2 || uw >= W - 2) continue;
-            const int val = (int)sad16(own, oth[img ? d : -d]);
+            if ((d >= dlo && d <= dhi) || d > hi_ok) continue;
+            const int val = (int)sad16(own, oth[step * d]);
             if (val < min_val) { min_val = val; min_d = d; }
         }
     }
     return min_d < 0 ? -1 : ((min_val << 16) | min_d);
 }
 
-template <int RADIUS>     // plane_radius (elas.cpp:993); 0 = generic
+constexpr int kPad = 4;     // strip entries before/after the addressed range: window taps may step outside [0, disp_max]
+
+struct RowCtx {
+    const uint4* strip[2];  // smem, strip[k][j] = descriptor k at column org[k] + j
+    int org[2];
+    const uint16_t* lists;  // smem [2][max_cells][kGridListStride]
+    const int32_t* tmap;    // smem [2][segw]: triangle ids of this row segment
+    int x0, n, v, c0, gy;
+};
+
+// findMatch (elas.cpp:814-955) for the pixels of one image in this row segment
+template <int IMG, int RADIUS, int kThreads>
+__device__ __forceinline__ void match_row(const MatchArgs& a, const RowCtx& r, const int* s_prior)
+{
+    const FrameGeom& g = a.g;
+    const TriRaster* __restrict__ tris = a.tri[IMG];
+    const uint4* own_strip = r.strip[IMG] - r.org[IMG];          // indexable by column
+    const uint4* oth_strip = r.strip[1 - IMG] - r.org[1 - IMG];
+    const int32_t* tmap = r.tmap + IMG * a.segw;
+    const uint16_t* lists = r.lists + IMG * a.max_cells * kGridListStride;
+    constexpr int step = IMG ? 1 : -1;                            // warped column = u + step * d
+    const int radius = RADIUS ? RADIUS : g.plane_radius;
+    const float fv = (float)r.v;
+    float* __restrict__ Drow = a.D[IMG] + (a.subsampling ? (size_t)(r.v >> 1) * g.Dw : (size_t)r.v * g.W);
+
+    // software pipeline: the covering triangle's plane for the next pixel is in flight while this one is matched
+    int i = threadIdx.x;
+    int t = i < r.n ? tmap[i] : -1;
+    float4 pl = t >= 0 ? __ldg(reinterpret_cast<const float4*>(&tris[t].pa)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; i < r.n; i += kThreads) {
+        const int u = r.x0 + i;
+        const int t_cur = t;
+        const float4 pl_cur = pl;
+        const int i_next = i + kThreads;
+        t = i_next < r.n ? tmap[i_next] : -1;
+        if (t >= 0) pl = __ldg(reinterpret_cast<const float4*>(&tris[t].pa));
+        if (a.subsampling && ((u & 1) || (u >> 1) >= g.Dw)) continue;      // elas.cpp:1079
+
+        float out = (float)kInvalid;                                       // elas.cpp:977-980
+        if (t_cur >= 0 && u >= 2 && u < g.W - 2) {                         // elas.cpp:828
+            const uint4 own = own_strip[u];
+            if ((int)texture16(own) >= a.match_texture) {                  // elas.cpp:851-859
+                const bool valid = __float_as_int(pl_cur.w) != 0;
+                // elas.cpp:861: (int32_t)(plane_a*u + plane_b*v + plane_c), evaluated left to right
+                const int d_plane = __float2int_rz(
+                    __fadd_rn(__fadd_rn(__fmul_rn(pl_cur.x, (float)u), __fmul_rn(pl_cur.y, fv)), pl_cur.z));
+                const int dlo = max(d_plane - radius, 0);
+                const int dhi = min(d_plane + radius, a.disp_max);
+                const uint4* oth = oth_strip + u;                          // other descriptor at disparity d: oth[step*d]
+                // the warped column stays inside [2, W-2) and d inside [0, disp_max]  <=>  0 <= d <= hi_ok
+                const int hi_ok = min(a.disp_max, IMG ? g.W - 3 - u : u - 2);
+
+                int best = kInitKey;                                       // elas.cpp:878-879
+                // (i) grid candidates outside the plane window, ascending (elas.cpp:890-903, :919-932)
+                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - r.c0;        // u / grid_size - c0
+                const uint16_t* list = lists + c * kGridListStride;
+                const int cnt = list[0];
+                int wide = -1;
+                if (cnt != 0xFFFF) {
+                    const unsigned span = (unsigned)(dhi - dlo);
+                    for (int k = 1; k <= cnt; k++) {
+                        const int d = list[k];
+                        if ((unsigned)(d - dlo) <= span && dhi >= dlo) continue;
+                        int val = (int)sad16(own, oth[step * d]);
+                        val += d > hi_ok ? kSkip : 0;
+                        best = min(best, val * 256 + k);
+                    }
+                } else {
+                    wide = scan_cell_bitmask(a.grid[IMG] + ((size_t)r.gy * g.gw + r.c0 + c) * g.gwords, g.gwords,
+                                             dlo, dhi, hi_ok, step, own, oth);
+                }
+                // (ii) the plane window with the prior (elas.cpp:904-913, :934-943)
+                if (RADIUS) {
+#pragma unroll
+                    for (int k = -RADIUS; k <= RADIUS; k++) {
+                        const int d = d_plane + k;                         // may leave [0, disp_max] by <= RADIUS: padded strips
+                        const int dd = min(max(d, -kPad), a.disp_max + kPad);
+                        const int prior = valid ? s_prior[k < 0 ? -k : k] : 0;
+                        const int val = (int)sad16(own, oth[step * dd]) + ((unsigned)d > (unsigned)hi_ok ? prior + kSkip : prior);
+                        best = min(best, val * 256 + (64 + k + RADIUS));
+                    }
+                } else {
+                    for (int d = dlo; d <= dhi; d++) {
+                        int val = (int)sad16(own, oth[step * d]) + (valid ? s_prior[abs(d - d_plane)] : 0);
+                        val += d > hi_ok ? kSkip : 0;
+                        best = min(best, val * 256 + (64 + d - (d_plane - radius)));
+                    }
+                }
+                // decode: evaluation order -> disparity
+                int min_d = -1;
+                if (best < kInitKey) {
+                    const int ord = best & 255;
+                    min_d = ord < 64 ? list[ord] : d_plane - radius + (ord - 64);
+                }
+                if (wide >= 0) {
+                    // the bitmask path ran first in evaluation order: it wins ties
+                    const int wval = wide >> 16, wd = wide & 0xFFFF;
+                    if (min_d < 0 || wval <= (best >> 8)) min_d = wd;
+                }
+                out = min_d >= 0 ? (float)min_d : -1.0f;                   // elas.cpp:947-954
+            }
+        }
+        Drow[a.subsampling ? (u >> 1) : u] = out;
+    }
+}
+
+template <int RADIUS, int kThreads>     // plane_radius (elas.cpp:993); 0 = generic
 __global__ void __launch_bounds__(kThreads)
 k_matching(const __grid_constant__ MatchArgs a)
 {
@@ -126,119 +237,71 @@ k_matching(const __grid_constant__ MatchArgs a)
     const int v = blockIdx.y;
     if (a.subsampling && ((v & 1) || (v >> 1) >= g.Dh)) return;           // elas.cpp:1085
     const int x0 = blockIdx.x * a.segw, x1 = min(x0 + a.segw, g.W);
-    // strip 0 holds desc1 columns [x0, x0+cap), strip 1 holds desc2 columns [x0-disp_max, x0-disp_max+cap)
-    // (cap = segw + disp_max); only the part inside the image is copied, the rest is never selected
-    const int cap = a.segw + a.disp_max;
-    const int s0org = x0, s1org = x0 - a.disp_max;
+    // strip 0 holds desc1 columns from x0 - kPad, strip 1 holds desc2 columns from x0 - disp_max - kPad,
+    // cap = segw + disp_max + 2*kPad entries each; only the part inside the image is copied, the rest
+    // is addressable garbage that the skip penalty keeps from ever being selected
+    const int cap = a.segw + a.disp_max + 2 * kPad;
+    RowCtx r;
+    r.org[0] = x0 - kPad; r.org[1] = x0 - a.disp_max - kPad;
     uint4* strip0 = reinterpret_cast<uint4*>(smem_raw);
     uint4* strip1 = strip0 + cap;
-    const uint16_t* lists = reinterpret_cast<const uint16_t*>(strip1 + cap);   // [2][max_cells][kGridListStride]
+    uint16_t* lists = reinterpret_cast<uint16_t*>(strip1 + cap);           // [2][max_cells][kGridListStride]
+    int32_t* tmap = reinterpret_cast<int32_t*>(lists + 2 * a.max_cells * kGridListStride);   // [2][segw]
+    r.strip[0] = strip0; r.strip[1] = strip1; r.lists = lists; r.tmap = tmap;
+    r.x0 = x0; r.n = x1 - x0; r.v = v;
+    r.gy = v / a.grid_size;                                                // elas.cpp:867
+    r.c0 = x0 / a.grid_size;
+    const int ncell = (x1 - 1) / a.grid_size - r.c0 + 1;
 
     const int vrow = max(min(v, g.H - 3), 2);                              // elas.cpp:834
-    const int gy = v / a.grid_size;                                        // elas.cpp:867
-    const int c0 = x0 / a.grid_size, c1 = (x1 - 1) / a.grid_size, ncell = c1 - c0 + 1;
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     if (threadIdx.x < kPriorCap) s_prior[threadIdx.x] = threadIdx.x < g.dn ? __ldg(a.prior + threadIdx.x) : 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        // four TMA bulk copies on one mbarrier: two descriptor strips, two runs of candidate lists
-        const int s0hi = min(x1 + a.disp_max, g.W), s1lo = max(s1org, 0);
+        // six TMA bulk copies on one mbarrier: two descriptor strips, two runs of candidate lists, two
+        // triangle-id row segments
+        const int s0hi = min(x1 + a.disp_max, g.W), s1lo = max(x0 - a.disp_max, 0);
         const uint32_t b0 = (uint32_t)(s0hi - x0) * 16u, b1 = (uint32_t)(x1 - s1lo) * 16u;
         const uint32_t bl = (uint32_t)ncell * kGridListStride * 2u;
-        mbar_expect_tx(&bar, b0 + b1 + 2 * bl);
-        tma_bulk_g2s(strip0, a.desc[0] + (size_t)vrow * g.W + x0, b0, &bar);
-        tma_bulk_g2s(strip1 + (s1lo - s1org), a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
-        const size_t cell0 = ((size_t)gy * g.gw + c0) * kGridListStride;
-        tma_bulk_g2s(const_cast<uint16_t*>(lists), a.lists[0] + cell0, bl, &bar);
-        tma_bulk_g2s(const_cast<uint16_t*>(lists) + a.max_cells * kGridListStride, a.lists[1] + cell0, bl, &bar);
+        const uint32_t bm = (uint32_t)((r.n + 3) & ~3) * 4u;
+        mbar_expect_tx(&bar, b0 + b1 + 2 * bl + 2 * bm);
+        tma_bulk_g2s(strip0 + kPad, a.desc[0] + (size_t)vrow * g.W + x0, b0, &bar);
+        tma_bulk_g2s(strip1 + (s1lo - r.org[1]), a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
+        const size_t cell0 = ((size_t)r.gy * g.gw + r.c0) * kGridListStride;
+        tma_bulk_g2s(lists, a.lists[0] + cell0, bl, &bar);
+        tma_bulk_g2s(lists + a.max_cells * kGridListStride, a.lists[1] + cell0, bl, &bar);
+        tma_bulk_g2s(tmap, a.map[0] + (size_t)v * a.map_pitch + x0, bm, &bar);
+        tma_bulk_g2s(tmap + a.segw, a.map[1] + (size_t)v * a.map_pitch + x0, bm, &bar);
     }
+    mbar_wait(&bar, 0);
+    match_row<0, RADIUS, kThreads>(a, r, s_prior);
+    match_row<1, RADIUS, kThreads>(a, r, s_prior);
+}
 
-    const int n = x1 - x0;
-    const int radius = RADIUS ? RADIUS : g.plane_radius;
-    bool waited = false;
-
-    // items 0..n-1: left image pixels, n..2n-1: right image pixels
-    for (int item = threadIdx.x; item < 2 * n; item += kThreads) {
-        const int img = item >= n;
-        const int u = x0 + (img ? item - n : item);
-        if (a.subsampling && ((u & 1) || (u >> 1) >= g.Dw)) continue;      // elas.cpp:1079
-        const int t = __ldg(a.map[img] + (size_t)v * g.W + u);             // issued before the wait
-        if (!waited) { mbar_wait(&bar, 0); waited = true; }
-
-        float out = (float)kInvalid;                                       // elas.cpp:977-980
-        if (t >= 0 && u >= 2 && u < g.W - 2) {                             // elas.cpp:828
-            const uint4 own = img ? strip1[u - s1org] : strip0[u - s0org];
-            if ((int)texture16(own) >= a.match_texture) {                  // elas.cpp:851-859
-                // plane (a,b,c) and validity of the covering triangle: one 16-byte load
-                const float4 pl = __ldg(reinterpret_cast<const float4*>(&a.tri[img][t].pa));
-                const bool valid = __float_as_int(pl.w) != 0;
-                // elas.cpp:861: (int32_t)(plane_a*u + plane_b*v + plane_c), evaluated left to right
-                const int d_plane = __float2int_rz(
-                    __fadd_rn(__fadd_rn(__fmul_rn(pl.x, (float)u), __fmul_rn(pl.y, (float)v)), pl.z));
-                const int dlo = max(d_plane - radius, 0);
-                const int dhi = min(d_plane + radius, g.dn - 1);
-                // other image's descriptor at warped column u -+ d is oth[-+d]; the signed step keeps the
-                // inner loops free of the left/right distinction
-                const uint4* oth = img ? strip0 + (u - s0org) : strip1 + (u - s1org);
-                const int step = img ? 1 : -1;
-                // u -+ d inside [2, W-2)  <=>  d in [dmin_ok, dmax_ok]
-                const int dmax_ok = img ? g.W - 3 - u : u - 2;
-
-                int best = kInitKey;                                       // elas.cpp:878-879
-                // (i) grid candidates outside the plane window, ascending (elas.cpp:890-903, :919-932)
-                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - c0;          // u / grid_size - c0
-                const uint16_t* list = lists + (img * a.max_cells + c) * kGridListStride;
-                const int cnt = list[0];
-                int wide = -1;
-                if (cnt != 0xFFFF) {
-                    for (int i = 0; i < cnt; i++) {
-                        const int d = list[1 + i];
-                        if (d >= dlo && d <= dhi) continue;
-                        int val = (int)sad16(own, oth[step * d]);
-                        val += d > dmax_ok ? kSkip : 0;
-                        best = min(best, val * 256 + i);
-                    }
-                } else {
-                    wide = scan_cell_bitmask(a.grid[img] + ((size_t)gy * g.gw + c0 + c) * g.gwords, g.gwords,
-                                             dlo, dhi, u, img, g.W, own, oth, best);
-                }
-                // (ii) the plane window with the prior (elas.cpp:904-913, :934-943)
-                if (RADIUS) {
-#pragma unroll
-                    for (int k = -RADIUS; k <= RADIUS; k++) {
-                        const int d = d_plane + k;
-                        const int prior = valid ? s_prior[k < 0 ? -k : k] : 0;
-                        // d outside [0, disp_max] is not part of the loop; reading oth[] stays inside the strips
-                        const int dc = min(max(d, 0), a.disp_max);
-                        int val = (int)sad16(own, oth[step * dc]) + prior;
-                        val += (d < 0 || d > a.disp_max || d > dmax_ok) ? kSkip : 0;
-                        best = min(best, val * 256 + (64 + k + RADIUS));
-                    }
-                } else {
-                    for (int d = dlo; d <= dhi; d++) {
-                        int val = (int)sad16(own, oth[step * d]) + (valid ? s_prior[abs(d - d_plane)] : 0);
-                        val += d > dmax_ok ? kSkip : 0;
-                        best = min(best, val * 256 + (64 + d - (d_plane - radius)));
-                    }
-                }
-                // decode: evaluation order -> disparity
-                int min_d = -1;
-                if (best < kInitKey) {
-                    const int ord = best & 255;
-                    min_d = ord < 64 ? list[1 + ord] : d_plane - radius + (ord - 64);
-                }
-                if (wide >= 0) {
-                    // the bitmask path ran first in evaluation order: it wins ties
-                    const int wval = wide >> 16, wd = wide & 0xFFFF;
-                    if (min_d < 0 || wval <= (best >> 8)) min_d = wd;
-                }
-                out = min_d >= 0 ? (float)min_d : -1.0f;                   // elas.cpp:947-954
-            }
-        }
-        const size_t addr = a.subsampling ? (size_t)(v >> 1) * g.Dw + (u >> 1) : (size_t)v * g.W + u;
-        a.D[img][addr] = out;
+template <int RADIUS, int THREADS>
+void launch_one(dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_matching<RADIUS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
     }
-    if (!waited) mbar_wait(&bar, 0);     // never leave with a bulk copy in flight
+    k_matching<RADIUS, THREADS><<<grid, THREADS, smem, s>>>(a);
+}
+
+template <int THREADS>
+void launch_radius(int radius, dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
+{
+    if (radius == 2)      launch_one<2, THREADS>(grid, smem, s, a);      // ROBOTICS
+    else if (radius == 3) launch_one<3, THREADS>(grid, smem, s, a);      // MIDDLEBURY
+    else                  launch_one<0, THREADS>(grid, smem, s, a);
+}
+
+void launch_variant(int radius, int threads, dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
+{
+    if (threads == 256)      launch_radius<256>(radius, grid, smem, s, a);
+    else if (threads == 64)  launch_radius<64>(radius, grid, smem, s, a);
+    else                     launch_radius<128>(radius, grid, smem, s, a);
 }
 
 int max_cells_per_segment(const FrameGeom& g, int grid_size, int segw) { return (segw + grid_size - 1) / grid_size + 1; }
@@ -250,7 +313,7 @@ size_t smem_bytes_for(const FrameGeom& g, int grid_size)
     const size_t strip = (size_t)((s.segw + dmax) < g.W ? (s.segw + dmax) : g.W);
     const size_t cells = (size_t)max_cells_per_segment(g, grid_size, s.segw);
     (void)strip;
-    return 2 * (size_t)(s.segw + dmax) * 16 + 2 * cells * kGridListStride * 2;
+    return 2 * (size_t)(s.segw + dmax + 2 * kPad) * 16 + 2 * cells * kGridListStride * 2 + 2 * (size_t)s.segw * 4;
 }
 
 }  // namespace
@@ -263,13 +326,6 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
                      const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
                      const int32_t* prior, float* D1, float* D2, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_matching<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_matching<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_matching<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     const SegPlan sp = plan_segments(g.W);
     MatchArgs a;
     a.g = g;
@@ -277,6 +333,7 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.subsampling = p.subsampling;
     a.segw = sp.segw;
     a.max_cells = max_cells_per_segment(g, p.grid_size, sp.segw);
+    a.map_pitch = map_pitch(g);
     a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;
     a.desc[0] = desc1; a.desc[1] = desc2;
     a.tri[0] = tri1; a.tri[1] = tri2;
@@ -287,9 +344,8 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.D[0] = D1; a.D[1] = D2;
     dim3 grid(sp.nseg, g.H, 1);
     const size_t smem = smem_bytes_for(g, p.grid_size);
-    if (g.plane_radius == 2)      k_matching<2><<<grid, kThreads, smem, s>>>(a);     // ROBOTICS
-    else if (g.plane_radius == 3) k_matching<3><<<grid, kThreads, smem, s>>>(a);     // MIDDLEBURY
-    else                          k_matching<0><<<grid, kThreads, smem, s>>>(a);
+    static const int threads = env_int("ELAS_B200_K7_THREADS", 128);
+    launch_variant(g.plane_radius, threads, grid, smem, s, a);
     count_launch();
 }
 
