@@ -160,6 +160,10 @@ int32_t elas_b200_stage_timing(elas_b200_ctx* ctx, int32_t enable);
 int32_t elas_b200_stage_times(elas_b200_ctx* ctx, int32_t slot,
                               const char** names_out, float* ms_out, int32_t cap);
 
+/* Host-side wall time spent per frame phase, summed over all frames since the last reset, in
+ * milliseconds: {submit phase A, wait phase A, host stage, submit phase B, wait phase B}. */
+int32_t elas_b200_host_times(elas_b200_ctx* ctx, double ms_out[5], int64_t* frames, int32_t reset);
+
 /* Bench hook: runs only the dense matching kernel (left+right, elas.cpp:960-1118) `iters` times
  * on the tables left in `slot` by the last frame and returns the mean milliseconds per launch
  * (CUDA events on the slot's stream; flush_l2 != 0 rewrites a >L2-sized buffer between

@@ -75,6 +75,9 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
 void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
                  uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
                  cudaStream_t s);
+// K5  disparity planes + per-triangle raster records, both images (elas.cpp:605-680, :1006-1072)
+void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const int32_t* tri2, int nt2,
+                   TriRaster* out1, TriRaster* out2, float* planes1, float* planes2, cudaStream_t s);
 // triangle-id maps: scan conversion with last-writer-wins (elas.cpp:1074-1114)
 void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
                    const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s);

@@ -10,6 +10,7 @@
 //                -> GPU phase B (tables in, grid, triangle-id maps, K7 matching, K8-K12, copy-out)
 // and the GPU overlaps the phases of different slots.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
@@ -58,8 +59,9 @@ struct Slot {
     uint8_t* d_img[2] = {nullptr, nullptr};
     uint4* d_desc[2] = {nullptr, nullptr};
     int16_t* d_dcan = nullptr;
-    int32_t* d_support = nullptr;
-    TriRaster* d_tri[2] = {nullptr, nullptr};
+    int32_t* d_tables = nullptr;               // [support n x 3 | tri1 t1 x 3 | tri2 t2 x 3], packed, one copy per frame
+    TriRaster* d_tri[2] = {nullptr, nullptr};  // raster records, written by k_planes
+    float* d_planes[2] = {nullptr, nullptr};   // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle, written by k_planes
     uint32_t* d_grid_scratch = nullptr;
     uint32_t* d_grid[2] = {nullptr, nullptr};      // candidate grid, bitmask form [gh*gw][gwords]
     uint16_t* d_lists[2] = {nullptr, nullptr};     // candidate grid, list form [gh*gw][kGridListStride]
@@ -71,8 +73,8 @@ struct Slot {
     int32_t* d_size = nullptr;
     // pinned host
     int16_t* h_dcan = nullptr;
-    int32_t* h_support = nullptr;
-    TriRaster* h_tri[2] = {nullptr, nullptr};
+    int32_t* h_tables = nullptr;
+    cudaEvent_t ev_sync = nullptr;             // blocking wait (no spinning) when slots outnumber host cores
     // host stage + tables of the last frame (kept for elas_b200_time_matching)
     HostStage host;
     int n_tri[2] = {0, 0};
@@ -94,7 +96,10 @@ struct elas_b200_ctx {
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
     bool timing = false;
+    bool blocking_sync = false;              // wait on a blocking event instead of spinning in cudaStreamSynchronize
     long long launches_at_create = 0;
+    // host-side wall time per frame phase, summed over all frames and slots (nanoseconds)
+    std::atomic<long long> ns_submit_a{0}, ns_wait_a{0}, ns_host{0}, ns_submit_b{0}, ns_wait_b{0}, frames{0};
     std::vector<std::unique_ptr<Slot>> slots;
 
     // worker pool: one thread per slot, fed by process_batch
@@ -116,6 +121,11 @@ struct elas_b200_ctx {
 };
 
 namespace {
+
+inline long long now_ns()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 FrameGeom make_geom(const elas_b200_params& p, int W, int H)
 {
@@ -152,11 +162,12 @@ void free_slot(Slot& s)
     for (int k = 0; k < 2; k++) {
         cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
-        cudaFreeHost(s.h_tri[k]);
+        cudaFree(s.d_planes[k]);
     }
-    cudaFree(s.d_dcan); cudaFree(s.d_support); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
+    cudaFree(s.d_dcan); cudaFree(s.d_tables); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
     cudaFree(s.d_parent); cudaFree(s.d_size);
-    cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_support);
+    cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
+    if (s.ev_sync) cudaEventDestroy(s.ev_sync);
     for (auto& m : s.timer.marks) cudaEventDestroy(m.second);
     if (s.timer.begin) cudaEventDestroy(s.timer.begin);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -178,16 +189,18 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
         CK(cudaMalloc(&s.d_map[k], (size_t)map_pitch(g) * g.H * 4));
         CK(cudaMalloc(&s.d_raw[k], ND * 4));
         CK(cudaMalloc(&s.d_D[k], ND * 4));
-        CK(cudaMallocHost(&s.h_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
+        CK(cudaMalloc(&s.d_planes[k], (size_t)c->tri_cap * 24));
     }
+    const size_t table_ints = 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap);
+    CK(cudaMalloc(&s.d_tables, table_ints * 4));
+    CK(cudaMallocHost(&s.h_tables, table_ints * 4));
+    CK(cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CK(cudaMalloc(&s.d_dcan, (size_t)g.Wc * g.Hc * 2));
-    CK(cudaMalloc(&s.d_support, (size_t)c->support_cap * 12));
     CK(cudaMalloc(&s.d_grid_scratch, 2 * cells * 4));
     CK(cudaMalloc(&s.d_tmp, 2 * ND * 4));
     CK(cudaMalloc(&s.d_parent, ND * 4));
     CK(cudaMalloc(&s.d_size, ND * 4));
     CK(cudaMallocHost(&s.h_dcan, (size_t)g.Wc * g.Hc * 2));
-    CK(cudaMallocHost(&s.h_support, (size_t)c->support_cap * 12));
     return ELAS_B200_OK;
 }
 
@@ -233,6 +246,26 @@ std::vector<uint8_t> expand_grid(const FrameGeom& g, const std::vector<uint8_t>&
     return out;
 }
 
+int32_t wait_stream(elas_b200_ctx* c, Slot& s)
+{
+    if (c->blocking_sync) {
+        CK(cudaEventRecord(s.ev_sync, s.stream));
+        CK(cudaEventSynchronize(s.ev_sync));
+    } else {
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    return ELAS_B200_OK;
+}
+
+// elas.cpp:35-56: W bytes of every row go into the 16-byte-aligned zero-padded copy; when the caller's
+// pitch already equals that padded pitch the reference memcpy's the whole block (:44-48) -- one 1-D copy
+int32_t copy_image_in(const FrameGeom& g, uint8_t* dst, const uint8_t* src, int pitch, cudaStream_t st)
+{
+    if (pitch == g.bpl) CK(cudaMemcpyAsync(dst, src, (size_t)g.bpl * g.H, cudaMemcpyDefault, st));
+    else CK(cudaMemcpy2DAsync(dst, g.bpl, src, pitch, g.W, g.H, cudaMemcpyDefault, st));
+    return ELAS_B200_OK;
+}
+
 // ---- one frame through one slot ----------------------------------------------------------------
 
 int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool device_io)
@@ -261,17 +294,19 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         cudaEventRecord(s.timer.begin, st);
     }
 
+    const long long t0 = now_ns();
     // ---- phase A: images in, descriptors, support search, lattice out --------------------------
-    // elas.cpp:35-56: W bytes of every row into the 16-byte-aligned zero-padded copy
-    CK(cudaMemcpy2DAsync(s.d_img[0], g.bpl, I1, bytes_per_line, g.W, g.H, cudaMemcpyDefault, st));
-    CK(cudaMemcpy2DAsync(s.d_img[1], g.bpl, I2, bytes_per_line, g.W, g.H, cudaMemcpyDefault, st));
+    if (int32_t rc = copy_image_in(g, s.d_img[0], I1, bytes_per_line, st)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[1], I2, bytes_per_line, st)) return rc;
     mark(c, s, "copy_in");
     launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
     mark(c, s, "descriptor");
     launch_support(g, p, s.d_desc[0], s.d_desc[1], s.d_dcan, st);
     mark(c, s, "support");
     CK(cudaMemcpyAsync(s.h_dcan, s.d_dcan, (size_t)g.Wc * g.Hc * 2, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const long long t1 = now_ns();
+    if (int32_t rc = wait_stream(c, s)) return rc;
+    const long long t2 = now_ns();
     if (s.capture) {
         if (int32_t rc = grab(s, "desc1", s.d_desc[0], N * 16)) return rc;
         if (int32_t rc = grab(s, "desc2", s.d_desc[1], N * 16)) return rc;
@@ -281,7 +316,7 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     }
 
     // ---- host stage ---------------------------------------------------------------------------
-    const int n = s.host.run(g, p, s.h_dcan, s.capture);
+    const int n = s.host.run(g, p, s.h_dcan, s.capture, false);
     if (s.capture) {
         grab_host(s, "dcan_incon", s.host.dcan_incon.data(), s.host.dcan_incon.size() * 2);
         grab_host(s, "dcan", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
@@ -291,29 +326,34 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         if (int32_t rc = fill_invalid(c, s, D1, D2, device_io)) return rc;
         return ELAS_B200_E_FEW_SUPPORT;
     }
-    if (n > c->support_cap) return ELAS_B200_E_BAD_ARG;
-    std::memcpy(s.h_support, s.host.support.data(), (size_t)n * 12);
-    for (int k = 0; k < 2; k++) {
-        s.n_tri[k] = (int)s.host.raster[k].size();
-        if (s.n_tri[k] > c->tri_cap) return ELAS_B200_E_BAD_ARG;
-        std::memcpy(s.h_tri[k], s.host.raster[k].data(), (size_t)s.n_tri[k] * sizeof(TriRaster));
-    }
+    const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
+    if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap) return ELAS_B200_E_BAD_ARG;
+    s.n_tri[0] = nt1; s.n_tri[1] = nt2;
+    std::memcpy(s.h_tables, s.host.support.data(), (size_t)n * 12);
+    std::memcpy(s.h_tables + 3 * n, s.host.tri[0].data(), (size_t)nt1 * 12);
+    std::memcpy(s.h_tables + 3 * (n + nt1), s.host.tri[1].data(), (size_t)nt2 * 12);
+    const int32_t* d_support = s.d_tables;
+    const int32_t* d_tri1 = s.d_tables + 3 * n;
+    const int32_t* d_tri2 = s.d_tables + 3 * (n + nt1);
     if (s.capture) {
         grab_host(s, "tri1", s.host.tri[0].data(), s.host.tri[0].size() * 4);
         grab_host(s, "tri2", s.host.tri[1].data(), s.host.tri[1].size() * 4);
-        grab_host(s, "planes1", s.host.planes[0].data(), s.host.planes[0].size() * 4);
-        grab_host(s, "planes2", s.host.planes[1].data(), s.host.planes[1].size() * 4);
         int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
         grab_host(s, "grid_dims", gd, sizeof gd);
     }
 
+    const long long t3 = now_ns();
     // ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------
     if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
-    CK(cudaMemcpyAsync(s.d_support, s.h_support, (size_t)n * 12, cudaMemcpyHostToDevice, st));
-    for (int k = 0; k < 2; k++)
-        CK(cudaMemcpyAsync(s.d_tri[k], s.h_tri[k], (size_t)s.n_tri[k] * sizeof(TriRaster), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (size_t)(n + nt1 + nt2) * 12, cudaMemcpyHostToDevice, st));
     mark(c, s, "tables_in");
-    launch_grid(g, p, s.d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], st);
+    launch_planes(d_support, d_tri1, nt1, d_tri2, nt2, s.d_tri[0], s.d_tri[1], s.d_planes[0], s.d_planes[1], st);   // elas.cpp:87-88
+    mark(c, s, "planes");
+    if (s.capture) {
+        if (int32_t rc = grab(s, "planes1", s.d_planes[0], (size_t)nt1 * 24)) return rc;
+        if (int32_t rc = grab(s, "planes2", s.d_planes[1], (size_t)nt2 * 24)) return rc;
+    }
+    launch_grid(g, p, d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], st);
     mark(c, s, "grid");
     launch_raster(g, p.subsampling, s.d_tri[0], s.n_tri[0], s.d_tri[1], s.n_tri[1], s.d_map[0], s.d_map[1], st);
     mark(c, s, "raster");
@@ -362,8 +402,12 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     CK(cudaMemcpyAsync(D1, s.d_D[0], ND * 4, cudaMemcpyDefault, st));
     CK(cudaMemcpyAsync(D2, s.d_D[1], ND * 4, cudaMemcpyDefault, st));
     mark(c, s, "copy_out");
-    CK(cudaStreamSynchronize(st));
+    const long long t4 = now_ns();
+    if (int32_t rc = wait_stream(c, s)) return rc;
     CK(cudaGetLastError());
+    const long long t5 = now_ns();
+    c->ns_submit_a += t1 - t0; c->ns_wait_a += t2 - t1; c->ns_host += t3 - t2;
+    c->ns_submit_b += t4 - t3; c->ns_wait_b += t5 - t4; c->frames += 1;
     if (s.capture) {
         if (int32_t rc = grab(s, "D1", s.d_D[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2", s.d_D[1], ND * 4)) return rc;
@@ -509,6 +553,12 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
     c->launches_at_create = launches_issued();
+    {
+        // spinning waits are the fastest while every slot's worker has a core of its own
+        const unsigned cores = std::thread::hardware_concurrency();
+        c->blocking_sync = cores > 0 && (unsigned)n_slots > cores;
+        if (const char* e = std::getenv("ELAS_B200_BLOCKING_SYNC")) c->blocking_sync = std::atoi(e) != 0;
+    }
     for (int i = 0; i < n_slots; i++) {
         c->slots.emplace_back(new Slot);
         if (int32_t rc = alloc_slot(c.get(), *c->slots.back())) {
@@ -628,7 +678,7 @@ int32_t elas_b200_host_stage(const elas_b200_params* p, int32_t width, int32_t h
     if (!p || !dcan || !support || !tri1 || !tri2 || !planes1 || !planes2 || !n_out) return ELAS_B200_E_BAD_ARG;
     const FrameGeom g = make_geom(*p, width, height);
     HostStage hs;
-    const int n = hs.run(g, *p, dcan, false);
+    const int n = hs.run(g, *p, dcan, false, true);
     n_out[0] = n; n_out[1] = (int)hs.tri[0].size() / 3; n_out[2] = (int)hs.tri[1].size() / 3;
     if (n > support_cap || n_out[1] > tri_cap || n_out[2] > tri_cap) return ELAS_B200_E_BAD_ARG;
     std::memcpy(support, hs.support.data(), hs.support.size() * 4);
@@ -643,6 +693,16 @@ int32_t elas_b200_host_stage(const elas_b200_params* p, int32_t width, int32_t h
 int64_t elas_b200_launch_count(elas_b200_ctx* c)
 {
     return c ? launches_issued() - c->launches_at_create : launches_issued();
+}
+
+int32_t elas_b200_host_times(elas_b200_ctx* c, double ms_out[5], int64_t* frames, int32_t reset)
+{
+    if (!c || !ms_out) return ELAS_B200_E_BAD_ARG;
+    ms_out[0] = c->ns_submit_a * 1e-6; ms_out[1] = c->ns_wait_a * 1e-6; ms_out[2] = c->ns_host * 1e-6;
+    ms_out[3] = c->ns_submit_b * 1e-6; ms_out[4] = c->ns_wait_b * 1e-6;
+    if (frames) *frames = c->frames;
+    if (reset) { c->ns_submit_a = 0; c->ns_wait_a = 0; c->ns_host = 0; c->ns_submit_b = 0; c->ns_wait_b = 0; c->frames = 0; }
+    return ELAS_B200_OK;
 }
 
 int32_t elas_b200_stage_timing(elas_b200_ctx* c, int32_t enable)

@@ -601,7 +601,7 @@ void raster_records(const std::vector<int32_t>& sup, const std::vector<int32_t>&
 
 }  // namespace
 
-int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages)
+int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages, bool with_planes)
 {
     remove_inconsistent(p, dcan, g.Wc, g.Hc);                     // elas.cpp:496
     if (keep_stages) dcan_incon.assign(dcan, dcan + (size_t)g.Wc * g.Hc);
@@ -626,8 +626,10 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
             py_[i] = support[3 * i + 1];
         }
         delaunay_.run(px_.data(), py_.data(), n_support, tri[k]);
-        disparity_planes(support, tri[k], planes[k]);             // :87-88
-        raster_records(support, tri[k], planes[k], k, raster[k]);
+        if (with_planes) {
+            disparity_planes(support, tri[k], planes[k]);         // :87-88
+            raster_records(support, tri[k], planes[k], k, raster[k]);
+        }
     }
     return n_support;
 }

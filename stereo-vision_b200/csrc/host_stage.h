@@ -70,7 +70,9 @@ struct HostStage {
 
     // dcan: the candidate lattice [Hc][Wc] as produced by K2; filtered in place.
     // Returns the number of support points (callers stop at < 3, elas.cpp:69-75).
-    int run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages);
+    // with_planes: also fit the disparity planes and raster records on the host (the frame path does
+    // that on the device, k_planes; the host version serves elas_b200_host_stage and its CPU tests).
+    int run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages, bool with_planes);
 
 private:
     Triangulator delaunay_;

@@ -72,6 +72,97 @@ __global__ void k_grid_diffuse(FrameGeom g, const uint32_t* __restrict__ scratch
     list[0] = count <= kGridListCap ? (uint16_t)count : (uint16_t)0xFFFF;
 }
 
+// Disparity planes (elas.cpp:605-680) and the per-triangle set-up of computeDisparity
+// (elas.cpp:1006-1072), one thread per triangle of either image.  Matrix::solve (matrix.cpp:414-502)
+// is Gauss-Jordan elimination with full pivoting in double precision; it is restated with explicit
+// round-to-nearest intrinsics so that no multiply-add is contracted: the reference is x86-64 SSE2
+// code, every operation rounds separately, and the planes must come out bit-identical.
+__device__ bool solve3(double A[3][3], double b[3])
+{
+    int ipiv[3] = {0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) {
+        double big = 0.0;
+        int irow = 0, icol = 0;
+        for (int j = 0; j < 3; j++)
+            if (ipiv[j] != 1)
+                for (int k = 0; k < 3; k++)
+                    if (ipiv[k] == 0 && fabs(A[j][k]) >= big) { big = fabs(A[j][k]); irow = j; icol = k; }
+        ++ipiv[icol];
+        if (irow != icol) {
+            for (int l = 0; l < 3; l++) { const double t = A[irow][l]; A[irow][l] = A[icol][l]; A[icol][l] = t; }
+            const double t = b[irow]; b[irow] = b[icol]; b[icol] = t;
+        }
+        if (fabs(A[icol][icol]) < 1e-20) return false;
+        const double pivinv = __ddiv_rn(1.0, A[icol][icol]);
+        A[icol][icol] = 1.0;
+        for (int l = 0; l < 3; l++) A[icol][l] = __dmul_rn(A[icol][l], pivinv);
+        b[icol] = __dmul_rn(b[icol], pivinv);
+        for (int ll = 0; ll < 3; ll++)
+            if (ll != icol) {
+                const double dum = A[ll][icol];
+                A[ll][icol] = 0.0;
+                for (int l = 0; l < 3; l++) A[ll][l] = __dsub_rn(A[ll][l], __dmul_rn(A[icol][l], dum));
+                b[ll] = __dsub_rn(b[ll], __dmul_rn(b[icol], dum));
+            }
+    }
+    return true;
+}
+
+__global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __restrict__ tri1, int nt1,
+                         const int32_t* __restrict__ tri2, int nt2, TriRaster* __restrict__ out1,
+                         TriRaster* __restrict__ out2, float* __restrict__ planes1, float* __restrict__ planes2)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int right_image = i >= nt1;
+    if (right_image) { i -= nt1; if (i >= nt2) return; }
+    const int32_t* tri = (right_image ? tri2 : tri1) + 3 * i;
+    int su[3], sv[3], sd[3];
+    for (int c = 0; c < 3; c++) {
+        const int32_t* s = support + 3 * (size_t)tri[c];
+        su[c] = s[0]; sv[c] = s[1]; sd[c] = s[2];
+    }
+    float pl[6];
+    for (int k = 0; k < 2; k++) {                        // k = 0: left coordinates (t1), k = 1: right (t2)
+        double A[3][3], b[3];
+        for (int c = 0; c < 3; c++) {
+            A[c][0] = k ? su[c] - sd[c] : su[c];
+            A[c][1] = sv[c];
+            A[c][2] = 1.0;
+            b[c] = sd[c];
+        }
+        const bool ok = solve3(A, b);
+        for (int c = 0; c < 3; c++) pl[3 * k + c] = ok ? __double2float_rn(b[c]) : 0.f;
+    }
+    float* po = (right_image ? planes2 : planes1) + 6 * (size_t)i;
+    for (int c = 0; c < 6; c++) po[c] = pl[c];
+
+    TriRaster r;
+    const float pd = right_image ? pl[0] : pl[3];
+    r.pa = right_image ? pl[3] : pl[0];
+    r.pb = right_image ? pl[4] : pl[1];
+    r.pc = right_image ? pl[5] : pl[2];
+    float tu[3], tv[3];
+    for (int c = 0; c < 3; c++) { tu[c] = right_image ? (float)(su[c] - sd[c]) : (float)su[c]; tv[c] = (float)sv[c]; }
+    // the reference's 3-element bubble sort by u (elas.cpp:1043-1053), unrolled: (1,0) (2,0) (2,1)
+#define ELASB_SWAP_IF(k, j) if (tu[k] > tu[j]) { float t_ = tu[j]; tu[j] = tu[k]; tu[k] = t_; t_ = tv[j]; tv[j] = tv[k]; tv[k] = t_; }
+    ELASB_SWAP_IF(0, 1) ELASB_SWAP_IF(0, 2) ELASB_SWAP_IF(1, 2)
+#undef ELASB_SWAP_IF
+    const float Au = tu[0], Av = tv[0], Bu = tu[1], Bv = tv[1], Cu = tu[2], Cv = tv[2];
+    float ABa = 0.f, ACa = 0.f, BCa = 0.f;               // :1061-1067
+    if ((int)Au != (int)Bu) ABa = __fdiv_rn(__fsub_rn(Av, Bv), __fsub_rn(Au, Bu));
+    if ((int)Au != (int)Cu) ACa = __fdiv_rn(__fsub_rn(Av, Cv), __fsub_rn(Au, Cu));
+    if ((int)Bu != (int)Cu) BCa = __fdiv_rn(__fsub_rn(Bv, Cv), __fsub_rn(Bu, Cu));
+    r.ABa = ABa; r.ACa = ACa; r.BCa = BCa;
+    r.ABb = __fsub_rn(Av, __fmul_rn(ABa, Au));
+    r.ACb = __fsub_rn(Av, __fmul_rn(ACa, Au));
+    r.BCb = __fsub_rn(Bv, __fmul_rn(BCa, Bu));
+    r.uA = (int)Au; r.uB = (int)Bu; r.uC = (int)Cu;
+    r.valid = (double)fabsf(r.pa) < 0.7 && (double)fabsf(pd) < 0.7;     // :1072
+    r.pad0 = r.pad1 = r.pad2 = 0;
+    (right_image ? out2 : out1)[i] = r;
+}
+
 // Scan conversion of one triangle per warp (elas.cpp:1074-1114): lanes take the columns u of both
 // halves (A->B, B->C), v runs over the half-open range [min(v1,v2), max(v1,v2)) with
 //   v1 = (uint32_t)(AC_a*u + AC_b),  v2 = (uint32_t)(AB_a*u + AB_b)   (separate mul and add, no FMA;
@@ -123,6 +214,15 @@ void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* s
     }
     const int cells2 = 2 * g.gw * g.gh;
     k_grid_diffuse<<<(cells2 + 127) / 128, 128, 0, s>>>(g, scratch, grid1, grid2, lists1, lists2);
+    count_launch();
+}
+
+void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const int32_t* tri2, int nt2,
+                   TriRaster* out1, TriRaster* out2, float* planes1, float* planes2, cudaStream_t s)
+{
+    const int total = nt1 + nt2;
+    if (total <= 0) return;
+    k_planes<<<(total + 127) / 128, 128, 0, s>>>(support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
     count_launch();
 }
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "elas_b200_create", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
-    "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_time_matching",
+    "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
     "elas_b200_version", "elas_b200_device_count",
 ]
 
@@ -88,6 +88,7 @@ def load_library():
     lib.elas_b200_launch_count.restype = C.c_int64
     lib.elas_b200_stage_timing.argtypes = [C.c_void_p, C.c_int32]
     lib.elas_b200_stage_times.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int32]
+    lib.elas_b200_host_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     lib.elas_b200_time_matching.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.elas_b200_time_matching.restype = C.c_float
     lib.elas_b200_version.restype = C.c_char_p
@@ -249,6 +250,15 @@ class ElasB200:
         ms = (C.c_float * 32)()
         n = self.lib.elas_b200_stage_times(self.ctx, slot, names, ms, 32)
         return [(names[i].decode(), float(ms[i])) for i in range(max(n, 0))]
+
+    def host_times(self, reset=True):
+        """Per-frame host wall time by phase (ms): submit A, wait A, host stage, submit B, wait B."""
+        ms = (C.c_double * 5)()
+        frames = C.c_int64(0)
+        self.lib.elas_b200_host_times(self.ctx, ms, C.byref(frames), 1 if reset else 0)
+        n = max(frames.value, 1)
+        names = ["submit_a", "wait_a", "host_stage", "submit_b", "wait_b"]
+        return {k: ms[i] / n for i, k in enumerate(names)}, frames.value
 
     def time_matching(self, iters=20, flush_l2=True, slot=0):
         ms = float(self.lib.elas_b200_time_matching(self.ctx, slot, iters, 1 if flush_l2 else 0))
