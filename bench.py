@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = from host core count)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-4k", action="store_true", help="skip the 4096x2160 roofline point of the matching kernel")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +199,7 @@ def main():
     import torch
     import torch.distributed as dist
     import elas_b200
+    import sharding
     import synth
 
     if not torch.cuda.is_available():
@@ -208,11 +210,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # the one collective of the path: rank 0's parameter block to every rank (NCCL broadcast)
-    params = elas_b200.stereomapper(DMAX)
-    blob = torch.frombuffer(bytearray(bytes(params)), dtype=torch.uint8).to(dev)
-    if world > 1:
-        dist.broadcast(blob, src=0)
-    params = elas_b200.Params.from_buffer_copy(bytes(blob.cpu().numpy().tobytes()))
+    params = sharding.broadcast_params(elas_b200.stereomapper(DMAX), dev, src=0)
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     slots = args.slots or max(2, min(16, cores // max(world, 1)))
@@ -283,10 +281,7 @@ def main():
     # parity guard inside the bench: device-resident and host paths must give identical maps
     same = bool(torch.equal(d_D.cpu(), h_D))
 
-    t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev_max, ms_host_max = float(t[0]), float(t[1])
+    ms_dev_max, ms_host_max = sharding.max_over_ranks([ms_dev, ms_host], dev)
 
     # roofline of the matching kernel: isolated launches cycling over all slots' tables (their
     # combined descriptors exceed L2), CUDA events on the launching stream, L2 flushed first
@@ -294,6 +289,24 @@ def main():
     peak, peak_src = measured_hbm_peak()
     b_match = algorithmic_bytes_matching(W, H, DMAX)
     achieved = b_match / (k7_ms * 1e-3) / 1e9
+
+    engine.close()
+
+    # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
+    # (683 MB algorithmic) does not fit L2, so this is the honest HBM-roofline point of the same kernel
+    roof_4k = None
+    if rank == 0 and world == 1 and not args.no_4k:
+        W4, H4, D4 = 4096, 2160, 256
+        L4, R4, _ = synth.synthetic_pair(W4, H4, D4, seed=0)
+        e4 = elas_b200.ElasB200(elas_b200.stereomapper(D4), W4, H4, n_slots=1, device=local_rank)
+        e4.process(L4, R4)
+        ms4 = e4.time_matching(iters=20, flush_l2=True)
+        e4.close()
+        b4 = algorithmic_bytes_matching(W4, H4, D4)
+        a4 = b4 / (ms4 * 1e-3) / 1e9
+        roof_4k = {"workload": f"synthetic {W4}x{H4}, d_max={D4}", "bound": "hbm", "achieved": round(a4, 1), "peak": peak,
+                   "unit": "GB/s", "frac": round(a4 / peak, 4), "algorithmic_bytes_per_launch": b4,
+                   "ms_per_launch": round(ms4, 5)}
 
     if rank == 0:
         cpu = None
@@ -322,12 +335,12 @@ def main():
                          "frac": round(achieved / peak, 4), "traffic": None,
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
                          "peak_source": peak_src},
+            "roofline_bandwidth_config": roof_4k,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},
         }
         print(json.dumps(line), flush=True)
-    engine.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -656,7 +656,7 @@ static void d_recurse(dmesh* m, int* s, int n, int axis, otri* farleft, otri* fa
  */
 int32_t oracle_delaunay(const int32_t* sup, int32_t n, int32_t right_image, int32_t* tri_out, int32_t cap)
 {
-    if (n < 2) return 0;
+    if (n < 3) return 0;            /* never reached from process(): elas.cpp:69-75 */
     int32_t* x = (int32_t*)malloc(sizeof(int32_t) * n);
     int32_t* y = (int32_t*)malloc(sizeof(int32_t) * n);
     int* s = (int*)malloc(sizeof(int) * n);

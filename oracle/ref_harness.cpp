@@ -263,6 +263,7 @@ int32_t ref_stage_read(const char* name, void* dst, int64_t cap)
 // count and writes up to cap triangles (3 indices each).
 int32_t ref_delaunay(const int32_t* sup, int32_t n, int32_t right_image, int32_t* tri_out, int32_t cap)
 {
+    if (n < 3) return 0;     // Triangle exit()s below three vertices; Elas::process never gets there (elas.cpp:69-75)
     elas_b200_params dp; ref_default_params(&dp, 0);
     Elas e(to_ref(&dp));
     std::vector<Elas::support_pt> s;

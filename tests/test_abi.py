@@ -97,3 +97,57 @@ def test_host_stage_random_lattices_match_oracle(lib, oracle):
         if len(sup) >= 3:
             for right, key in ((0, "tri1"), (1, "tri2")):
                 assert np.array_equal(mine[key], oracle.delaunay(sup, right)), (it, key)
+
+
+def test_drop_in_class_compiles_and_refuses_without_device(lib, tmp_path):
+    """The C++ drop-in Elas class builds against its own header with the reference call-site code, and
+    without a GPU it reports the failure and marks the maps invalid instead of computing on the CPU."""
+    import subprocess
+    src = os.path.join(ROOT, "stereo-vision_b200", "dropin", "libelas", "src")
+    exe = str(tmp_path / "dropin_demo")
+    subprocess.check_call(["g++", "-O2", "-std=c++11", "-Wall", "-I" + src, os.path.join(ROOT, "tests", "dropin_demo.cpp"),
+                           os.path.join(src, "elas.cpp"), os.path.join(src, "descriptor.cpp"), "-ldl", "-o", exe])
+    if lib.elas_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    L, R, _ = synth.synthetic_pair(160, 100, 31, 0)
+    L.tofile(str(tmp_path / "l.raw")); R.tofile(str(tmp_path / "r.raw"))
+    env = dict(os.environ, ELAS_B200_LIB=elas_b200.LIB_PATH)
+    r = subprocess.run([exe, "stereomapper", "160", "100", "31", str(tmp_path / "l.raw"), str(tmp_path / "r.raw"),
+                        str(tmp_path / "d1.out"), str(tmp_path / "d2.out")], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "elas_b200_process failed" in r.stderr
+    assert (np.fromfile(str(tmp_path / "d1.out"), np.float32) == -10).all()
+
+
+def test_drop_in_header_matches_reference_header(tmp_path):
+    """Field order, types and preset values of Elas::parameters are those of the reference header."""
+    import subprocess
+    ref_hdr = "/root/reference/libelas/src"
+    if not os.path.isdir(ref_hdr):
+        pytest.skip("/root/reference not present")
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "elas.h"
+#define F(x) printf("%s %zu %zu ", #x, offsetof(Elas::parameters, x), sizeof(((Elas::parameters*)0)->x))
+int main() {
+  F(disp_min); F(disp_max); F(support_threshold); F(support_texture); F(candidate_stepsize); F(incon_window_size);
+  F(incon_threshold); F(incon_min_support); F(add_corners); F(grid_size); F(beta); F(gamma); F(sigma); F(sradius);
+  F(match_texture); F(lr_threshold); F(speckle_sim_threshold); F(speckle_size); F(ipol_gap_width); F(filter_median);
+  F(filter_adaptive_mean); F(postprocess_only_left); F(subsampling);
+  printf("size %zu\n", sizeof(Elas::parameters));
+  for (int s = 0; s < 2; s++) { Elas::parameters p(s ? Elas::MIDDLEBURY : Elas::ROBOTICS);
+    printf("%d %d %.6f %d %d %d %d %d %d %d %.6f %.6f %.6f %.6f %d %d %.6f %d %d %d %d %d %d\n", p.disp_min, p.disp_max,
+      p.support_threshold, p.support_texture, p.candidate_stepsize, p.incon_window_size, p.incon_threshold,
+      p.incon_min_support, (int)p.add_corners, p.grid_size, p.beta, p.gamma, p.sigma, p.sradius, p.match_texture,
+      p.lr_threshold, p.speckle_sim_threshold, p.speckle_size, p.ipol_gap_width, (int)p.filter_median,
+      (int)p.filter_adaptive_mean, (int)p.postprocess_only_left, (int)p.subsampling); }
+  return 0; }
+'''
+    (tmp_path / "layout.cpp").write_text(prog)
+    mine = os.path.join(ROOT, "stereo-vision_b200", "dropin", "libelas", "src")
+    outs = []
+    for inc, extra in ((ref_hdr, []), (mine, [os.path.join(mine, "elas.cpp"), "-ldl"])):
+        exe = str(tmp_path / ("layout_" + ("ref" if inc == ref_hdr else "mine")))
+        subprocess.check_call(["g++", "-std=c++11", "-msse3", "-w", "-I" + inc, str(tmp_path / "layout.cpp")] + extra + ["-o", exe])
+        outs.append(subprocess.check_output([exe], text=True))
+    assert outs[0] == outs[1]

@@ -77,6 +77,10 @@ CASES = [
     ("ragged-333x131", 333, 131, 63, 2, lambda d: checkers.stereomapper(d)),
     ("dmin3", 320, 160, 63, 6, lambda d: checkers.stereomapper(d).copy(disp_min=3)),
     ("dmax-not-multiple-of-32", 400, 180, 100, 9, lambda d: checkers.demo(d)),
+    ("subsampling", 416, 200, 95, 3, lambda d: checkers.stereomapper(d).copy(subsampling=1)),
+    ("subsampling-demo-odd-size", 417, 201, 95, 13, lambda d: checkers.demo(d).copy(subsampling=1)),
+    ("middlebury-preset", 320, 160, 63, 4, lambda d: checkers.middlebury().copy(disp_max=d)),
+    ("robotics+median", 320, 160, 63, 5, lambda d: checkers.demo(d).copy(filter_median=1)),
     ("wide-4096x160-d256-ten-segments", 4096, 160, 256, 12, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255", 1242, 375, 255, 0, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255-seed1-demo", 1242, 375, 255, 1, lambda d: checkers.demo(d)),
@@ -177,3 +181,26 @@ def test_reference_available_on_box_matches(ref):
     _, R1, R2 = ref.process(L, R, p)
     rc, D1, D2 = elas_b200.process(L, R, as_product_params(p))
     assert rc == 0 and bits_equal(D1, R1) and bits_equal(D2, R2)
+
+
+def test_cpp_drop_in_class_matches_oracle(oracle, tmp_path):
+    """The C++ drop-in `Elas` class (stereo-vision_b200/dropin/libelas/src), compiled into a headless
+    stand-in for the reference's call sites (stereothread.cpp:76-114, main.cpp:61-64), gives the
+    oracle's maps bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "stereo-vision_b200", "dropin", "libelas", "src")
+    exe = str(tmp_path / "dropin_demo")
+    subprocess.check_call(["g++", "-O2", "-std=c++11", "-I" + src, os.path.join(root, "tests", "dropin_demo.cpp"),
+                           os.path.join(src, "elas.cpp"), os.path.join(src, "descriptor.cpp"), "-ldl", "-o", exe])
+    W, H, dmax = 640, 240, 127
+    L, R, _ = synth.synthetic_pair(W, H, dmax, 21)
+    L.tofile(str(tmp_path / "l.raw")); R.tofile(str(tmp_path / "r.raw"))
+    env = dict(os.environ, ELAS_B200_LIB=elas_b200.LIB_PATH)
+    for mode, p in (("stereomapper", checkers.stereomapper(dmax)), ("demo", checkers.demo(dmax))):
+        subprocess.check_call([exe, mode, str(W), str(H), str(dmax), str(tmp_path / "l.raw"), str(tmp_path / "r.raw"),
+                               str(tmp_path / "d1.out"), str(tmp_path / "d2.out")], env=env)
+        D1 = np.fromfile(str(tmp_path / "d1.out"), np.float32).reshape(H, W)
+        D2 = np.fromfile(str(tmp_path / "d2.out"), np.float32).reshape(H, W)
+        _, O1, O2 = oracle.process(L, R, p)
+        assert bits_equal(D1, O1) and bits_equal(D2, O2), mode
