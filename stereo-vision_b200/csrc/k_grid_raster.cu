@@ -163,12 +163,15 @@ __global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __r
     (right_image ? out2 : out1)[i] = r;
 }
 
-// Scan conversion of one triangle per warp (elas.cpp:1074-1114): lanes take the columns u of both
-// halves (A->B, B->C), v runs over the half-open range [min(v1,v2), max(v1,v2)) with
+// Scan conversion of one triangle per warp (elas.cpp:1074-1114).  The reference walks the columns u of
+// both halves (A->B, B->C) and, per column, the half-open row range [min(v1,v2), max(v1,v2)) with
 //   v1 = (uint32_t)(AC_a*u + AC_b),  v2 = (uint32_t)(AB_a*u + AB_b)   (separate mul and add, no FMA;
 // the x86-64 conversion truncates through 64 bits, i.e. trunc toward zero for the values met here).
-// The reference lets later triangles overwrite earlier ones; atomicMax on the triangle index gives
-// the same winner (findMatch's early returns depend on the pixel only, never on the triangle).
+// Here each lane owns a column (32 columns per pass), computes its row range once, and the warp then
+// sweeps the rows of the triangle's bounding box together: every store instruction touches one row
+// segment (coalesced) and the loop bounds are warp-uniform.  The reference lets later triangles
+// overwrite earlier ones; atomicMax on the triangle index gives the same winner (findMatch's early
+// returns depend on the pixel only, never on the triangle).
 __global__ void __launch_bounds__(256)
 k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int nt1,
          const TriRaster* __restrict__ tri2, int nt2, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
@@ -179,23 +182,30 @@ k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int n
     const TriRaster* tri; int32_t* map;
     if (t < nt1) { tri = tri1 + t; map = map1; }
     else { t -= nt1; if (t >= nt2) return; tri = tri2 + t; map = map2; }
-    const float ACa = tri->ACa, ACb = tri->ACb;
-    const int uA = tri->uA, uB = tri->uB, uC = tri->uC;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int ua = half ? uB : uA, ub = half ? uC : uB;
-        if (ua == ub) continue;                                                   // :1075, :1096
-        const float ea = half ? tri->BCa : tri->ABa, eb = half ? tri->BCb : tri->ABb;
-        for (int u = max(ua, 0) + lane; u < min(ub, g.W); u += 32) {              // :1077, :1098
-            if (subsampling && (u & 1)) continue;
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(tri));          // ACa, ACb, ABa, ABb
+    const float4 e1 = __ldg(reinterpret_cast<const float4*>(tri) + 1);      // BCa, BCb, uA, uB
+    const int uA = __float_as_int(e1.z), uB = __float_as_int(e1.w), uC = __ldg(&tri->uC);
+    const int u_begin = max(uA, 0), u_end = min(uC, g.W);                   // :1077, :1098
+    for (int u0 = u_begin; u0 < u_end; u0 += 32) {
+        const int u = u0 + lane;
+        int lo = 0, hi = 0;
+        if (u < u_end && !(subsampling && (u & 1))) {
+            const bool first = u < uB;                                       // A->B part, else B->C part
             const float fu = (float)u;
-            const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(ACa, fu), ACb));    // :1081, :1102
-            const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(ea, fu), eb));      // :1082, :1103
-            const int lo = max(min(v1, v2), 0), hi = min(max(v1, v2), g.H);
-            for (int v = lo; v < hi; v++) {
-                if (subsampling && (v & 1)) continue;
-                atomicMax(map + (size_t)v * pitch + u, t);
-            }
+            const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(e0.x, fu), e0.y));                                  // :1081, :1102
+            const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(first ? e0.z : e1.x, fu), first ? e0.w : e1.y));    // :1082, :1103
+            lo = max(min(v1, v2), 0);
+            hi = min(max(v1, v2), g.H);
+        }
+        int vlo = hi > lo ? lo : g.H, vhi = hi > lo ? hi : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, off));
+            vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, off));
+        }
+        int32_t* col = map + u;
+        for (int v = vlo; v < vhi; v++) {
+            if (v >= lo && v < hi && !(subsampling && (v & 1))) atomicMax(col + (size_t)v * pitch, t);
         }
     }
 }

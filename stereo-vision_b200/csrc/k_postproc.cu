@@ -49,16 +49,25 @@ __device__ __forceinline__ bool seg_conn(float a, float b, float thr)
     return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr;                    // :1281, :1285
 }
 
+// parent[] is read at L2 (ld.global.cg): other SMs hook roots concurrently.
 __device__ __forceinline__ int uf_find(int32_t* parent, int x)
 {
     int p = parent[x];
     while (p != x) {
         const int gp = parent[p];
-        if (gp != p) parent[x] = gp;       // path halving; parents only ever move towards the root
+        if (gp != p) parent[x] = gp;           // path halving
         x = p; p = gp;
     }
     return x;
 }
+
+// Hooking order: a root goes under the root with the smaller PRIORITY, a fixed pseudo-random
+// permutation of the pixel index.  Index order would let the thousands of unions of a frame, which run
+// concurrently, build chains as long as the image is high (every run of a vertical structure hooking
+// under the run above it at the same moment), and every later find would walk them at L2 latency;
+// with random priorities simultaneous hooks only chain along decreasing-priority sequences, whose
+// expected length is logarithmic.
+__device__ __forceinline__ uint32_t uf_priority(int x) { return (uint32_t)x * 0x9E3779B1u; }
 
 __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
 {
@@ -66,8 +75,8 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
         a = uf_find(parent, a);
         b = uf_find(parent, b);
         if (a == b) return;
-        if (a < b) { int t = a; a = b; b = t; }        // hook the larger root under the smaller
-        const int old = atomicMin(parent + a, b);
+        if (uf_priority(a) < uf_priority(b)) { const int t = a; a = b; b = t; }   // hook a (larger priority) under b
+        const int old = atomicCAS(parent + a, a, b);
         if (old == a) return;
         a = old;
     }
@@ -121,7 +130,7 @@ __global__ void k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__
         b_start = !seg_conn(lb, db, thr);
         if (!a_start && !b_start && seg_conn(la, lb, thr)) return;   // the pair to the left joins the same runs
     }
-    uf_union(parent, a_start ? a : parent[a], b_start ? b : parent[b]);
+    uf_union(parent, a_start ? a : __ldcg(parent + a), b_start ? b : __ldcg(parent + b));
 }
 
 __global__ void k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
@@ -134,9 +143,9 @@ __global__ void k_seg_count(int Dw, int Dh, float thr, int speckle, const float*
     if (!(d >= 0.f)) return;
     if (u + 1 < Dw && seg_conn(d, D[a + 1], thr)) return;             // not the last pixel of its run
     const bool is_start = !(u > 0 && seg_conn(D[a - 1], d, thr));
-    const int start = is_start ? a : parent[a];
+    const int start = is_start ? a : __ldcg(parent + a);
     const int root = uf_find(parent, start);
-    parent[start] = root;                                             // every run ends up one hop from its root
+    __stcg(parent + start, root);                                           // every run ends up one hop from its root
     if (__ldcg(size + root) < speckle) atomicAdd(size + root, a - start + 1);
 }
 
