@@ -15,6 +15,8 @@ constexpr int kInvalid = -10;        // elas.cpp:977-980: disparity maps are pre
 constexpr int kGridListStride = 64;
 constexpr int kGridListCap = kGridListStride - 1;
 
+constexpr int kRasterBandRows = 32;   // k_raster work unit: 32 columns x this many rows of a triangle's bounding box
+
 struct FrameGeom;
 // triangle-id maps are int32 [H][map_pitch]: rows padded to 16 bytes so the matching kernel can TMA them
 __host__ __device__ inline int map_pitch_of(int W) { return (W + 3) & ~3; }
@@ -79,8 +81,8 @@ void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* s
 void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const int32_t* tri2, int nt2,
                    TriRaster* out1, TriRaster* out2, float* planes1, float* planes2, cudaStream_t s);
 // triangle-id maps: scan conversion with last-writer-wins (elas.cpp:1074-1114)
-void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
-                   const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s);
+void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, const TriRaster* tri2,
+                   const int32_t* units, int n_units, int32_t* map1, int32_t* map2, cudaStream_t s);
 // K7  dense matching, both images (elas.cpp:814-955, :960-1118)
 void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,

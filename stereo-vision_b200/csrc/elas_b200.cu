@@ -78,6 +78,8 @@ struct Slot {
     // host stage + tables of the last frame (kept for elas_b200_time_matching)
     HostStage host;
     int n_tri[2] = {0, 0};
+    int n_units = 0;
+    size_t units_at = 0;
     bool tables_valid = false;
     // introspection
     bool capture = false;
@@ -91,7 +93,7 @@ struct elas_b200_ctx {
     int device = 0;
     elas_b200_params p{};
     FrameGeom g{};
-    int support_cap = 0, tri_cap = 0;
+    int support_cap = 0, tri_cap = 0, unit_cap = 0;
     int32_t* d_prior = nullptr;
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
@@ -191,7 +193,7 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
         CK(cudaMalloc(&s.d_D[k], ND * 4));
         CK(cudaMalloc(&s.d_planes[k], (size_t)c->tri_cap * 24));
     }
-    const size_t table_ints = 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap);
+    const size_t table_ints = 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap) + 2 * (size_t)c->unit_cap;
     CK(cudaMalloc(&s.d_tables, table_ints * 4));
     CK(cudaMallocHost(&s.h_tables, table_ints * 4));
     CK(cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
@@ -327,11 +329,15 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         return ELAS_B200_E_FEW_SUPPORT;
     }
     const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
-    if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap) return ELAS_B200_E_BAD_ARG;
+    const int n_units = (int)s.host.units.size() / 2;
+    if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap || n_units > c->unit_cap) return ELAS_B200_E_BAD_ARG;
     s.n_tri[0] = nt1; s.n_tri[1] = nt2;
     std::memcpy(s.h_tables, s.host.support.data(), (size_t)n * 12);
     std::memcpy(s.h_tables + 3 * n, s.host.tri[0].data(), (size_t)nt1 * 12);
     std::memcpy(s.h_tables + 3 * (n + nt1), s.host.tri[1].data(), (size_t)nt2 * 12);
+    const size_t units_at = 3 * (size_t)(n + nt1 + nt2) + ((n + nt1 + nt2) & 1);      // 8-byte aligned
+    std::memcpy(s.h_tables + units_at, s.host.units.data(), (size_t)n_units * 8);
+    s.n_units = n_units; s.units_at = units_at;
     const int32_t* d_support = s.d_tables;
     const int32_t* d_tri1 = s.d_tables + 3 * n;
     const int32_t* d_tri2 = s.d_tables + 3 * (n + nt1);
@@ -345,7 +351,7 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     const long long t3 = now_ns();
     // ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------
     if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
-    CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (size_t)(n + nt1 + nt2) * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (units_at + 2 * (size_t)n_units) * 4, cudaMemcpyHostToDevice, st));
     mark(c, s, "tables_in");
     launch_planes(d_support, d_tri1, nt1, d_tri2, nt2, s.d_tri[0], s.d_tri[1], s.d_planes[0], s.d_planes[1], st);   // elas.cpp:87-88
     mark(c, s, "planes");
@@ -355,7 +361,7 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     }
     launch_grid(g, p, d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], st);
     mark(c, s, "grid");
-    launch_raster(g, p.subsampling, s.d_tri[0], s.n_tri[0], s.d_tri[1], s.n_tri[1], s.d_map[0], s.d_map[1], st);
+    launch_raster(g, p.subsampling, s.d_tri[0], s.d_tri[1], s.d_tables + units_at, n_units, s.d_map[0], s.d_map[1], st);
     mark(c, s, "raster");
     launch_matching(g, p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
                     s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1], st);
@@ -545,6 +551,9 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
     c->g = make_geom(*p, width, height);
     c->support_cap = c->g.Wc * c->g.Hc + 6;
     c->tri_cap = 2 * c->support_cap + 8;
+    // raster work units: every triangle is at least one unit; large ones split into 32-column x 32-row
+    // pieces of their bounding boxes (bounded by a few times the image area)
+    c->unit_cap = 2 * c->tri_cap + 8 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
     if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
     // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15

@@ -617,6 +617,7 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
     if (p.add_corners) add_corners(g.W, g.H, support);            // :520-523
     n_support = (int)support.size() / 3;
     for (int k = 0; k < 2; k++) { tri[k].clear(); planes[k].clear(); raster[k].clear(); }
+    units.clear();
     if (n_support < 3) return n_support;                          // :69-75
 
     px_.resize(n_support); py_.resize(n_support);
@@ -626,6 +627,22 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
             py_[i] = support[3 * i + 1];
         }
         delaunay_.run(px_.data(), py_.data(), n_support, tri[k]);
+        // work units: 32-column chunks x kRasterBandRows-row bands of each triangle's bounding box
+        const size_t nt = tri[k].size() / 3;
+        for (size_t t = 0; t < nt; t++) {
+            const int a = tri[k][3 * t], b = tri[k][3 * t + 1], c = tri[k][3 * t + 2];
+            const int u_lo = std::max(std::min(px_[a], std::min(px_[b], px_[c])), 0);
+            const int u_hi = std::min(std::max(px_[a], std::max(px_[b], px_[c])), g.W);      // columns [u_lo, u_hi)
+            // one row of slack below the smallest corner row: an edge line evaluated in float may truncate to it
+            const int v_lo = std::max(std::min(py_[a], std::min(py_[b], py_[c])) - 1, 0);
+            const int v_hi = std::min(std::max(py_[a], std::max(py_[b], py_[c])) + 1, g.H);  // rows [v_lo, v_hi)
+            const int chunks = (u_hi - u_lo + 31) / 32, bands = (v_hi - v_lo + kRasterBandRows - 1) / kRasterBandRows;
+            for (int ch = 0; ch < chunks; ch++)
+                for (int bd = 0; bd < bands; bd++) {
+                    units.push_back((int32_t)t | (k << 30));
+                    units.push_back(ch | (bd << 16));
+                }
+        }
         if (with_planes) {
             disparity_planes(support, tri[k], planes[k]);         // :87-88
             raster_records(support, tri[k], planes[k], k, raster[k]);

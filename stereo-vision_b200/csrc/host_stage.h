@@ -66,6 +66,9 @@ struct HostStage {
     std::vector<int32_t> tri[2];             // (c1,c2,c3) per image
     std::vector<float> planes[2];            // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle
     std::vector<TriRaster> raster[2];
+    // scan-conversion work units for k_raster: {triangle | image << 30, column chunk | row band << 16};
+    // a big triangle becomes several units so that no single warp rasterises a large area alone
+    std::vector<int32_t> units;
     std::vector<int16_t> dcan_incon;         // lattice after removeInconsistentSupportPoints (stage dump)
 
     // dcan: the candidate lattice [Hc][Wc] as produced by K2; filtered in place.

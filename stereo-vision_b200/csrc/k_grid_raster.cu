@@ -159,54 +159,61 @@ __global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __r
     r.BCb = __fsub_rn(Bv, __fmul_rn(BCa, Bu));
     r.uA = (int)Au; r.uB = (int)Bu; r.uC = (int)Cu;
     r.valid = (double)fabsf(r.pa) < 0.7 && (double)fabsf(pd) < 0.7;     // :1072
-    r.pad0 = r.pad1 = r.pad2 = 0;
+    r.pad0 = min(sv[0], min(sv[1], sv[2]));     // smallest corner row: anchor of k_raster's row bands
+    r.pad1 = r.pad2 = 0;
     (right_image ? out2 : out1)[i] = r;
 }
 
-// Scan conversion of one triangle per warp (elas.cpp:1074-1114).  The reference walks the columns u of
-// both halves (A->B, B->C) and, per column, the half-open row range [min(v1,v2), max(v1,v2)) with
+// Scan conversion (elas.cpp:1074-1114), one work unit per warp: 32 columns x kRasterBandRows rows of one
+// triangle's bounding box (units are listed by the host stage, which knows the corner coordinates).
+// The reference walks the columns u of both halves (A->B, B->C) and, per column, the half-open row
+// range [min(v1,v2), max(v1,v2)) with
 //   v1 = (uint32_t)(AC_a*u + AC_b),  v2 = (uint32_t)(AB_a*u + AB_b)   (separate mul and add, no FMA;
 // the x86-64 conversion truncates through 64 bits, i.e. trunc toward zero for the values met here).
-// Here each lane owns a column (32 columns per pass), computes its row range once, and the warp then
-// sweeps the rows of the triangle's bounding box together: every store instruction touches one row
-// segment (coalesced) and the loop bounds are warp-uniform.  The reference lets later triangles
-// overwrite earlier ones; atomicMax on the triangle index gives the same winner (findMatch's early
-// returns depend on the pixel only, never on the triangle).
+// Each lane owns a column and computes its row range once; the warp then sweeps the rows of the band
+// together, so every store instruction touches one row segment (coalesced) with warp-uniform loop
+// bounds.  The reference lets later triangles overwrite earlier ones; atomicMax on the triangle index
+// gives the same winner (findMatch's early returns depend on the pixel only, never on the triangle).
 __global__ void __launch_bounds__(256)
-k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, int nt1,
-         const TriRaster* __restrict__ tri2, int nt2, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
+k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
+         const int2* __restrict__ units, int n_units, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
 {
     const int lane = threadIdx.x & 31;
     const int pitch = map_pitch(g);
-    int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const TriRaster* tri; int32_t* map;
-    if (t < nt1) { tri = tri1 + t; map = map1; }
-    else { t -= nt1; if (t >= nt2) return; tri = tri2 + t; map = map2; }
+    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (unit >= n_units) return;
+    const int2 w = __ldg(units + unit);
+    const int t = w.x & 0x3FFFFFFF, img = (w.x >> 30) & 1, chunk = w.y & 0xFFFF, band = w.y >> 16;
+    const TriRaster* tri = (img ? tri2 : tri1) + t;
+    int32_t* map = img ? map2 : map1;
     const float4 e0 = __ldg(reinterpret_cast<const float4*>(tri));          // ACa, ACb, ABa, ABb
     const float4 e1 = __ldg(reinterpret_cast<const float4*>(tri) + 1);      // BCa, BCb, uA, uB
     const int uA = __float_as_int(e1.z), uB = __float_as_int(e1.w), uC = __ldg(&tri->uC);
-    const int u_begin = max(uA, 0), u_end = min(uC, g.W);                   // :1077, :1098
-    for (int u0 = u_begin; u0 < u_end; u0 += 32) {
-        const int u = u0 + lane;
-        int lo = 0, hi = 0;
-        if (u < u_end && !(subsampling && (u & 1))) {
-            const bool first = u < uB;                                       // A->B part, else B->C part
-            const float fu = (float)u;
-            const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(e0.x, fu), e0.y));                                  // :1081, :1102
-            const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(first ? e0.z : e1.x, fu), first ? e0.w : e1.y));    // :1082, :1103
-            lo = max(min(v1, v2), 0);
-            hi = min(max(v1, v2), g.H);
-        }
-        int vlo = hi > lo ? lo : g.H, vhi = hi > lo ? hi : 0;
+    const int u_end = min(uC, g.W);                                          // :1077, :1098
+    const int u = max(uA, 0) + 32 * chunk + lane;
+    int lo = 0, hi = 0;
+    if (u < u_end && !(subsampling && (u & 1))) {
+        const bool first = u < uB;                                           // A->B part, else B->C part
+        const float fu = (float)u;
+        const int v1 = __float2int_rz(__fadd_rn(__fmul_rn(e0.x, fu), e0.y));                                  // :1081, :1102
+        const int v2 = __float2int_rz(__fadd_rn(__fmul_rn(first ? e0.z : e1.x, fu), first ? e0.w : e1.y));    // :1082, :1103
+        lo = max(min(v1, v2), 0);
+        hi = min(max(v1, v2), g.H);
+    }
+    // rows of this unit: band `band` of the triangle's row range; the band grid is anchored at the
+    // smallest corner row, which bounds every column's range from below
+    int vmin = hi > lo ? lo : g.H, vmax = hi > lo ? hi : 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, off));
-            vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, off));
-        }
-        int32_t* col = map + u;
-        for (int v = vlo; v < vhi; v++) {
-            if (v >= lo && v < hi && !(subsampling && (v & 1))) atomicMax(col + (size_t)v * pitch, t);
-        }
+    for (int off = 16; off > 0; off >>= 1) {
+        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
+        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+    }
+    const int v_anchor = max(__ldg(&tri->pad0) - 1, 0);                      // min corner row - 1 (host_stage.cc units)
+    const int b_lo = v_anchor + band * kRasterBandRows, b_hi = b_lo + kRasterBandRows;
+    const int vlo = max(vmin, b_lo), vhi = min(vmax, b_hi);
+    int32_t* col = map + u;
+    for (int v = vlo; v < vhi; v++) {
+        if (v >= lo && v < hi && !(subsampling && (v & 1))) atomicMax(col + (size_t)v * pitch, t);
     }
 }
 
@@ -236,15 +243,15 @@ void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const i
     count_launch();
 }
 
-void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, int nt1,
-                   const TriRaster* tri2, int nt2, int32_t* map1, int32_t* map2, cudaStream_t s)
+void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, const TriRaster* tri2,
+                   const int32_t* units, int n_units, int32_t* map1, int32_t* map2, cudaStream_t s)
 {
     const size_t bytes = (size_t)map_pitch(g) * g.H * sizeof(int32_t);
     cudaMemsetAsync(map1, 0xFF, bytes, s);      // -1 = not covered by any triangle
     cudaMemsetAsync(map2, 0xFF, bytes, s);
-    const int total = nt1 + nt2;
-    if (total <= 0) return;
-    k_raster<<<(total + 7) / 8, 256, 0, s>>>(g, subsampling, tri1, nt1, tri2, nt2, map1, map2);
+    if (n_units <= 0) return;
+    k_raster<<<(n_units + 7) / 8, 256, 0, s>>>(g, subsampling, tri1, tri2, reinterpret_cast<const int2*>(units),
+                                               n_units, map1, map2);
     count_launch();
 }
 
