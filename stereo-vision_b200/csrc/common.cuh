@@ -47,13 +47,14 @@ static_assert(sizeof(TriRaster) == 64, "TriRaster is one 64-byte record");
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned sad16(const uint4& a, const uint4& b)
 {
-    // VABSDIFF4.U8.ACC x4: sum of |a_i - b_i| over 16 bytes (_mm_sad_epu8 both halves, elas.cpp:787-789)
-    unsigned s = 0;
+    // VABSDIFF4.U8.ACC x4: sum of |a_i - b_i| over 16 bytes (_mm_sad_epu8 both halves, elas.cpp:787-789);
+    // two accumulation chains of two so the XU-pipe latencies overlap
+    unsigned s = 0, t = 0;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.x), "r"(b.x));
-    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.y), "r"(b.y));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(t) : "r"(a.y), "r"(b.y));
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.z), "r"(b.z));
-    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.w), "r"(b.w));
-    return s;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(t) : "r"(a.w), "r"(b.w));
+    return s + t;
 }
 
 // sum |desc[i] - 128| (elas.cpp:358-362, :851-855)

@@ -113,17 +113,24 @@ __global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __r
                          const int32_t* __restrict__ tri2, int nt2, TriRaster* __restrict__ out1,
                          TriRaster* __restrict__ out2, float* __restrict__ planes1, float* __restrict__ planes2)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // two threads per triangle: the even lane fits the plane in left-image coordinates (t1), the odd lane
+    // the one in right-image coordinates (t2); the two solves are the long serial part of this kernel
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = gid & 1;
+    int i = gid >> 1;
+    const bool active = i < nt1 + nt2;
     const int right_image = i >= nt1;
-    if (right_image) { i -= nt1; if (i >= nt2) return; }
-    const int32_t* tri = (right_image ? tri2 : tri1) + 3 * i;
-    int su[3], sv[3], sd[3];
-    for (int c = 0; c < 3; c++) {
-        const int32_t* s = support + 3 * (size_t)tri[c];
-        su[c] = s[0]; sv[c] = s[1]; sd[c] = s[2];
+    if (right_image) i -= nt1;
+    int su[3] = {0, 1, 2}, sv[3] = {0, 0, 1}, sd[3] = {0, 0, 0};
+    if (active) {
+        const int32_t* tri = (right_image ? tri2 : tri1) + 3 * i;
+        for (int c = 0; c < 3; c++) {
+            const int32_t* s = support + 3 * (size_t)tri[c];
+            su[c] = s[0]; sv[c] = s[1]; sd[c] = s[2];
+        }
     }
-    float pl[6];
-    for (int k = 0; k < 2; k++) {                        // k = 0: left coordinates (t1), k = 1: right (t2)
+    float mine[3];
+    {
         double A[3][3], b[3];
         for (int c = 0; c < 3; c++) {
             A[c][0] = k ? su[c] - sd[c] : su[c];
@@ -132,8 +139,15 @@ __global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __r
             b[c] = sd[c];
         }
         const bool ok = solve3(A, b);
-        for (int c = 0; c < 3; c++) pl[3 * k + c] = ok ? __double2float_rn(b[c]) : 0.f;
+        for (int c = 0; c < 3; c++) mine[c] = ok ? __double2float_rn(b[c]) : 0.f;
     }
+    float pl[6];
+    for (int c = 0; c < 3; c++) {
+        const float other = __shfl_xor_sync(0xffffffffu, mine[c], 1);
+        pl[c] = k ? other : mine[c];
+        pl[3 + c] = k ? mine[c] : other;
+    }
+    if (!active || k) return;
     float* po = (right_image ? planes2 : planes1) + 6 * (size_t)i;
     for (int c = 0; c < 6; c++) po[c] = pl[c];
 
@@ -239,7 +253,7 @@ void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const i
 {
     const int total = nt1 + nt2;
     if (total <= 0) return;
-    k_planes<<<(total + 127) / 128, 128, 0, s>>>(support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
+    k_planes<<<(2 * total + 63) / 64, 64, 0, s>>>(support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
     count_launch();
 }
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 struct MatchArgs {
     FrameGeom g;
     int disp_max, match_texture, grid_size, subsampling;
-    int segw, max_cells, map_pitch;
+    int segw, max_cells, map_pitch, variant;
     uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
     const uint4* desc[2];
     const TriRaster* tri[2];
@@ -178,13 +178,25 @@ __device__ __forceinline__ void match_row(const MatchArgs& a, const RowCtx& r, c
                 const int cnt = list[0];
                 int wide = -1;
                 if (cnt != 0xFFFF) {
-                    const unsigned span = (unsigned)(dhi - dlo);
-                    for (int k = 1; k <= cnt; k++) {
-                        const int d = list[k];
-                        if ((unsigned)(d - dlo) <= span && dhi >= dlo) continue;
-                        int val = (int)sad16(own, oth[step * d]);
-                        val += d > hi_ok ? kSkip : 0;
-                        best = min(best, val * 256 + k);
+                    const unsigned span = dhi >= dlo ? (unsigned)(dhi - dlo) : 0u;
+                    const int wlo = dhi >= dlo ? dlo : -1 - a.disp_max;      // empty window: nothing matches
+                    if (a.variant == 1) {
+                        // branch-free body (an in-window entry is evaluated and then disqualified like a skipped
+                        // one), two entries per trip: the loads and SAD chains of neighbouring entries overlap
+#pragma unroll 2
+                        for (int k = 1; k <= cnt; k++) {
+                            const int d = list[k];
+                            const bool out = (unsigned)(d - wlo) <= span || d > hi_ok;
+                            const int val = (int)sad16(own, oth[step * d]) + (out ? kSkip : 0);
+                            best = min(best, val * 256 + k);
+                        }
+                    } else {
+                        for (int k = 1; k <= cnt; k++) {
+                            const int d = list[k];
+                            if ((unsigned)(d - wlo) <= span) continue;
+                            const int val = (int)sad16(own, oth[step * d]) + (d > hi_ok ? kSkip : 0);
+                            best = min(best, val * 256 + k);
+                        }
                     }
                 } else {
                     wide = scan_cell_bitmask(a.grid[IMG] + ((size_t)r.gy * g.gw + r.c0 + c) * g.gwords, g.gwords,
@@ -334,6 +346,8 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.segw = sp.segw;
     a.max_cells = max_cells_per_segment(g, p.grid_size, sp.segw);
     a.map_pitch = map_pitch(g);
+    static const int variant = env_int("ELAS_B200_K7_VARIANT", 1);
+    a.variant = variant;
     a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;
     a.desc[0] = desc1; a.desc[1] = desc2;
     a.tri[0] = tri1; a.tri[1] = tri2;

@@ -283,12 +283,6 @@ __global__ void k_mean_pass(int Dw, int Dh, int vertical, const float* __restric
     out[a] = o;
 }
 
-__global__ void k_invalid_to_m10(int n, const float* __restrict__ in, float* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { const float d = in[i]; out[i] = d >= 0.f ? d : (float)kInvalid; }
-}
-
 // ---------------------------------------------------------------------------------------------
 // K12 separable 7-tap median, elas.cpp:1758-1838 (MIDDLEBURY preset).  Horizontal pass into a
 // zero-initialised temporary (calloc, :1770), vertical pass back into D; 3-pixel border untouched.
@@ -358,19 +352,18 @@ void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* 
 void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp,
                           cudaStream_t s)
 {
-    // tmp holds two planes: [0] = D_copy (invalid -> -10), [1] = D_tmp
-    const int n = g.Dw * g.Dh;
-    float* copy = tmp;
-    float* dtmp = tmp + n;
-    k_invalid_to_m10<<<(n + 255) / 256, 256, 0, s>>>(n, D, copy);
+    // The reference filters a copy of D in which invalid pixels are set to -10 (elas.cpp:1553-1559).
+    // Here every invalid pixel already IS -10: the L/R check writes -10 for everything it rejects
+    // (elas.cpp:1172-1196) and speckle removal / gap interpolation only write -10 or valid values,
+    // so the copy is D itself.  tmp = the reference's D_tmp (one plane).
     if (p.subsampling) {
-        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, copy, copy, dtmp);
-        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, dtmp, D, D);
+        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp);
+        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D);
     } else {
-        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, copy, copy, dtmp);
-        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, dtmp, D, D);
+        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp);
+        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D);
     }
-    count_launch(3);
+    count_launch(2);
 }
 
 void launch_median(const FrameGeom& g, float* D, float* tmp, cudaStream_t s)
