@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="stereo pairs per GPU per step")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled through the batch")
     ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = from host core count)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
@@ -307,6 +307,8 @@ def main():
         roof_4k = {"workload": f"synthetic {W4}x{H4}, d_max={D4}", "bound": "hbm", "achieved": round(a4, 1), "peak": peak,
                    "unit": "GB/s", "frac": round(a4 / peak, 4), "algorithmic_bytes_per_launch": b4,
                    "ms_per_launch": round(ms4, 5)}
+
+    (launches,) = sharding.sum_over_ranks([launches], dev)      # whole job
 
     if rank == 0:
         cpu = None

@@ -12,8 +12,9 @@ e.process(L,R)
 print("%%s thr=%%s seg=%%s  %%.2f us (flushed) %%.2f us (warm)" %% ((W,H), os.environ.get("ELAS_B200_K7_THREADS"), os.environ.get("ELAS_B200_K7_SEG"), e.time_matching(50, True)*1e3, e.time_matching(50, False)*1e3))
 e.close()
 '''
-for (W, H, D) in [(1242, 375, 255), (4096, 2160, 256)]:
+configs = [(1242, 375, 255)] if len(sys.argv) > 1 and sys.argv[1] == "k" else [(1242, 375, 255), (4096, 2160, 256)]
+for (W, H, D) in configs:
     for thr in (64, 128, 256):
-        for seg in (160, 224, 320, 448, 640, 1300):
+        for seg in (96, 128, 160, 224, 320, 448):
             env = dict(os.environ, ELAS_B200_K7_THREADS=str(thr), ELAS_B200_K7_SEG=str(seg))
             subprocess.run([sys.executable, "-c", code % (ROOT, W, H, D)], env=env)

@@ -6,7 +6,7 @@ import numpy as np, torch
 import elas_b200, synth
 
 W, H, D = 1242, 375, 255
-B = 64
+B = int(os.environ.get("PROBE_B", "64"))
 slots = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 bpl = W + 15 - (W - 1) % 16
 pairs = [synth.synthetic_pair(W, H, D, seed=i)[:2] for i in range(8)]
