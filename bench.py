@@ -46,6 +46,15 @@ def algorithmic_bytes_matching(w, h, dmax, grid_size=20):
     return 72 * w * h + 8 * gw * gh * (dmax + 2)
 
 
+def ncu_traffic_k7():
+    """DRAM bytes per launch of the matching kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r01_k7_traffic.json")
+    if not os.path.exists(path):
+        return None
+    rec = json.load(open(path))
+    return int(rec["dram_bytes_read_per_launch"]) + int(rec["dram_bytes_write_per_launch"])
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -334,7 +343,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right in one launch)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic_k7(),
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
