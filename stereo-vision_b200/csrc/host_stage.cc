@@ -6,6 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+
+#include <emmintrin.h>
 
 namespace elasb {
 
@@ -40,6 +43,13 @@ int Triangulator::incircle(int a, int b, int c, int d) const
     const int64_t adx = x_[a] - x_[d], ady = y_[a] - y_[d];
     const int64_t bdx = x_[b] - x_[d], bdy = y_[b] - y_[d];
     const int64_t cdx = x_[c] - x_[d], cdy = y_[c] - y_[d];
+    if (small_) {
+        // coordinate differences below 2^14: every product below 2^58, the sum below 2^60
+        const int64_t det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
+                            (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
+                            (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
+        return (det > 0) - (det < 0);
+    }
     const __int128 det = (__int128)(adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
                          (__int128)(bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
                          (__int128)(cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
@@ -405,6 +415,14 @@ void Triangulator::run(const int32_t* x, const int32_t* y, int n, std::vector<in
     out.clear();
     if (n < 2) return;
     x_ = x; y_ = y; seed_ = 1; ntri_ = 0;                 // randomseed reset per call, triangle.cpp:4030
+    {
+        int32_t xmin = x[0], xmax = x[0], ymin = y[0], ymax = y[0];
+        for (int i = 1; i < n; i++) {
+            xmin = std::min(xmin, x[i]); xmax = std::max(xmax, x[i]);
+            ymin = std::min(ymin, y[i]); ymax = std::max(ymax, y[i]);
+        }
+        small_ = (int64_t)xmax - xmin < (1 << 14) && (int64_t)ymax - ymin < (1 << 14);
+    }
     const size_t cap = 3 * (size_t)(3 * n + 8);
     if (nbr_.size() < cap) { nbr_.resize(cap); vtx_.resize(cap); }
     order_.resize(n);
@@ -441,12 +459,47 @@ void Triangulator::run(const int32_t* x, const int32_t* y, int n, std::vector<in
 // =============================================================================================
 namespace {
 
+// The three lattice filters run on a padded copy of the lattice (pitch Wc + 2*kPadC, kPadR rows above and
+// below, padding = -1 = invalid) so that no neighbour access needs a bounds check and an 11-wide
+// window row is two unaligned 128-bit loads.
+constexpr int kPadC = 8, kPadR = 8;
+
 // removeInconsistentSupportPoints, elas.cpp:174-209 (in place, u outer / v inner: every decision
 // sees the invalidations made before it).  The reference counts all valid neighbours within the
 // (2*win+1)^2 lattice window whose disparity differs by <= incon_threshold and invalidates the
 // point when the count is below incon_min_support; only that comparison is observable, so the
 // count stops as soon as it reaches incon_min_support (rows nearest the centre are visited first).
-void remove_inconsistent(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
+// A window row (<= 16 lattice points) is compared with SSE2: lanes d2 in [max(d-thr,0), d+thr].
+void remove_inconsistent_padded(const elas_b200_params& p, int16_t* P, int pitch, int Wc, int Hc)
+{
+    const int win = p.incon_window_size, need = p.incon_min_support, thr = p.incon_threshold;
+    const int span = 2 * win + 1;                           // lanes of a window row, <= 16 on this path
+    const uint32_t lane_mask = span >= 16 ? 0xFFFFFFFFu : ((1u << (2 * span)) - 1u);
+    for (int u = 0; u < Wc; u++) {
+        for (int v = 0; v < Hc; v++) {
+            int16_t* centre = P + (size_t)(v + kPadR) * pitch + kPadC + u;
+            const int d = *centre;
+            if (d < 0) continue;
+            const __m128i lo1 = _mm_set1_epi16((short)(std::max(d - thr, 0) - 1));      // x > lo-1
+            const __m128i hi1 = _mm_set1_epi16((short)std::min(d + thr + 1, 32767));    // x < hi+1
+            int support = 0;
+            for (int k = 0; k <= 2 * win && support < need; k++) {
+                const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);          // v, v+1, v-1, v+2, v-2, ...
+                const int16_t* row = centre + (ptrdiff_t)dv * pitch - win;
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row + 8));
+                const __m128i ma = _mm_and_si128(_mm_cmpgt_epi16(a, lo1), _mm_cmpgt_epi16(hi1, a));
+                const __m128i mb = _mm_and_si128(_mm_cmpgt_epi16(b, lo1), _mm_cmpgt_epi16(hi1, b));
+                const uint32_t m = ((uint32_t)_mm_movemask_epi8(ma) | ((uint32_t)_mm_movemask_epi8(mb) << 16)) & lane_mask;
+                support += __builtin_popcount(m) >> 1;
+            }
+            if (support < need) *centre = -1;
+        }
+    }
+}
+
+// generic window sizes (incon_window_size > 7): the same scan, scalar
+void remove_inconsistent_scalar(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
 {
     const int win = p.incon_window_size, need = p.incon_min_support, thr = p.incon_threshold;
     for (int u = 0; u < Wc; u++) {
@@ -457,7 +510,7 @@ void remove_inconsistent(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
             const int lo = std::max(d - thr, 0), hi = d + thr;
             int support = 0;
             for (int k = 0; k <= 2 * win && support < need; k++) {
-                const int v2 = v + ((k & 1) ? (k + 1) / 2 : -(k / 2));      // v, v+1, v-1, v+2, v-2, ...
+                const int v2 = v + ((k & 1) ? (k + 1) / 2 : -(k / 2));
                 if (v2 < 0 || v2 >= Hc) continue;
                 const int16_t* row = D + v2 * Wc;
                 for (int u2 = u_lo; u2 <= u_hi; u2++) support += row[u2] >= lo && row[u2] <= hi;
@@ -467,8 +520,27 @@ void remove_inconsistent(const elas_b200_params& p, int16_t* D, int Wc, int Hc)
     }
 }
 
-// removeRedundantSupportPoints, elas.cpp:213-279 (in place)
-void remove_redundant(int16_t* D, int Wc, int Hc, int max_dist, int thresh, bool vertical)
+// removeRedundantSupportPoints, elas.cpp:213-279 (in place): a point goes when, in BOTH directions along
+// the axis, a valid point with |d - d2| <= thresh lies within max_dist lattice steps.  `step` is the
+// element stride of the axis in the padded array (pitch for the vertical pass, 1 for the horizontal).
+void remove_redundant_padded(int16_t* P, int pitch, int Wc, int Hc, int max_dist, int thresh, ptrdiff_t step)
+{
+    for (int u = 0; u < Wc; u++)
+        for (int v = 0; v < Hc; v++) {
+            int16_t* centre = P + (size_t)(v + kPadR) * pitch + kPadC + u;
+            const int d = *centre;
+            if (d < 0) continue;
+            const int lo = std::max(d - thresh, 0), hi = d + thresh;
+            bool back = false, fwd = false;
+            for (int j = 1; j <= max_dist; j++) { const int x = centre[-j * step]; back |= x >= lo && x <= hi; }
+            if (!back) continue;
+            for (int j = 1; j <= max_dist; j++) { const int x = centre[j * step]; fwd |= x >= lo && x <= hi; }
+            if (fwd) *centre = -1;
+        }
+}
+
+// removeRedundantSupportPoints without padding (max_dist beyond the padding)
+void remove_redundant_scalar(int16_t* D, int Wc, int Hc, int max_dist, int thresh, bool vertical)
 {
     const int du = vertical ? 0 : 1, dv = vertical ? 1 : 0;
     for (int u = 0; u < Wc; u++)
@@ -603,17 +675,47 @@ void raster_records(const std::vector<int32_t>& sup, const std::vector<int32_t>&
 
 int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan, bool keep_stages, bool with_planes)
 {
-    remove_inconsistent(p, dcan, g.Wc, g.Hc);                     // elas.cpp:496
-    if (keep_stages) dcan_incon.assign(dcan, dcan + (size_t)g.Wc * g.Hc);
-    remove_redundant(dcan, g.Wc, g.Hc, 5, 1, true);               // :501
-    remove_redundant(dcan, g.Wc, g.Hc, 5, 1, false);              // :502
-
+    const int Wc = g.Wc, Hc = g.Hc;
     support.clear();
-    for (int uc = 1; uc < g.Wc; uc++)                             // :505-517, u outer / v inner
-        for (int vc = 1; vc < g.Hc; vc++) {
-            const int d = dcan[vc * g.Wc + uc];
-            if (d >= 0) { support.push_back(uc * g.step); support.push_back(vc * g.step); support.push_back(d); }
+    if (p.incon_window_size <= 7) {
+        // padded working copy (see kPadC/kPadR)
+        const int pitch = Wc + 2 * kPadC;
+        pad_.assign((size_t)pitch * (Hc + 2 * kPadR) + 16, (int16_t)-1);
+        int16_t* P = pad_.data();
+        for (int v = 0; v < Hc; v++) std::memcpy(P + (size_t)(v + kPadR) * pitch + kPadC, dcan + (size_t)v * Wc, (size_t)Wc * 2);
+        auto unpad = [&](int16_t* dst) {
+            for (int v = 0; v < Hc; v++) std::memcpy(dst + (size_t)v * Wc, P + (size_t)(v + kPadR) * pitch + kPadC, (size_t)Wc * 2);
+        };
+        remove_inconsistent_padded(p, P, pitch, Wc, Hc);              // elas.cpp:496
+        if (keep_stages) { dcan_incon.resize((size_t)Wc * Hc); unpad(dcan_incon.data()); }
+        remove_redundant_padded(P, pitch, Wc, Hc, 5, 1, pitch);       // :501 (vertical)
+        remove_redundant_padded(P, pitch, Wc, Hc, 5, 1, 1);           // :502 (horizontal)
+        unpad(dcan);
+    } else {
+        remove_inconsistent_scalar(p, dcan, Wc, Hc);
+        if (keep_stages) dcan_incon.assign(dcan, dcan + (size_t)Wc * Hc);
+        remove_redundant_scalar(dcan, Wc, Hc, 5, 1, true);
+        remove_redundant_scalar(dcan, Wc, Hc, 5, 1, false);
+    }
+
+    // :505-517, u outer / v inner.  Rows are scanned contiguously into per-column counts first, so
+    // the column-major emission is a scatter into a prefix-summed layout.
+    col_fill_.assign((size_t)Wc + 1, 0);
+    for (int vc = 1; vc < Hc; vc++) {
+        const int16_t* row = dcan + (size_t)vc * Wc;
+        for (int uc = 1; uc < Wc; uc++) col_fill_[uc + 1] += row[uc] >= 0;
+    }
+    for (int uc = 1; uc <= Wc; uc++) col_fill_[uc] += col_fill_[uc - 1];
+    support.resize(3 * (size_t)col_fill_[Wc]);
+    for (int vc = 1; vc < Hc; vc++) {
+        const int16_t* row = dcan + (size_t)vc * Wc;
+        for (int uc = 1; uc < Wc; uc++) {
+            const int d = row[uc];
+            if (d < 0) continue;
+            int32_t* o = support.data() + 3 * (size_t)col_fill_[uc]++;
+            o[0] = uc * g.step; o[1] = vc * g.step; o[2] = d;
         }
+    }
     if (p.add_corners) add_corners(g.W, g.H, support);            // :520-523
     n_support = (int)support.size() / 3;
     for (int k = 0; k < 2; k++) { tri[k].clear(); planes[k].clear(); raster[k].clear(); }

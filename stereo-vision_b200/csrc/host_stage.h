@@ -56,6 +56,7 @@ private:
     std::vector<int> nbr_, vtx_, order_, sx_, sy_, tmp_, count_;
     std::vector<uint8_t> side_;
     int ntri_ = 0;
+    bool small_ = false;      // coordinate range below 2^14: incircle fits 64-bit integers
     uint64_t seed_ = 1;
 };
 
@@ -79,7 +80,8 @@ struct HostStage {
 
 private:
     Triangulator delaunay_;
-    std::vector<int32_t> px_, py_;
+    std::vector<int32_t> px_, py_, col_fill_;
+    std::vector<int16_t> pad_;
 };
 
 }  // namespace elasb
