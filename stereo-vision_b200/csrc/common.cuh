@@ -74,29 +74,42 @@ void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const 
 // K2  support matching on the candidate lattice, forward + reverse (elas.cpp:322-445, :471-493)
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                     const uint4* desc2, int16_t* dcan, cudaStream_t s);
-// K6  candidate grid as per-cell disparity bitmasks, both images (elas.cpp:684-780)
-void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
-                 cudaStream_t s);
-// K5  disparity planes + per-triangle raster records, both images (elas.cpp:605-680, :1006-1072)
-void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const int32_t* tri2, int nt2,
-                   TriRaster* out1, TriRaster* out2, float* planes1, float* planes2, cudaStream_t s);
-// triangle-id maps: scan conversion with last-writer-wins (elas.cpp:1074-1114)
-void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, const TriRaster* tri2,
-                   const int32_t* units, int n_units, int32_t* map1, int32_t* map2, cudaStream_t s);
+// K5 + K6 scatter: disparity planes + per-triangle raster records (elas.cpp:605-680, :1006-1072) and the
+// support points' d-1..d+1 marks in the candidate-grid scatter planes (elas.cpp:697-727), one launch.
+// scratch = this frame's scatter planes [2][gh*gw][gwords], all zero on entry.
+void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
+                           const int32_t* tri1, int nt1, const int32_t* tri2, int nt2, TriRaster* out1,
+                           TriRaster* out2, float* planes1, float* planes2, uint32_t* scratch, cudaStream_t s);
+// K6 diffusion (elas.cpp:732-775) + triangle-id maps by scan conversion with last-writer-wins
+// (elas.cpp:1074-1114), one launch.  scratch_next (the slot's other scatter buffer) is zeroed for the
+// next frame.  Map entries are tag_bits | triangle index (see k_grid_raster.cu).
+void launch_diffuse_raster(const FrameGeom& g, int subsampling, const uint32_t* scratch, uint32_t* scratch_next,
+                           uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units, int n_units,
+                           int32_t* map1, int32_t* map2, int tag_bits, cudaStream_t s);
 // K7  dense matching, both images (elas.cpp:814-955, :960-1118)
 void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
                      const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
                      const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
-                     const int32_t* prior, float* D1, float* D2, cudaStream_t s);
+                     const int32_t* prior, float* D1, float* D2, int map_tag_bits, int map_tag_shift,
+                     cudaStream_t s);
 size_t matching_smem_bytes(const FrameGeom& g, int grid_size);
 // K8  left/right consistency (elas.cpp:1122-1204)
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
                      float* O1, float* O2, cudaStream_t s);
 // K9  speckle removal (elas.cpp:1208-1326)
+// apply = false: stop after the component sizes are known; launch_post_fused then applies them
 void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, cudaStream_t s);
+                     int32_t* size, cudaStream_t s, bool apply = true, bool rows_done = false);
+// K8 + K9's row step for D1 in one kernel (rows staged in shared memory)
+bool lr_rows_fusable(const FrameGeom& g);
+void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
+                    float* O1, float* O2, int32_t* parent, int32_t* size, cudaStream_t s);
+// K9 apply + K10 + K11 in one tiled kernel (ipol_gap_width <= 3, no add_corners); out must not alias in
+bool post_fusable(const elas_b200_params& p);
+void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
+                       const int32_t* size, float* out, float* dump_seg, float* dump_gap, cudaStream_t s);
 // K10 gap interpolation (elas.cpp:1330-1530)
 void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, cudaStream_t s);
 // K11 adaptive mean (elas.cpp:1535-1754)

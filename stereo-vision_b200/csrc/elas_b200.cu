@@ -80,6 +80,8 @@ struct Slot {
     int n_tri[2] = {0, 0};
     int n_units = 0;
     size_t units_at = 0;
+    int map_tag = 0;                           // frame tag of the triangle-id map entries (k_grid_raster.cu)
+    int scratch_phase = 0;                     // which of the two grid scatter buffers this frame uses
     bool tables_valid = false;
     // introspection
     bool capture = false;
@@ -94,6 +96,7 @@ struct elas_b200_ctx {
     elas_b200_params p{};
     FrameGeom g{};
     int support_cap = 0, tri_cap = 0, unit_cap = 0;
+    int map_tag_shift = 0, map_tag_max = 0;  // map entry = tag << shift | triangle index
     int32_t* d_prior = nullptr;
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
@@ -189,6 +192,7 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
         CK(cudaMalloc(&s.d_lists[k], (size_t)g.gw * g.gh * kGridListStride * 2));
         CK(cudaMalloc(&s.d_map[k], (size_t)map_pitch(g) * g.H * 4));
+        CK(cudaMemset(s.d_map[k], 0xFF, (size_t)map_pitch(g) * g.H * 4));   // -1 = not covered by any triangle
         CK(cudaMalloc(&s.d_raw[k], ND * 4));
         CK(cudaMalloc(&s.d_D[k], ND * 4));
         CK(cudaMalloc(&s.d_planes[k], (size_t)c->tri_cap * 24));
@@ -198,7 +202,8 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     CK(cudaMallocHost(&s.h_tables, table_ints * 4));
     CK(cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     CK(cudaMalloc(&s.d_dcan, (size_t)g.Wc * g.Hc * 2));
-    CK(cudaMalloc(&s.d_grid_scratch, 2 * cells * 4));
+    CK(cudaMalloc(&s.d_grid_scratch, 4 * cells * 4));                      // two buffers of [2][cells] words
+    CK(cudaMemset(s.d_grid_scratch, 0, 4 * cells * 4));
     CK(cudaMalloc(&s.d_tmp, 2 * ND * 4));
     CK(cudaMalloc(&s.d_parent, ND * 4));
     CK(cudaMalloc(&s.d_size, ND * 4));
@@ -353,18 +358,30 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
     CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (units_at + 2 * (size_t)n_units) * 4, cudaMemcpyHostToDevice, st));
     mark(c, s, "tables_in");
-    launch_planes(d_support, d_tri1, nt1, d_tri2, nt2, s.d_tri[0], s.d_tri[1], s.d_planes[0], s.d_planes[1], st);   // elas.cpp:87-88
-    mark(c, s, "planes");
+    const size_t scratch_words = 2 * (size_t)g.gw * g.gh * g.gwords;
+    uint32_t* scratch_cur = s.d_grid_scratch + (size_t)s.scratch_phase * scratch_words;
+    uint32_t* scratch_next = s.d_grid_scratch + (size_t)(1 - s.scratch_phase) * scratch_words;
+    s.scratch_phase ^= 1;
+    if (++s.map_tag > c->map_tag_max) {
+        // tag space used up: start over from cleared maps
+        for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s.d_map[k], 0xFF, (size_t)map_pitch(g) * g.H * 4, st));
+        s.map_tag = 1;
+    }
+    const int tag_bits = s.map_tag << c->map_tag_shift;
+    launch_planes_scatter(g, p, d_support, n, d_tri1, nt1, d_tri2, nt2, s.d_tri[0], s.d_tri[1], s.d_planes[0],
+                          s.d_planes[1], scratch_cur, st);                                 // elas.cpp:87-88, :697-727
+    mark(c, s, "planes+scatter");
     if (s.capture) {
         if (int32_t rc = grab(s, "planes1", s.d_planes[0], (size_t)nt1 * 24)) return rc;
         if (int32_t rc = grab(s, "planes2", s.d_planes[1], (size_t)nt2 * 24)) return rc;
     }
-    launch_grid(g, p, d_support, n, s.d_grid_scratch, s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], st);
-    mark(c, s, "grid");
-    launch_raster(g, p.subsampling, s.d_tri[0], s.d_tri[1], s.d_tables + units_at, n_units, s.d_map[0], s.d_map[1], st);
-    mark(c, s, "raster");
+    launch_diffuse_raster(g, p.subsampling, scratch_cur, scratch_next, s.d_grid[0], s.d_grid[1], s.d_lists[0],
+                          s.d_lists[1], s.d_tri[0], s.d_tri[1], s.d_tables + units_at, n_units, s.d_map[0],
+                          s.d_map[1], tag_bits, st);                                        // :732-775, :1074-1114
+    mark(c, s, "diffuse+raster");
     launch_matching(g, p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                    s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1], st);
+                    s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1],
+                    tag_bits, c->map_tag_shift, st);
     mark(c, s, "matching");
     s.tables_valid = true;
     if (s.capture) {
@@ -374,39 +391,63 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         if (int32_t rc = grab(s, "D1_raw", s.d_raw[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2_raw", s.d_raw[1], ND * 4)) return rc;
     }
-    launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], st);             // elas.cpp:116
+    const bool rows_fused = lr_rows_fusable(g);
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], s.d_parent, s.d_size, st);
+    else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], st);         // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
         if (int32_t rc = grab(s, "D1_lr", s.d_D[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2_lr", s.d_D[1], ND * 4)) return rc;
     }
     const int n_post = p.postprocess_only_left ? 1 : 2;                                  // elas.cpp:121-159
-    for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st);
-    mark(c, s, "segments");
-    if (s.capture) {
-        if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
+    float* final_map[2] = {s.d_D[0], s.d_D[1]};
+    if (post_fusable(p)) {
+        // speckle sizes (K9 rows/merge/count), then ONE kernel for speckle apply + gap interpolation +
+        // adaptive mean; it reads d_D and writes the final map into d_raw (dead after the L/R check)
+        for (int k = 0; k < n_post; k++) {
+            launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, false, rows_fused && k == 0);
+            mark(c, s, k ? "segments2" : "segments");
+            launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, s.d_raw[k],
+                              s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, st);
+            final_map[k] = s.d_raw[k];
+            if (s.capture) {
+                if (int32_t rc = grab(s, k ? "D2_seg" : "D1_seg", s.d_tmp, ND * 4)) return rc;
+                if (int32_t rc = grab(s, k ? "D2_gap" : "D1_gap", p.filter_adaptive_mean ? s.d_tmp + ND : s.d_raw[k], ND * 4)) return rc;
+            }
+        }
+        mark(c, s, "apply+gap+mean");
+        if (s.capture && n_post == 1) {
+            if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
+        }
+    } else {
+        for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, true, rows_fused && k == 0);
+        mark(c, s, "segments");
+        if (s.capture) {
+            if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
+        }
+        for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, st);
+        mark(c, s, "gap");
+        if (s.capture) {
+            if (int32_t rc = grab(s, "D1_gap", s.d_D[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
+        }
+        if (p.filter_adaptive_mean) {
+            for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, st);
+            mark(c, s, "adaptive_mean");
+        }
     }
-    for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, st);
-    mark(c, s, "gap");
     if (s.capture) {
-        if (int32_t rc = grab(s, "D1_gap", s.d_D[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
-    }
-    if (p.filter_adaptive_mean) {
-        for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, st);
-        mark(c, s, "adaptive_mean");
-    }
-    if (s.capture) {
-        if (int32_t rc = grab(s, "D1_mean", s.d_D[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_mean", s.d_D[1], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D1_mean", final_map[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_mean", final_map[1], ND * 4)) return rc;
     }
     if (p.filter_median) {
-        for (int k = 0; k < n_post; k++) launch_median(g, s.d_D[k], s.d_tmp, st);
+        for (int k = 0; k < n_post; k++) launch_median(g, final_map[k], s.d_tmp, st);
         mark(c, s, "median");
     }
-    CK(cudaMemcpyAsync(D1, s.d_D[0], ND * 4, cudaMemcpyDefault, st));
-    CK(cudaMemcpyAsync(D2, s.d_D[1], ND * 4, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(D1, final_map[0], ND * 4, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(D2, final_map[1], ND * 4, cudaMemcpyDefault, st));
     mark(c, s, "copy_out");
     const long long t4 = now_ns();
     if (int32_t rc = wait_stream(c, s)) return rc;
@@ -415,8 +456,8 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     c->ns_submit_a += t1 - t0; c->ns_wait_a += t2 - t1; c->ns_host += t3 - t2;
     c->ns_submit_b += t4 - t3; c->ns_wait_b += t5 - t4; c->frames += 1;
     if (s.capture) {
-        if (int32_t rc = grab(s, "D1", s.d_D[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2", s.d_D[1], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D1", final_map[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2", final_map[1], ND * 4)) return rc;
     }
     if (c->timing) {
         s.timer.last.clear();
@@ -553,6 +594,9 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
     c->tri_cap = 2 * c->support_cap + 8;
     // raster work units: every triangle is at least one unit; large ones split into 32-column x 32-row
     // pieces of their bounding boxes (bounded by a few times the image area)
+    while ((1 << c->map_tag_shift) < c->tri_cap) c->map_tag_shift++;
+    c->map_tag_max = (1 << (30 - c->map_tag_shift)) - 1;
+    if (c->map_tag_max < 1) return ELAS_B200_E_UNSUPPORTED;
     c->unit_cap = 2 * c->tri_cap + 8 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
     if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
@@ -754,7 +798,8 @@ float elas_b200_time_matching(elas_b200_ctx* c, int32_t slot, int32_t iters, int
         if (flush_l2) cudaMemsetAsync(c->d_flush, i & 0xff, c->flush_bytes, s.stream);
         cudaEventRecord(e0, s.stream);
         launch_matching(c->g, c->p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                        s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1], s.stream);
+                        s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1],
+                        s.map_tag << c->map_tag_shift, c->map_tag_shift, s.stream);
         cudaEventRecord(e1, s.stream);
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { total = -1; break; }
         float ms = 0;

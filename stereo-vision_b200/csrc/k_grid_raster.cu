@@ -16,10 +16,10 @@ __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b :
 // elas.cpp:697-727: every support point marks d-1..d+1 in its cell, for the left image at
 // (u/grid_size, v/grid_size) and for the right image at (floor((u-d)/grid_size), v/grid_size).
 // scratch = two bitmask planes [2][gh*gw][gwords], zeroed before this kernel.
-__global__ void k_grid_scatter(FrameGeom g, elas_b200_params p, const int32_t* __restrict__ support,
-                               int n, uint32_t* __restrict__ scratch)
+__device__ __forceinline__ void grid_scatter_body(int i, const FrameGeom& g, const elas_b200_params& p,
+                                                  const int32_t* __restrict__ support, int n,
+                                                  uint32_t* __restrict__ scratch)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int u = support[3 * i], v = support[3 * i + 1], d = support[3 * i + 2];
     const int y = floor_div(v, p.grid_size);
@@ -41,12 +41,14 @@ __global__ void k_grid_scatter(FrameGeom g, elas_b200_params p, const int32_t* _
 // cell's bitmask and, for the matching kernel, the same set as an ascending uint16 list
 // (elas.cpp:754-775 packs exactly this list): list[0] = count, list[1..] = disparities; a cell with
 // more than kGridListCap candidates gets count 0xFFFF and is read from its bitmask instead.
-__global__ void k_grid_diffuse(FrameGeom g, const uint32_t* __restrict__ scratch,
-                               uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
-                               uint16_t* __restrict__ lists1, uint16_t* __restrict__ lists2)
+// The scatter planes are double-buffered per slot: while this frame's planes are read, the other
+// buffer (used by the previous frame, needed again by the next one) is zeroed -- no memset launch.
+__device__ __forceinline__ void grid_diffuse_body(int i, const FrameGeom& g, const uint32_t* __restrict__ scratch,
+                                                  uint32_t* __restrict__ scratch_next,
+                                                  uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
+                                                  uint16_t* __restrict__ lists1, uint16_t* __restrict__ lists2)
 {
     const int cells = g.gw * g.gh;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * cells) return;
     const int img = i >= cells, c = img ? i - cells : i;
     uint32_t* bits = (img ? grid2 : grid1) + (size_t)c * g.gwords;
@@ -63,6 +65,7 @@ __global__ void k_grid_diffuse(FrameGeom g, const uint32_t* __restrict__ scratch
                 for (int dx = -1; dx <= 1; dx++) m |= t[(size_t)(c + dy * g.gw + dx) * g.gwords];
         }
         bits[w] = m;
+        scratch_next[(size_t)i * g.gwords + w] = 0u;
         while (m) {
             if (count < kGridListCap) list[1 + count] = (uint16_t)(32 * w + __ffs(m) - 1);
             count++;
@@ -109,13 +112,14 @@ __device__ bool solve3(double A[3][3], double b[3])
     return true;
 }
 
-__global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __restrict__ tri1, int nt1,
-                         const int32_t* __restrict__ tri2, int nt2, TriRaster* __restrict__ out1,
-                         TriRaster* __restrict__ out2, float* __restrict__ planes1, float* __restrict__ planes2)
+__device__ __forceinline__ void planes_body(int gid, const int32_t* __restrict__ support,
+                                            const int32_t* __restrict__ tri1, int nt1,
+                                            const int32_t* __restrict__ tri2, int nt2, TriRaster* __restrict__ out1,
+                                            TriRaster* __restrict__ out2, float* __restrict__ planes1, float* __restrict__ planes2)
 {
     // two threads per triangle: the even lane fits the plane in left-image coordinates (t1), the odd lane
-    // the one in right-image coordinates (t2); the two solves are the long serial part of this kernel
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    // the one in right-image coordinates (t2); the two solves are the long serial part of this kernel.
+    // Whole warps call this together (shuffles below).
     const int k = gid & 1;
     int i = gid >> 1;
     const bool active = i < nt1 + nt2;
@@ -188,13 +192,17 @@ __global__ void k_planes(const int32_t* __restrict__ support, const int32_t* __r
 // together, so every store instruction touches one row segment (coalesced) with warp-uniform loop
 // bounds.  The reference lets later triangles overwrite earlier ones; atomicMax on the triangle index
 // gives the same winner (findMatch's early returns depend on the pixel only, never on the triangle).
-__global__ void __launch_bounds__(256)
-k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
-         const int2* __restrict__ units, int n_units, int32_t* __restrict__ map1, int32_t* __restrict__ map2)
+//
+// Map entries are (frame tag << tag_shift) | triangle index: a new frame's entries compare greater than
+// anything an earlier frame left behind, so the maps are never cleared between frames (the matching
+// kernel ignores entries whose tag is not the current one).
+__device__ __forceinline__ void raster_body(int unit, const FrameGeom& g, int subsampling,
+                                            const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
+                                            const int2* __restrict__ units, int n_units,
+                                            int32_t* __restrict__ map1, int32_t* __restrict__ map2, int tag_bits)
 {
     const int lane = threadIdx.x & 31;
     const int pitch = map_pitch(g);
-    const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (unit >= n_units) return;
     const int2 w = __ldg(units + unit);
     const int t = w.x & 0x3FFFFFFF, img = (w.x >> 30) & 1, chunk = w.y & 0xFFFF, band = w.y >> 16;
@@ -227,45 +235,67 @@ k_raster(FrameGeom g, int subsampling, const TriRaster* __restrict__ tri1, const
     const int vlo = max(vmin, b_lo), vhi = min(vmax, b_hi);
     int32_t* col = map + u;
     for (int v = vlo; v < vhi; v++) {
-        if (v >= lo && v < hi && !(subsampling && (v & 1))) atomicMax(col + (size_t)v * pitch, t);
+        if (v >= lo && v < hi && !(subsampling && (v & 1))) atomicMax(col + (size_t)v * pitch, tag_bits | t);
     }
+}
+
+// K5 + the scatter half of K6 in one launch: blocks [0, plane_blocks) fit planes, the rest scatter
+// support points into the candidate-grid bitmasks.  Both read only the uploaded tables.
+constexpr int kSetupThreads = 128;
+__global__ void __launch_bounds__(kSetupThreads)
+k_planes_scatter(FrameGeom g, elas_b200_params p, int plane_blocks, const int32_t* __restrict__ support, int n,
+                 const int32_t* __restrict__ tri1, int nt1, const int32_t* __restrict__ tri2, int nt2,
+                 TriRaster* __restrict__ out1, TriRaster* __restrict__ out2, float* __restrict__ planes1,
+                 float* __restrict__ planes2, uint32_t* __restrict__ scratch)
+{
+    if ((int)blockIdx.x < plane_blocks)
+        planes_body(blockIdx.x * kSetupThreads + threadIdx.x, support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
+    else
+        grid_scatter_body((blockIdx.x - plane_blocks) * kSetupThreads + threadIdx.x, g, p, support, n, scratch);
+}
+
+// The diffusion half of K6 + scan conversion in one launch: blocks [0, diffuse_blocks) turn the scatter
+// planes into per-cell bitmasks and lists, the rest rasterise triangle work units (8 per block).
+constexpr int kRasterThreads = 256;
+__global__ void __launch_bounds__(kRasterThreads)
+k_diffuse_raster(FrameGeom g, int subsampling, int diffuse_blocks, const uint32_t* __restrict__ scratch,
+                 uint32_t* __restrict__ scratch_next, uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
+                 uint16_t* __restrict__ lists1, uint16_t* __restrict__ lists2,
+                 const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
+                 const int2* __restrict__ units, int n_units, int32_t* __restrict__ map1, int32_t* __restrict__ map2,
+                 int tag_bits)
+{
+    if ((int)blockIdx.x < diffuse_blocks)
+        grid_diffuse_body(blockIdx.x * kRasterThreads + threadIdx.x, g, scratch, scratch_next, grid1, grid2, lists1, lists2);
+    else
+        raster_body((blockIdx.x - diffuse_blocks) * (kRasterThreads >> 5) + (threadIdx.x >> 5), g, subsampling,
+                    tri1, tri2, units, n_units, map1, map2, tag_bits);
 }
 
 }  // namespace
 
-void launch_grid(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                 uint32_t* scratch, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
-                 cudaStream_t s)
+void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
+                           const int32_t* tri1, int nt1, const int32_t* tri2, int nt2, TriRaster* out1,
+                           TriRaster* out2, float* planes1, float* planes2, uint32_t* scratch, cudaStream_t s)
 {
-    const size_t words = (size_t)g.gw * g.gh * g.gwords;
-    cudaMemsetAsync(scratch, 0, 2 * words * sizeof(uint32_t), s);
-    if (n_support > 0) {
-        k_grid_scatter<<<(n_support + 127) / 128, 128, 0, s>>>(g, p, support, n_support, scratch);
-        count_launch();
-    }
-    const int cells2 = 2 * g.gw * g.gh;
-    k_grid_diffuse<<<(cells2 + 127) / 128, 128, 0, s>>>(g, scratch, grid1, grid2, lists1, lists2);
+    const int plane_blocks = (2 * (nt1 + nt2) + kSetupThreads - 1) / kSetupThreads;
+    const int scatter_blocks = (n_support + kSetupThreads - 1) / kSetupThreads;
+    if (plane_blocks + scatter_blocks == 0) return;
+    k_planes_scatter<<<plane_blocks + scatter_blocks, kSetupThreads, 0, s>>>(g, p, plane_blocks, support, n_support, tri1, nt1,
+                                                                             tri2, nt2, out1, out2, planes1, planes2, scratch);
     count_launch();
 }
 
-void launch_planes(const int32_t* support, const int32_t* tri1, int nt1, const int32_t* tri2, int nt2,
-                   TriRaster* out1, TriRaster* out2, float* planes1, float* planes2, cudaStream_t s)
+void launch_diffuse_raster(const FrameGeom& g, int subsampling, const uint32_t* scratch, uint32_t* scratch_next,
+                           uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units, int n_units,
+                           int32_t* map1, int32_t* map2, int tag_bits, cudaStream_t s)
 {
-    const int total = nt1 + nt2;
-    if (total <= 0) return;
-    k_planes<<<(2 * total + 63) / 64, 64, 0, s>>>(support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
-    count_launch();
-}
-
-void launch_raster(const FrameGeom& g, int subsampling, const TriRaster* tri1, const TriRaster* tri2,
-                   const int32_t* units, int n_units, int32_t* map1, int32_t* map2, cudaStream_t s)
-{
-    const size_t bytes = (size_t)map_pitch(g) * g.H * sizeof(int32_t);
-    cudaMemsetAsync(map1, 0xFF, bytes, s);      // -1 = not covered by any triangle
-    cudaMemsetAsync(map2, 0xFF, bytes, s);
-    if (n_units <= 0) return;
-    k_raster<<<(n_units + 7) / 8, 256, 0, s>>>(g, subsampling, tri1, tri2, reinterpret_cast<const int2*>(units),
-                                               n_units, map1, map2);
+    const int diffuse_blocks = (2 * g.gw * g.gh + kRasterThreads - 1) / kRasterThreads;
+    const int raster_blocks = (n_units + (kRasterThreads >> 5) - 1) / (kRasterThreads >> 5);
+    k_diffuse_raster<<<diffuse_blocks + raster_blocks, kRasterThreads, 0, s>>>(
+        g, subsampling, diffuse_blocks, scratch, scratch_next, grid1, grid2, lists1, lists2, tri1, tri2,
+        reinterpret_cast<const int2*>(units), n_units, map1, map2, tag_bits);
     count_launch();
 }
 

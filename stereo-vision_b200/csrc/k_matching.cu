@@ -82,6 +82,7 @@ struct MatchArgs {
     FrameGeom g;
     int disp_max, match_texture, grid_size, subsampling;
     int segw, max_cells, map_pitch, variant;
+    int map_tag_bits, map_tag_mask;      // triangle-id map entries are tag_bits | index; other tags = stale = uncovered
     uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
     const uint4* desc[2];
     const TriRaster* tri[2];
@@ -145,15 +146,17 @@ __device__ __forceinline__ void match_row(const MatchArgs& a, const RowCtx& r, c
     float* __restrict__ Drow = a.D[IMG] + (a.subsampling ? (size_t)(r.v >> 1) * g.Dw : (size_t)r.v * g.W);
 
     // software pipeline: the covering triangle's plane for the next pixel is in flight while this one is matched
+    // entries written for an earlier frame carry another tag and count as "not covered" (k_grid_raster.cu)
+    auto covering = [&](int e) { return (e & ~a.map_tag_mask) == a.map_tag_bits ? (e & a.map_tag_mask) : -1; };
     int i = threadIdx.x;
-    int t = i < r.n ? tmap[i] : -1;
+    int t = i < r.n ? covering(tmap[i]) : -1;
     float4 pl = t >= 0 ? __ldg(reinterpret_cast<const float4*>(&tris[t].pa)) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (; i < r.n; i += kThreads) {
         const int u = r.x0 + i;
         const int t_cur = t;
         const float4 pl_cur = pl;
         const int i_next = i + kThreads;
-        t = i_next < r.n ? tmap[i_next] : -1;
+        t = i_next < r.n ? covering(tmap[i_next]) : -1;
         if (t >= 0) pl = __ldg(reinterpret_cast<const float4*>(&tris[t].pa));
         if (a.subsampling && ((u & 1) || (u >> 1) >= g.Dw)) continue;      // elas.cpp:1079
 
@@ -336,7 +339,8 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
                      const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
                      const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
                      const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
-                     const int32_t* prior, float* D1, float* D2, cudaStream_t s)
+                     const int32_t* prior, float* D1, float* D2, int map_tag_bits, int map_tag_shift,
+                     cudaStream_t s)
 {
     const SegPlan sp = plan_segments(g.W);
     MatchArgs a;
@@ -346,6 +350,8 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
     a.segw = sp.segw;
     a.max_cells = max_cells_per_segment(g, p.grid_size, sp.segw);
     a.map_pitch = map_pitch(g);
+    a.map_tag_bits = map_tag_bits;
+    a.map_tag_mask = (1 << map_tag_shift) - 1;
     static const int variant = env_int("ELAS_B200_K7_VARIANT", 1);
     a.variant = variant;
     a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;

@@ -82,16 +82,14 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
     }
 }
 
-// one CTA per row: parent[pixel] = index of the first pixel of its run (-1 for invalid pixels)
-__global__ void __launch_bounds__(256)
-k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+// one CTA per row: parent[pixel] = index of the first pixel of its run (-1 for invalid pixels).
+// `row` may live in shared memory (k_lr_rows) or in global memory (k_seg_rows).
+__device__ __forceinline__ void label_row_runs(const float* row, int Dw, int base, float thr,
+                                               int32_t* __restrict__ parent, int32_t* __restrict__ size,
+                                               int* warp_last, int* carry_s)
 {
-    __shared__ int warp_last[8];
-    __shared__ int carry_s;
-    const int v = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* row = D + (size_t)v * Dw;
-    const int base = v * Dw;
-    if (threadIdx.x == 0) carry_s = -1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *carry_s = -1;
     __syncthreads();
     for (int u0 = 0; u0 < Dw; u0 += 256) {
         const int u = u0 + threadIdx.x;
@@ -104,16 +102,58 @@ k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__
         int last = upto ? u0 + (warp << 5) + 31 - __clz(upto) : -1;      // most recent start in this warp
         if (lane == 31) warp_last[warp] = last;
         __syncthreads();
-        const int carry = carry_s;
+        const int carry = *carry_s;
         if (last < 0) {
             for (int w = warp - 1; w >= 0 && last < 0; w--) last = warp_last[w];
             if (last < 0) last = carry;
         }
         if (u < Dw) { parent[base + u] = valid ? base + last : -1; size[base + u] = 0; }
         __syncthreads();
-        if (threadIdx.x == 255) carry_s = last >= 0 ? last : carry;     // runs never span an invalid pixel
+        if (threadIdx.x == 255) *carry_s = last >= 0 ? last : carry;     // runs never span an invalid pixel
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+{
+    __shared__ int warp_last[8];
+    __shared__ int carry_s;
+    const int v = blockIdx.x;
+    label_row_runs(D + (size_t)v * Dw, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
+}
+
+// K8 + the row step of K9 in one pass: a CTA owns one row of both maps.  The L/R check of a pixel
+// only reads the other map within the same row (elas.cpp:1164-1197), so both raw rows are staged in
+// shared memory, the checked rows are written out, and the checked D1 row -- still in shared memory --
+// is labelled into runs.
+__global__ void __launch_bounds__(256)
+k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
+          const float* __restrict__ D1, const float* __restrict__ D2,
+          float* __restrict__ O1, float* __restrict__ O2, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+{
+    extern __shared__ float s_rows[];          // [3][Dw]: raw D1 row, raw D2 row, checked D1 row
+    __shared__ int warp_last[8];
+    __shared__ int carry_s;
+    float* r1 = s_rows; float* r2 = s_rows + Dw; float* c1 = s_rows + 2 * Dw;
+    const int v = blockIdx.x;
+    const size_t row = (size_t)v * Dw;
+    for (int u = threadIdx.x; u < Dw; u += 256) { r1[u] = D1[row + u]; r2[u] = D2[row + u]; }
+    __syncthreads();
+    for (int u = threadIdx.x; u < Dw; u += 256) {
+        const float d1 = r1[u], d2 = r2[u];
+        const float w1 = subsampling ? __fsub_rn((float)u, __fmul_rn(d1, 0.5f)) : __fsub_rn((float)u, d1);  // :1152-1161
+        const float w2 = subsampling ? __fadd_rn((float)u, __fmul_rn(d2, 0.5f)) : __fadd_rn((float)u, d2);
+        float o1 = (float)kInvalid, o2 = (float)kInvalid;
+        if (d1 >= 0.f && w1 >= 0.f && w1 < (float)Dw)                                                       // :1164-1179
+            if (!(fabsf(__fsub_rn(r2[(int)w1], d1)) > lr_threshold)) o1 = d1;
+        if (d2 >= 0.f && w2 >= 0.f && w2 < (float)Dw)                                                       // :1182-1197
+            if (!(fabsf(__fsub_rn(r1[(int)w2], d2)) > lr_threshold)) o2 = d2;
+        O1[row + u] = o1; O2[row + u] = o2;
+        c1[u] = o1;
+    }
+    __syncthreads();
+    label_row_runs(c1, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
 }
 
 __global__ void k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
@@ -316,6 +356,159 @@ __global__ void k_median_pass(int Dw, int Dh, int vertical, const float* D,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused tail of the post-processing chain: speckle "apply" (the last step of K9), K10 gap
+// interpolation (row pass, column pass) and K11 adaptive mean (row pass, column pass) in ONE kernel.
+// The five stages are local stencils of each other -- row pass reach <= kFuseGap columns, column pass
+// reach <= kFuseGap rows, mean window [c-BACK, c+FWD] -- so a CTA computes an output tile from an
+// input tile with (BACK+kFuseGap | FWD+kFuseGap) halos entirely in shared memory:
+//   A  = D after speckle removal   rows [r0-BACK-G, r0+TH+FWD+G) x cols [c0-BACK-G, c0+TW+FWD+G)
+//   B  = after the gap row pass    same rows                      x cols [c0-BACK,   c0+TW+FWD)
+//   C  = after the gap column pass rows [r0-BACK,   r0+TH+FWD)    x same cols          (= K10 output)
+//   M  = after the mean row pass   same rows                      x cols [c0, c0+TW)   (reuses A)
+//   out= after the mean column pass rows [r0, r0+TH)              x cols [c0, c0+TW)
+// Pixels outside the image enter as invalid (-10): a gap run that reaches them finds no bounding
+// valid pixel, which is the reference's "run touches the line end" case (elas.cpp:1374, :1463), and
+// the mean windows are only evaluated where the reference evaluates them (all taps inside the image).
+// Per-pixel expressions are the ones of k_gap_pass / mean_window, so results are bit-identical to
+// the unfused kernels.  Used when ipol_gap_width <= kFuseGap and add_corners is off (the ROBOTICS
+// family); other settings run the unfused kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFuseGap = 3;
+constexpr int kFuseTW = 64, kFuseTH = 32, kFuseThreads = 512;
+
+struct FuseArgs {
+    int Dw, Dh, gap, speckle, apply;     // apply: fold k_seg_apply in (parent/size valid)
+    const float* in;                     // D after the L/R check (apply) or after speckle removal
+    const int32_t* parent;
+    const int32_t* size;
+    float* out;                          // final map (must not alias in)
+    float* dump_seg;                     // optional stage dumps (tests): D after speckle removal, after gap interpolation
+    float* dump_gap;
+};
+
+__device__ __forceinline__ float gap_fill(const float* __restrict__ line, int stride, int gap)
+{
+    // line points at the pixel; neighbours at +-j*stride.  Same decisions as k_gap_pass without add_corners.
+    const float d = line[0];
+    if (d >= 0.f) return d;
+    int l = 1, r = 1;
+    while (l <= gap && !(line[-l * stride] >= 0.f)) l++;
+    while (r <= gap && !(line[r * stride] >= 0.f)) r++;
+    if (l <= gap && r <= gap && l + r - 1 <= gap) {
+        const float d1 = line[-l * stride], d2 = line[r * stride];
+        return fabsf(__fsub_rn(d1, d2)) < 3.0f ? __fmul_rn(__fadd_rn(d1, d2), 0.5f) : fminf(d1, d2);   // :1379-1380
+    }
+    return d;
+}
+
+template <int TAPS, bool MEAN>
+__global__ void __launch_bounds__(kFuseThreads)
+k_post_fused(const FuseArgs a)
+{
+    constexpr int BACK = MEAN ? (TAPS == 8 ? 4 : 2) : 0, FWD = MEAN ? TAPS - BACK - 1 : 0, G = kFuseGap;
+    constexpr int AW = kFuseTW + BACK + FWD + 2 * G, AH = kFuseTH + BACK + FWD + 2 * G;
+    constexpr int BW = kFuseTW + BACK + FWD, BH = AH;
+    constexpr int CW = BW, CH = kFuseTH + BACK + FWD;
+    constexpr int MW = kFuseTW, MH = CH;
+    __shared__ float sA[AH * AW];      // A, later M
+    __shared__ float sB[BH * BW];
+    __shared__ float sC[CH * CW];
+    const int c0 = blockIdx.x * kFuseTW, r0 = blockIdx.y * kFuseTH;
+    const int Dw = a.Dw, Dh = a.Dh;
+
+    // ---- A: load (+ speckle apply, elas.cpp:1309-1317) ------------------------------------------
+    // pixel -> run start -> root -> size is a chain of dependent L2 loads: four elements per thread are
+    // walked together so that the chains overlap
+    for (int i0 = threadIdx.x; i0 < AH * AW; i0 += 4 * kFuseThreads) {
+        int idx[4], root[4];
+        float d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * kFuseThreads;
+            const int y = i / AW, x = i - y * AW;
+            const int v = r0 - BACK - G + y, u = c0 - BACK - G + x;
+            idx[k] = (i < AH * AW && v >= 0 && v < Dh && u >= 0 && u < Dw) ? v * Dw + u : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = idx[k] >= 0 ? a.in[idx[k]] : (float)kInvalid;
+        if (a.apply) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) root[k] = d[k] >= 0.f ? a.parent[idx[k]] : -1;      // run start
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (root[k] >= 0) root[k] = a.parent[root[k]];      // its root (k_seg_count left it one hop away)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (root[k] < 0) continue;
+                for (int up = a.parent[root[k]]; up != root[k]; up = a.parent[root[k]]) root[k] = up;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (root[k] >= 0) { if (a.size[root[k]] < a.speckle) d[k] = (float)kInvalid; }
+                else if (1 < a.speckle) d[k] = (float)kInvalid;     // an invalid pixel is a segment of one (:1248-1250)
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * kFuseThreads;
+            if (i >= AH * AW) continue;
+            sA[i] = d[k];
+            if (a.dump_seg && idx[k] >= 0) {
+                const int y = i / AW, x = i - y * AW;
+                const int v = r0 - BACK - G + y, u = c0 - BACK - G + x;
+                if (v >= r0 && v < r0 + kFuseTH && u >= c0 && u < c0 + kFuseTW) a.dump_seg[idx[k]] = d[k];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- B: gap row pass (elas.cpp:1350-1437) -----------------------------------------------------
+    for (int i = threadIdx.x; i < BH * BW; i += kFuseThreads) {
+        const int y = i / BW, x = i - y * BW;
+        sB[i] = gap_fill(sA + y * AW + x + G, 1, a.gap);
+    }
+    __syncthreads();
+    // ---- C: gap column pass (elas.cpp:1440-1529) ----------------------------------------------------
+    for (int i = threadIdx.x; i < CH * CW; i += kFuseThreads) {
+        const int y = i / CW, x = i - y * CW;
+        const float d = gap_fill(sB + (y + G) * BW + x, BW, a.gap);
+        sC[i] = d;
+        if (a.dump_gap || !MEAN) {
+            const int v = r0 - BACK + y, u = c0 - BACK + x;
+            if (v >= r0 && v < min(r0 + kFuseTH, Dh) && u >= c0 && u < min(c0 + kFuseTW, Dw))
+                (MEAN ? a.dump_gap : a.out)[v * Dw + u] = d;
+        }
+    }
+    if (!MEAN) return;
+    __syncthreads();
+    // ---- M: mean row pass (elas.cpp:1651-1700; rows 3..Dh-4, centres BACK..Dw-FWD-1) ------------------
+    float* sM = sA;
+    for (int i = threadIdx.x; i < MH * MW; i += kFuseThreads) {
+        const int y = i / MW, x = i - y * MW;
+        const int v = r0 - BACK + y, u = c0 + x;
+        const float* centre = sC + y * CW + x + BACK;
+        float o = *centre;
+        if (v >= 3 && v < Dh - 3 && u >= BACK && u + FWD < Dw) {
+            float r;
+            // mean_window indexes line[c * stride]: pass the line origin such that c = u
+            if (mean_window<TAPS>(centre - u, 1, u, &r)) o = r;
+        }
+        sM[i] = o;
+    }
+    __syncthreads();
+    // ---- out: mean column pass (elas.cpp:1703-1746; columns 3..Dw-4, centres BACK..Dh-FWD-1) ----------
+    for (int i = threadIdx.x; i < kFuseTH * kFuseTW; i += kFuseThreads) {
+        const int y = i / kFuseTW, x = i - y * kFuseTW;
+        const int v = r0 + y, u = c0 + x;
+        if (v >= Dh || u >= Dw) continue;
+        float o = sC[(y + BACK) * CW + x + BACK];
+        if (u >= 3 && u < Dw - 3 && v >= BACK && v + FWD < Dh) {
+            float r;
+            if (mean_window<TAPS>(sM + (y + BACK) * MW + x - (ptrdiff_t)v * MW, MW, v, &r)) o = r;
+        }
+        a.out[v * Dw + u] = o;
+    }
+}
+
 inline dim3 grid2d(int Dw, int Dh, int bx) { return dim3((Dw + bx - 1) / bx, Dh, 1); }
 
 }  // namespace
@@ -327,18 +520,59 @@ void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float*
     count_launch();
 }
 
+bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 12 <= 160 * 1024; }
+
+// K8 for both maps + the run labelling of D1 (launch_segments(..., rows_done = true) continues from there)
+void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
+                    float* O1, float* O2, int32_t* parent, int32_t* size, cudaStream_t s)
+{
+    const size_t smem = (size_t)g.Dw * 12;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_lr_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    k_lr_rows<<<g.Dh, 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
+                                      D1, D2, O1, O2, parent, size);
+    count_launch();
+}
+
 void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, cudaStream_t s)
+                     int32_t* size, cudaStream_t s, bool apply, bool rows_done)
 {
     const int n = g.Dw * g.Dh;
     int speckle = p.speckle_size;
     if (p.subsampling) speckle = (int)(sqrtf((float)p.speckle_size) * 2);            // :1218
     const float thr = p.speckle_sim_threshold;
-    k_seg_rows<<<g.Dh, 256, 0, s>>>(g.Dw, thr, D, parent, size);
+    if (!rows_done) { k_seg_rows<<<g.Dh, 256, 0, s>>>(g.Dw, thr, D, parent, size); count_launch(); }
     k_seg_merge<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent);
     k_seg_count<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size);
+    if (!apply) { count_launch(2); return; }
     k_seg_apply<<<(n + 255) / 256, 256, 0, s>>>(n, speckle, D, parent, size);
-    count_launch(4);
+    count_launch(3);
+}
+
+bool post_fusable(const elas_b200_params& p)
+{
+    const int gap = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;
+    return gap <= kFuseGap && gap >= 0 && !p.add_corners;
+}
+
+// speckle apply (when parent != nullptr) + gap interpolation + adaptive mean (when filter_adaptive_mean)
+void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
+                       const int32_t* size, float* out, float* dump_seg, float* dump_gap, cudaStream_t s)
+{
+    FuseArgs a;
+    a.Dw = g.Dw; a.Dh = g.Dh;
+    a.gap = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;               // :1335-1341
+    a.speckle = p.subsampling ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;   // :1218
+    a.apply = parent != nullptr;
+    a.in = in; a.parent = parent; a.size = size; a.out = out; a.dump_seg = dump_seg; a.dump_gap = dump_gap;
+    const dim3 grid((g.Dw + kFuseTW - 1) / kFuseTW, (g.Dh + kFuseTH - 1) / kFuseTH, 1);
+    if (!p.filter_adaptive_mean) k_post_fused<8, false><<<grid, kFuseThreads, 0, s>>>(a);
+    else if (p.subsampling)      k_post_fused<4, true><<<grid, kFuseThreads, 0, s>>>(a);
+    else                         k_post_fused<8, true><<<grid, kFuseThreads, 0, s>>>(a);
+    count_launch();
 }
 
 void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, cudaStream_t s)

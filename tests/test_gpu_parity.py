@@ -138,7 +138,7 @@ def test_batch_pipeline_equals_single_frames(oracle):
         launches = e.launch_count()
     finally:
         e.close()
-    assert status == [0] * len(pairs) and launches > 10 * len(pairs)
+    assert status == [0] * len(pairs) and launches >= 9 * len(pairs)      # 9 kernels per frame
     for i, (L, R) in enumerate(pairs):
         _, O1, O2 = oracle.process(L, R, p)
         assert bits_equal(D1[i], O1) and bits_equal(D2[i], O2), f"frame {i}"
