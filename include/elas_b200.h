@@ -117,6 +117,32 @@ int32_t elas_b200_process_batch_device(elas_b200_ctx* ctx, int32_t n,
                                        int32_t bytes_per_line, int32_t* status);
 
 /* ------------------------------------------------------------------------------------------
+ * 2b. The consumers of D1 inside StereoThread::run, computed where D1 already is (HBM):
+ *     the HSV colour map shown by View2D (stereothread.cpp:116-147) and the back-projected
+ *     map StereoThread::createCurrentMap builds for the 3-D reconstruction (:180-255).
+ *     D1 == NULL uses the left disparity map the slot's last frame left on the device (no
+ *     device->host->device round trip); otherwise D1 is a host or device pointer to a dense
+ *     map.  Likewise I1 == NULL uses the slot's device copy of the last left image.  Output
+ *     pointers may be host or device memory.  Synchronous.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct elas_b200_view {
+    float  f, cu, cv, base;   /* StereoThread::getIntrinsics, stereothread.cpp:441-447 */
+    float  max_dist;          /* stereothread.h:196 */
+    float  gain;              /* stereothread.h:181; 0 = no gain ramp (stereothread.cpp:234) */
+    double H[12];             /* rows 0..2 of the accumulated pose _H_total (libviso2 Matrix, double) */
+} elas_b200_view;
+
+/* color: 3 floats (r,g,b) per pixel of the disparity map (width x height, halved with subsampling). */
+int32_t elas_b200_colormap(elas_b200_ctx* ctx, int32_t slot, const float* D1, float* color);
+
+/* I, D, X, Y, Z: width x height floats each.  D = D1 with -1 where z = f*base/d falls outside
+ * (0.1, max_dist); X/Y/Z are 0 where the reference writes nothing (d <= 0 or z out of range).
+ * Only without subsampling (createCurrentMap indexes D1 at full resolution). */
+int32_t elas_b200_reproject(elas_b200_ctx* ctx, int32_t slot, const uint8_t* I1, int32_t bytes_per_line,
+                            const float* D1, const elas_b200_view* view,
+                            float* I, float* D, float* X, float* Y, float* Z);
+
+/* ------------------------------------------------------------------------------------------
  * 3. Introspection for parity tests and the bench (not used by stereomapper).
  * ------------------------------------------------------------------------------------------ */
 

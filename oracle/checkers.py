@@ -15,6 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libelas_ref.so")
 ORACLE_SO = os.path.join(HERE, "_build", "libelas_oracle.so")
+VIEW_REF_SO = os.path.join(HERE, "_ref", "libview_ref.so")
 
 PARAM_FIELDS = [
     ("disp_min", C.c_int32), ("disp_max", C.c_int32), ("support_threshold", C.c_float),
@@ -184,3 +185,44 @@ class OracleElas(_StageLib):
         out = np.empty((2 * len(s) + 8, 3), np.int32)
         n = self.lib.oracle_delaunay(s.ctypes.data, len(s), int(right_image), out.ctypes.data, len(out))
         return out[:n].copy()
+
+
+class ViewChecker:
+    """Colour map + back-projection (stereothread.cpp:116-147, :180-255): the plain-C restatement
+    (kind="oracle") or the reference's own statements compiled by oracle/Makefile (kind="ref")."""
+
+    def __init__(self, kind="oracle"):
+        if kind == "ref":
+            self.lib, prefix = C.CDLL(VIEW_REF_SO), "ref"
+        else:
+            if not os.path.exists(ORACLE_SO):
+                build("oracle")
+            self.lib, prefix = C.CDLL(ORACLE_SO), "oracle"
+        self._colormap = getattr(self.lib, f"{prefix}_colormap")
+        self._colormap.restype = None
+        self._colormap.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        self._reproject = getattr(self.lib, f"{prefix}_reproject")
+        self._reproject.restype = None
+        self._reproject.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_void_p] * 5
+
+    def colormap(self, D1):
+        D1 = np.ascontiguousarray(D1, np.float32)
+        out = np.empty(D1.shape + (3,), np.float32)
+        self._colormap(D1.ctypes.data, D1.shape[1], D1.shape[0], out.ctypes.data)
+        return out
+
+    def reproject(self, I1, D1, view, H):
+        """view = (f, cu, cv, base, max_dist, gain); H = 3x4 pose.  Returns I, D, X, Y, Z."""
+        I1 = np.ascontiguousarray(I1, np.uint8)
+        D1 = np.ascontiguousarray(D1, np.float32)
+        h, w = D1.shape
+        view = np.ascontiguousarray(view, np.float32)
+        H = np.ascontiguousarray(H, np.float64).reshape(12)
+        outs = [np.empty((h, w), np.float32) for _ in range(5)]
+        self._reproject(I1.ctypes.data, D1.ctypes.data, w, h, I1.strides[0], view.ctypes.data, H.ctypes.data,
+                        *[o.ctypes.data for o in outs])
+        return outs
+
+
+def have_view_ref():
+    return os.path.exists(VIEW_REF_SO)

@@ -1240,3 +1240,86 @@ void oracle_planes(const int32_t* sup, const int32_t* tri, int32_t nt, float* pl
 {
     disparity_planes(sup, tri, nt, planes);
 }
+
+/* =============================================================================================
+ * the consumers of D1 inside StereoThread (pinned against the reference's own
+ * statements through oracle/_ref/libview_ref.so, tests/test_view.py).
+ * ============================================================================================= */
+
+/* HSV colour map of min(D1/200, 1), stereothread.cpp:116-147.  out = 3 floats per pixel.
+ * Expression types follow the C++ source: h2 and x are doubles narrowed to float, fmod is the float
+ * overload (exact either way). */
+void oracle_colormap(const float* D1, int32_t d_width, int32_t d_height, float* out)
+{
+    const float d_max = 200;                                                   /* :117 */
+    for (int32_t i = 0; i < d_width * d_height; i++) {
+        float* o = out + 3 * (size_t)i;
+        float val = D1[i] / d_max;                                             /* :130 */
+        if ((float)1.0 < val) val = (float)1.0;                                /* std::min(a,b): b < a ? b : a */
+        if (val <= 0) { o[0] = 0; o[1] = 0; o[2] = 0; continue; }              /* :131-134 */
+        const float h2 = (float)(6.0 * (1.0 - (double)val));                   /* :137 */
+        const float x = (float)(1.0 * (1.0 - fabs((double)fmodf(h2, (float)2.0) - 1.0)));   /* :138 */
+        if      (0 <= h2 && h2 < 1)  { o[0] = 1; o[1] = x; o[2] = 0; }         /* :139-144 */
+        else if (1 <= h2 && h2 < 2)  { o[0] = x; o[1] = 1; o[2] = 0; }
+        else if (2 <= h2 && h2 < 3)  { o[0] = 0; o[1] = 1; o[2] = x; }
+        else if (3 <= h2 && h2 < 4)  { o[0] = 0; o[1] = x; o[2] = 1; }
+        else if (4 <= h2 && h2 < 5)  { o[0] = x; o[1] = 0; o[2] = 1; }
+        else if (5 <= h2 && h2 <= 6) { o[0] = 1; o[1] = 0; o[2] = x; }
+        else                         { o[0] = 0; o[1] = 0; o[2] = 0; }         /* unreachable for val in (0,1] */
+    }
+}
+
+/* Back-projection of D1 and the intensity image with its border gain, StereoThread::createCurrentMap,
+ * stereothread.cpp:180-255.  view = {f, cu, cv, base, max_dist, gain}; H = rows 0..2 of the pose
+ * (3x4, row-major, double like libviso2's Matrix).  X/Y/Z are 0 where the reference writes nothing. */
+void oracle_reproject(const uint8_t* I1, const float* D1, int32_t width, int32_t height, int32_t step,
+                      const float* view, const double* H, float* I, float* D, float* X, float* Y, float* Z)
+{
+    const float f = view[0], cu = view[1], cv = view[2], base = view[3], max_dist = view[4], gain = view[5];
+    float h[12];
+    for (int k = 0; k < 12; k++) h[k] = (float)H[k];                           /* :201-204 */
+    for (int32_t v = 0; v < height; v++)                                       /* :193-200 */
+        for (int32_t u = 0; u < width; u++) {
+            const size_t a = (size_t)v * width + u;
+            D[a] = D1[a];
+            I[a] = (float)(((float)I1[(size_t)v * step + u]) / 255.0);
+            X[a] = Y[a] = Z[a] = 0.f;
+        }
+    for (int32_t u = 0; u < width; u++)                                        /* :205-229 */
+        for (int32_t v = 0; v < height; v++) {
+            const size_t a = (size_t)v * width + u;
+            const float d = D[a];
+            if (d > 0) {
+                const float z = (f * base) / d;
+                if (((double)z > 0.1) && (z < max_dist)) {
+                    const float x = ((float)u - cu) * base / d;
+                    const float y = ((float)v - cv) * base / d;
+                    X[a] = h[0] * x + h[1] * y + h[2] * z + h[3];
+                    Y[a] = h[4] * x + h[5] * y + h[6] * z + h[7];
+                    Z[a] = h[8] * x + h[9] * y + h[10] * z + h[11];
+                } else {
+                    D[a] = -1;
+                }
+            }
+        }
+    /* gain ramp on the image border, :231-252 */
+    int32_t margin = 200 < width / 2 ? 200 : width / 2;
+    if (height / 2 < margin) margin = height / 2;
+    float gain_inv = 1;
+    if (gain) gain_inv = (float)(1.0 / gain);
+    for (int32_t i = 0; i < margin; i++) {
+        const float g = (float)(((float)(margin - i) * gain_inv + (float)i * 1.0) / (float)margin);
+        for (int32_t u = margin; u < width - margin; u++) {
+            float* p0 = &I[(size_t)i * width + u];
+            float* p1 = &I[(size_t)(height - i - 1) * width + u];
+            float t = g * *p0; t = t < 0.f ? 0.f : t; *p0 = 1.f < t ? 1.f : t;
+            t = g * *p1; t = t < 0.f ? 0.f : t; *p1 = 1.f < t ? 1.f : t;
+        }
+        for (int32_t v = margin; v < height - margin; v++) {
+            float* p0 = &I[(size_t)v * width + i];
+            float* p1 = &I[(size_t)v * width + width - i - 1];
+            float t = g * *p0; t = t < 0.f ? 0.f : t; *p0 = 1.f < t ? 1.f : t;
+            t = g * *p1; t = t < 0.f ? 0.f : t; *p1 = 1.f < t ? 1.f : t;
+        }
+    }
+}

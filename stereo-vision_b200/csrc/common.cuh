@@ -118,6 +118,11 @@ void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* 
 // K12 median (elas.cpp:1758-1838)
 void launch_median(const FrameGeom& g, float* D, float* tmp, cudaStream_t s);
 
+// D1's consumers in StereoThread: colour map (stereothread.cpp:116-147), back-projection (:180-255)
+void launch_colormap(int n, const float* D1, float* out, cudaStream_t s);
+void launch_reproject(int W, int H, const uint8_t* img, int pitch, const float* D1, const elas_b200_view& view,
+                      float* I, float* D, float* X, float* Y, float* Z, cudaStream_t s);
+
 // number of kernel launches issued through the launchers above (process-wide, relaxed)
 long long launches_issued();
 void count_launch(int n = 1);

@@ -58,7 +58,6 @@ struct Slot {
     // device
     uint8_t* d_img[2] = {nullptr, nullptr};
     uint4* d_desc[2] = {nullptr, nullptr};
-    int16_t* d_dcan = nullptr;
     int32_t* d_tables = nullptr;               // [support n x 3 | tri1 t1 x 3 | tri2 t2 x 3], packed, one copy per frame
     TriRaster* d_tri[2] = {nullptr, nullptr};  // raster records, written by k_planes
     float* d_planes[2] = {nullptr, nullptr};   // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle, written by k_planes
@@ -75,11 +74,16 @@ struct Slot {
     int16_t* h_dcan = nullptr;
     int32_t* h_tables = nullptr;
     cudaEvent_t ev_sync = nullptr;             // blocking wait (no spinning) when slots outnumber host cores
+    cudaStream_t copy_stream = nullptr;        // disparity maps go out here while the slot starts its next frame
+    cudaEvent_t ev_done = nullptr;             // phase B kernels finished
+    cudaEvent_t ev_out = nullptr;              // the frame's maps are in the caller's buffers
     // host stage + tables of the last frame (kept for elas_b200_time_matching)
     HostStage host;
     int n_tri[2] = {0, 0};
     int n_units = 0;
     size_t units_at = 0;
+    float* d_view = nullptr;                   // colour map / back-projection outputs (5 planes), allocated on first use
+    float* last_D1 = nullptr;                  // where the last frame's final left map lives on the device
     int map_tag = 0;                           // frame tag of the triangle-id map entries (k_grid_raster.cu)
     int scratch_phase = 0;                     // which of the two grid scatter buffers this frame uses
     bool tables_valid = false;
@@ -169,10 +173,13 @@ void free_slot(Slot& s)
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
         cudaFree(s.d_planes[k]);
     }
-    cudaFree(s.d_dcan); cudaFree(s.d_tables); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
+    cudaFree(s.d_tables); cudaFree(s.d_view); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
     cudaFree(s.d_parent); cudaFree(s.d_size);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_sync) cudaEventDestroy(s.ev_sync);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_out) cudaEventDestroy(s.ev_out);
+    if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     for (auto& m : s.timer.marks) cudaEventDestroy(m.second);
     if (s.timer.begin) cudaEventDestroy(s.timer.begin);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -184,6 +191,10 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
     const size_t cells = (size_t)g.gw * g.gh * g.gwords;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    const unsigned ev_flags = cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0);
+    CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_out, ev_flags));
     for (int k = 0; k < 2; k++) {
         CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
         CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
@@ -201,13 +212,13 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     CK(cudaMalloc(&s.d_tables, table_ints * 4));
     CK(cudaMallocHost(&s.h_tables, table_ints * 4));
     CK(cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
-    CK(cudaMalloc(&s.d_dcan, (size_t)g.Wc * g.Hc * 2));
     CK(cudaMalloc(&s.d_grid_scratch, 4 * cells * 4));                      // two buffers of [2][cells] words
     CK(cudaMemset(s.d_grid_scratch, 0, 4 * cells * 4));
     CK(cudaMalloc(&s.d_tmp, 2 * ND * 4));
     CK(cudaMalloc(&s.d_parent, ND * 4));
     CK(cudaMalloc(&s.d_size, ND * 4));
-    CK(cudaMallocHost(&s.h_dcan, (size_t)g.Wc * g.Hc * 2));
+    // the candidate lattice lives in pinned host memory only: K2 writes it across PCIe (k_support.cu)
+    CK(cudaHostAlloc(&s.h_dcan, (size_t)g.Wc * g.Hc * 2, cudaHostAllocMapped));
     return ELAS_B200_OK;
 }
 
@@ -287,12 +298,19 @@ int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool devic
     return ELAS_B200_OK;
 }
 
-int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I2, float* D1,
-                  float* D2, int bytes_per_line, bool device_io)
+// One frame = phase A (GPU) -> host stage -> phase B (GPU) -> maps out.  The four steps are separate
+// so that a slot's worker can start frame i+1 while the maps of frame i are still on their way out.
+struct FrameIO {
+    const uint8_t* I1; const uint8_t* I2;
+    float* D1; float* D2;
+    int bytes_per_line; bool device_io;
+};
+
+// ---- phase A: images in, descriptors, support search (lattice lands in pinned host memory) ------
+int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
 {
     const FrameGeom& g = c->g;
     const elas_b200_params& p = c->p;
-    const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
     cudaStream_t st = s.stream;
     if (s.capture) s.stages.clear();
     s.tables_valid = false;
@@ -300,17 +318,24 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         if (!s.timer.begin) cudaEventCreate(&s.timer.begin);
         cudaEventRecord(s.timer.begin, st);
     }
-
     const long long t0 = now_ns();
-    // ---- phase A: images in, descriptors, support search, lattice out --------------------------
-    if (int32_t rc = copy_image_in(g, s.d_img[0], I1, bytes_per_line, st)) return rc;
-    if (int32_t rc = copy_image_in(g, s.d_img[1], I2, bytes_per_line, st)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
     mark(c, s, "copy_in");
     launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
     mark(c, s, "descriptor");
-    launch_support(g, p, s.d_desc[0], s.d_desc[1], s.d_dcan, st);
+    launch_support(g, p, s.d_desc[0], s.d_desc[1], s.h_dcan, st);
     mark(c, s, "support");
-    CK(cudaMemcpyAsync(s.h_dcan, s.d_dcan, (size_t)g.Wc * g.Hc * 2, cudaMemcpyDeviceToHost, st));
+    c->ns_submit_a += now_ns() - t0;
+    return ELAS_B200_OK;
+}
+
+// ---- wait for phase A, then the host stage.  Returns the number of support points in *n_out. ------
+int32_t phase_a_finish_and_host(elas_b200_ctx* c, Slot& s, int* n_out)
+{
+    const FrameGeom& g = c->g;
+    const elas_b200_params& p = c->p;
+    const size_t N = (size_t)g.W * g.H;
     const long long t1 = now_ns();
     if (int32_t rc = wait_stream(c, s)) return rc;
     const long long t2 = now_ns();
@@ -321,40 +346,48 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         int32_t lat[2] = {g.Wc, g.Hc};
         grab_host(s, "lattice_dims", lat, sizeof lat);
     }
-
-    // ---- host stage ---------------------------------------------------------------------------
     const int n = s.host.run(g, p, s.h_dcan, s.capture, false);
+    *n_out = n;
     if (s.capture) {
         grab_host(s, "dcan_incon", s.host.dcan_incon.data(), s.host.dcan_incon.size() * 2);
         grab_host(s, "dcan", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
         grab_host(s, "support", s.host.support.data(), s.host.support.size() * 4);
     }
-    if (n < 3) {
-        if (int32_t rc = fill_invalid(c, s, D1, D2, device_io)) return rc;
-        return ELAS_B200_E_FEW_SUPPORT;
+    if (n >= 3) {
+        const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
+        const int n_units = (int)s.host.units.size() / 2;
+        if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap || n_units > c->unit_cap) return ELAS_B200_E_BAD_ARG;
+        s.n_tri[0] = nt1; s.n_tri[1] = nt2;
+        std::memcpy(s.h_tables, s.host.support.data(), (size_t)n * 12);
+        std::memcpy(s.h_tables + 3 * n, s.host.tri[0].data(), (size_t)nt1 * 12);
+        std::memcpy(s.h_tables + 3 * (n + nt1), s.host.tri[1].data(), (size_t)nt2 * 12);
+        const size_t units_at = 3 * (size_t)(n + nt1 + nt2) + ((n + nt1 + nt2) & 1);      // 8-byte aligned
+        std::memcpy(s.h_tables + units_at, s.host.units.data(), (size_t)n_units * 8);
+        s.n_units = n_units; s.units_at = units_at;
+        if (s.capture) {
+            grab_host(s, "tri1", s.host.tri[0].data(), s.host.tri[0].size() * 4);
+            grab_host(s, "tri2", s.host.tri[1].data(), s.host.tri[1].size() * 4);
+            int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
+            grab_host(s, "grid_dims", gd, sizeof gd);
+        }
     }
-    const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
-    const int n_units = (int)s.host.units.size() / 2;
-    if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap || n_units > c->unit_cap) return ELAS_B200_E_BAD_ARG;
-    s.n_tri[0] = nt1; s.n_tri[1] = nt2;
-    std::memcpy(s.h_tables, s.host.support.data(), (size_t)n * 12);
-    std::memcpy(s.h_tables + 3 * n, s.host.tri[0].data(), (size_t)nt1 * 12);
-    std::memcpy(s.h_tables + 3 * (n + nt1), s.host.tri[1].data(), (size_t)nt2 * 12);
-    const size_t units_at = 3 * (size_t)(n + nt1 + nt2) + ((n + nt1 + nt2) & 1);      // 8-byte aligned
-    std::memcpy(s.h_tables + units_at, s.host.units.data(), (size_t)n_units * 8);
-    s.n_units = n_units; s.units_at = units_at;
+    c->ns_wait_a += t2 - t1; c->ns_host += now_ns() - t2;
+    return ELAS_B200_OK;
+}
+
+// ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------------
+int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
+{
+    const FrameGeom& g = c->g;
+    const elas_b200_params& p = c->p;
+    const size_t ND = (size_t)g.Dw * g.Dh;
+    cudaStream_t st = s.stream;
+    const int n = s.host.n_support, nt1 = s.n_tri[0], nt2 = s.n_tri[1], n_units = s.n_units;
+    const size_t units_at = s.units_at;
     const int32_t* d_support = s.d_tables;
     const int32_t* d_tri1 = s.d_tables + 3 * n;
     const int32_t* d_tri2 = s.d_tables + 3 * (n + nt1);
-    if (s.capture) {
-        grab_host(s, "tri1", s.host.tri[0].data(), s.host.tri[0].size() * 4);
-        grab_host(s, "tri2", s.host.tri[1].data(), s.host.tri[1].size() * 4);
-        int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
-        grab_host(s, "grid_dims", gd, sizeof gd);
-    }
-
     const long long t3 = now_ns();
-    // ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------
     if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
     CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (units_at + 2 * (size_t)n_units) * 4, cudaMemcpyHostToDevice, st));
     mark(c, s, "tables_in");
@@ -391,47 +424,52 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         if (int32_t rc = grab(s, "D1_raw", s.d_raw[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2_raw", s.d_raw[1], ND * 4)) return rc;
     }
+    const int n_post = p.postprocess_only_left ? 1 : 2;                                  // elas.cpp:121-159
+    const bool fused_post = post_fusable(p);
+    // With device-resident output buffers the last kernel that touches a map writes it straight into the
+    // caller's buffer.  D2 without post-processing is final after the L/R check.
+    float* lr_out[2] = {s.d_D[0], s.d_D[1]};
+    if (io.device_io && n_post == 1) lr_out[1] = io.D2;
     const bool rows_fused = lr_rows_fusable(g);
-    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], s.d_parent, s.d_size, st);
-    else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], s.d_D[1], st);         // elas.cpp:116
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], s.d_parent, s.d_size, st);
+    else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], st);          // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
-        if (int32_t rc = grab(s, "D1_lr", s.d_D[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_lr", s.d_D[1], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D1_lr", lr_out[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_lr", lr_out[1], ND * 4)) return rc;
     }
-    const int n_post = p.postprocess_only_left ? 1 : 2;                                  // elas.cpp:121-159
-    float* final_map[2] = {s.d_D[0], s.d_D[1]};
-    if (post_fusable(p)) {
+    float* final_map[2] = {lr_out[0], lr_out[1]};
+    if (fused_post) {
         // speckle sizes (K9 rows/merge/count), then ONE kernel for speckle apply + gap interpolation +
-        // adaptive mean; it reads d_D and writes the final map into d_raw (dead after the L/R check)
+        // adaptive mean; it reads d_D and writes the final map (d_raw is dead after the L/R check)
         for (int k = 0; k < n_post; k++) {
             launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, false, rows_fused && k == 0);
             mark(c, s, k ? "segments2" : "segments");
-            launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, s.d_raw[k],
+            final_map[k] = io.device_io ? (k ? io.D2 : io.D1) : s.d_raw[k];
+            launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, final_map[k],
                               s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, st);
-            final_map[k] = s.d_raw[k];
             if (s.capture) {
                 if (int32_t rc = grab(s, k ? "D2_seg" : "D1_seg", s.d_tmp, ND * 4)) return rc;
-                if (int32_t rc = grab(s, k ? "D2_gap" : "D1_gap", p.filter_adaptive_mean ? s.d_tmp + ND : s.d_raw[k], ND * 4)) return rc;
+                if (int32_t rc = grab(s, k ? "D2_gap" : "D1_gap", p.filter_adaptive_mean ? s.d_tmp + ND : final_map[k], ND * 4)) return rc;
             }
         }
         mark(c, s, "apply+gap+mean");
         if (s.capture && n_post == 1) {
-            if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_seg", lr_out[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", lr_out[1], ND * 4)) return rc;
         }
     } else {
         for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, true, rows_fused && k == 0);
         mark(c, s, "segments");
         if (s.capture) {
-            if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D1_seg", lr_out[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_seg", lr_out[1], ND * 4)) return rc;
         }
         for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, st);
         mark(c, s, "gap");
         if (s.capture) {
-            if (int32_t rc = grab(s, "D1_gap", s.d_D[0], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D1_gap", lr_out[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", lr_out[1], ND * 4)) return rc;
         }
         if (p.filter_adaptive_mean) {
             for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, st);
@@ -446,20 +484,39 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
         for (int k = 0; k < n_post; k++) launch_median(g, final_map[k], s.d_tmp, st);
         mark(c, s, "median");
     }
-    CK(cudaMemcpyAsync(D1, final_map[0], ND * 4, cudaMemcpyDefault, st));
-    CK(cudaMemcpyAsync(D2, final_map[1], ND * 4, cudaMemcpyDefault, st));
-    mark(c, s, "copy_out");
-    const long long t4 = now_ns();
-    if (int32_t rc = wait_stream(c, s)) return rc;
-    CK(cudaGetLastError());
-    const long long t5 = now_ns();
-    c->ns_submit_a += t1 - t0; c->ns_wait_a += t2 - t1; c->ns_host += t3 - t2;
-    c->ns_submit_b += t4 - t3; c->ns_wait_b += t5 - t4; c->frames += 1;
     if (s.capture) {
         if (int32_t rc = grab(s, "D1", final_map[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2", final_map[1], ND * 4)) return rc;
     }
+    s.last_D1 = final_map[0];
+    // maps out: nothing to do for maps already written in place; the others are copied on the slot's copy
+    // stream so that the compute stream is free for the next frame (stage timing keeps them in line)
+    float* user[2] = {io.D1, io.D2};
+    cudaStream_t out_stream = st;
+    bool copies = false;
+    for (int k = 0; k < 2; k++) copies |= final_map[k] != user[k];
+    if (copies && !c->timing) {
+        CK(cudaEventRecord(s.ev_done, st));
+        CK(cudaStreamWaitEvent(s.copy_stream, s.ev_done, 0));
+        out_stream = s.copy_stream;
+    }
+    for (int k = 0; k < 2; k++)
+        if (final_map[k] != user[k]) CK(cudaMemcpyAsync(user[k], final_map[k], ND * 4, cudaMemcpyDefault, out_stream));
+    mark(c, s, "copy_out");
+    CK(cudaEventRecord(s.ev_out, out_stream));
+    c->ns_submit_b += now_ns() - t3;
+    return ELAS_B200_OK;
+}
+
+// ---- the frame's maps are in the caller's buffers ----------------------------------------------------
+int32_t frame_finish(elas_b200_ctx* c, Slot& s)
+{
+    const long long t4 = now_ns();
+    CK(cudaEventSynchronize(s.ev_out));
+    CK(cudaGetLastError());
+    c->ns_wait_b += now_ns() - t4; c->frames += 1;
     if (c->timing) {
+        CK(cudaStreamSynchronize(s.stream));
         s.timer.last.clear();
         cudaEvent_t prev = s.timer.begin;
         // marks are appended in first-use order, which is pipeline order
@@ -472,10 +529,27 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     return ELAS_B200_OK;
 }
 
+// one frame, start to finish (the drop-in call and elas_b200_process_ctx)
+int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I2, float* D1,
+                  float* D2, int bytes_per_line, bool device_io)
+{
+    const FrameIO io{I1, I2, D1, D2, bytes_per_line, device_io};
+    if (int32_t rc = phase_a_submit(c, s, io)) return rc;
+    int n = 0;
+    if (int32_t rc = phase_a_finish_and_host(c, s, &n)) return rc;
+    if (n < 3) {
+        if (int32_t rc = fill_invalid(c, s, D1, D2, device_io)) return rc;
+        return ELAS_B200_E_FEW_SUPPORT;
+    }
+    if (int32_t rc = phase_b_submit(c, s, io)) return rc;
+    return frame_finish(c, s);
+}
+
 void worker_main(elas_b200_ctx* c, int slot)
 {
     cudaSetDevice(c->device);
     uint64_t seen = 0;
+    Slot& s = *c->slots[slot];
     for (;;) {
         elas_b200_ctx::Job* job = nullptr;
         {
@@ -486,15 +560,32 @@ void worker_main(elas_b200_ctx* c, int slot)
             seen = c->job_seq;
             job->active++;
         }
-        for (;;) {
-            const int i = job->next.fetch_add(1);
-            if (i >= job->n) break;
-            const int32_t rc = run_frame(c, *c->slots[slot], job->I1[i], job->I2[i], job->D1[i], job->D2[i],
-                                         job->bpl, job->device_io);
+        auto report = [&](int i, int32_t rc) {
             if (job->status) job->status[i] = rc;
             if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
             job->done.fetch_add(1);
+        };
+        // software pipeline over this slot's frames: frame i's maps travel out (copy stream) while frame
+        // i+1 runs phase A and its host stage; frame i is reported once its maps have landed
+        int in_flight = -1;
+        for (;;) {
+            const int i = job->next.fetch_add(1);
+            if (i >= job->n) break;
+            const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
+            int n = 0;
+            int32_t rc = phase_a_submit(c, s, io);
+            if (!rc) rc = phase_a_finish_and_host(c, s, &n);
+            if (in_flight >= 0) { report(in_flight, frame_finish(c, s)); in_flight = -1; }
+            if (!rc && n < 3) {
+                rc = fill_invalid(c, s, io.D1, io.D2, io.device_io);
+                if (!rc) rc = ELAS_B200_E_FEW_SUPPORT;
+            } else if (!rc) {
+                rc = phase_b_submit(c, s, io);
+                if (!rc) { in_flight = i; continue; }
+            }
+            report(i, rc);
         }
+        if (in_flight >= 0) report(in_flight, frame_finish(c, s));
         {
             std::lock_guard<std::mutex> lk(c->mu);
             job->active--;
@@ -682,6 +773,65 @@ int32_t elas_b200_process(const elas_b200_params* p, const uint8_t* I1, const ui
         g_cache[key] = c;
     } else c = it->second;
     return elas_b200_process_ctx(c, 0, I1, I2, D1, D2, dims[2]);
+}
+
+// ---- D1's consumers in StereoThread::run ---------------------------------------
+static int32_t view_buffers(elas_b200_ctx* c, Slot& s)
+{
+    if (!s.d_view) CK(cudaMalloc(&s.d_view, 5 * (size_t)c->g.W * c->g.H * sizeof(float)));
+    return ELAS_B200_OK;
+}
+
+int32_t elas_b200_colormap(elas_b200_ctx* c, int32_t slot, const float* D1, float* color)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !color) return ELAS_B200_E_BAD_ARG;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    CK(cudaSetDevice(c->device));
+    Slot& s = *c->slots[slot];
+    if (int32_t rc = view_buffers(c, s)) return rc;
+    const size_t nd = (size_t)c->g.Dw * c->g.Dh;
+    const float* src = s.last_D1;
+    if (D1) {
+        // staged behind the colour planes; a device pointer is copied device->device
+        CK(cudaMemcpyAsync(s.d_view + 3 * nd, D1, nd * 4, cudaMemcpyDefault, s.stream));
+        src = s.d_view + 3 * nd;
+    }
+    if (!src) return ELAS_B200_E_BAD_ARG;                 // no frame has run through this slot yet
+    launch_colormap((int)nd, src, s.d_view, s.stream);
+    CK(cudaMemcpyAsync(color, s.d_view, 3 * nd * 4, cudaMemcpyDefault, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    return ELAS_B200_OK;
+}
+
+int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, int32_t bytes_per_line,
+                            const float* D1, const elas_b200_view* view,
+                            float* I, float* D, float* X, float* Y, float* Z)
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !view || !I || !D || !X || !Y || !Z) return ELAS_B200_E_BAD_ARG;
+    if (c->p.subsampling) return ELAS_B200_E_UNSUPPORTED;            // createCurrentMap reads D1 at full resolution
+    if (I1 && bytes_per_line < c->g.W) return ELAS_B200_E_BAD_ARG;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    CK(cudaSetDevice(c->device));
+    Slot& s = *c->slots[slot];
+    if (int32_t rc = view_buffers(c, s)) return rc;
+    const FrameGeom& g = c->g;
+    const size_t n = (size_t)g.W * g.H;
+    const float* src = s.last_D1;
+    if (D1) {
+        // the slot's scratch planes are free between frames
+        CK(cudaMemcpyAsync(s.d_tmp, D1, n * 4, cudaMemcpyDefault, s.stream));
+        src = s.d_tmp;
+    }
+    if (!src) return ELAS_B200_E_BAD_ARG;
+    if (I1) { if (int32_t rc = copy_image_in(g, s.d_img[0], I1, bytes_per_line, s.stream)) return rc; }
+    float* out[5] = {s.d_view, s.d_view + n, s.d_view + 2 * n, s.d_view + 3 * n, s.d_view + 4 * n};
+    launch_reproject(g.W, g.H, s.d_img[0], g.bpl, src, *view, out[0], out[1], out[2], out[3], out[4], s.stream);
+    float* user[5] = {I, D, X, Y, Z};
+    for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(user[k], out[k], n * 4, cudaMemcpyDefault, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    return ELAS_B200_OK;
 }
 
 int32_t elas_b200_stage_capture(elas_b200_ctx* c, int32_t slot, int32_t enable)

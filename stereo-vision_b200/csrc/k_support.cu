@@ -143,6 +143,7 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
 
+    __shared__ int16_t s_result[kPointsPerCta];
     for (int i = warp; i < npts; i += 8) {
         const int uc = uc0 + i;
         int result = 0;                                       // calloc'ed column 0
@@ -155,8 +156,12 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
                 if (d2 >= 0 && abs(d - d2) <= p.lr_threshold) result = d;           // :487-490
             }
         }
-        if (lane == 0) dcan[vc * g.Wc + uc] = (int16_t)result;
+        if (lane == 0) s_result[i] = (int16_t)result;
     }
+    // dcan is pinned HOST memory (the host stage consumes the lattice): one coalesced store per CTA
+    // crosses PCIe instead of a device->host copy queued behind other slots' disparity-map copies
+    __syncthreads();
+    if (threadIdx.x < npts) dcan[vc * g.Wc + uc0 + threadIdx.x] = s_result[threadIdx.x];
 }
 
 }  // namespace

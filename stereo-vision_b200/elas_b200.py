@@ -38,6 +38,13 @@ class Params(C.Structure):
         return q
 
 
+class View(C.Structure):
+    """elas_b200_view: intrinsics, range limit, gain and pose used by StereoThread::createCurrentMap
+    (reference stereothread.cpp:180-255, :441-447)."""
+    _fields_ = [("f", C.c_float), ("cu", C.c_float), ("cv", C.c_float), ("base", C.c_float),
+                ("max_dist", C.c_float), ("gain", C.c_float), ("H", C.c_double * 12)]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -50,7 +57,7 @@ EXPORTS = [
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
-    "elas_b200_version", "elas_b200_device_count",
+    "elas_b200_version", "elas_b200_device_count", "elas_b200_colormap", "elas_b200_reproject",
 ]
 
 
@@ -91,6 +98,8 @@ def load_library():
     lib.elas_b200_host_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     lib.elas_b200_time_matching.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.elas_b200_time_matching.restype = C.c_float
+    lib.elas_b200_colormap.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.elas_b200_reproject.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(View)] + [C.c_void_p] * 5
     lib.elas_b200_version.restype = C.c_char_p
     lib.elas_b200_device_count.restype = C.c_int32
     _lib = lib
@@ -203,6 +212,35 @@ class ElasB200:
         if rc < 0:
             raise RuntimeError(f"elas_b200_process_ctx failed with {rc}")
         return rc, D1, D2
+
+    def colormap(self, D1=None, slot=0):
+        """HSV colour map (stereothread.cpp:116-147) of D1, or of the map the slot's last frame left in HBM."""
+        if D1 is not None:
+            D1 = np.ascontiguousarray(D1, np.float32)
+            assert D1.shape == self.shape
+        out = np.empty(self.shape + (3,), np.float32)
+        rc = self.lib.elas_b200_colormap(self.ctx, slot, D1.ctypes.data if D1 is not None else None, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"elas_b200_colormap failed with {rc}")
+        return out
+
+    def reproject(self, view, H, I1=None, D1=None, slot=0):
+        """StereoThread::createCurrentMap (stereothread.cpp:180-255): returns I, D, X, Y, Z.
+        view = (f, cu, cv, base, max_dist, gain), H = 3x4 pose; I1/D1 None = the slot's last frame."""
+        v = View(*[float(x) for x in view], (C.c_double * 12)(*[float(x) for x in np.asarray(H, np.float64).reshape(12)]))
+        pitch = 0
+        if I1 is not None:
+            assert I1.dtype == np.uint8 and I1.shape == (self.H, self.W) and I1.strides[1] == 1
+            pitch = I1.strides[0]
+        if D1 is not None:
+            D1 = np.ascontiguousarray(D1, np.float32)
+        outs = [np.empty((self.H, self.W), np.float32) for _ in range(5)]
+        rc = self.lib.elas_b200_reproject(self.ctx, slot, I1.ctypes.data if I1 is not None else None, pitch,
+                                          D1.ctypes.data if D1 is not None else None, C.byref(v),
+                                          *[o.ctypes.data for o in outs])
+        if rc != 0:
+            raise RuntimeError(f"elas_b200_reproject failed with {rc}")
+        return outs
 
     def stage(self, name, slot=0):
         n = self.lib.elas_b200_stage_bytes(self.ctx, slot, name.encode())
