@@ -11,9 +11,13 @@ namespace elasb {
 
 constexpr int kInvalid = -10;        // elas.cpp:977-980: disparity maps are pre-filled with -10
 
-// candidate grid, list form: per cell kGridListStride uint16 = {count, d0, d1, ...} (128 bytes)
-constexpr int kGridListStride = 64;
-constexpr int kGridListCap = kGridListStride - 1;
+// candidate grid, list form: per cell kGridListStride uint16 = {count, d0, d1, ..., sentinel}.
+// The entry after the last one is disp_max+1, a disparity no pixel can take, so the matching kernel
+// walks the list two entries at a time without a remainder case.
+// The stride is 144 bytes, not 128: lanes of a warp that sit in neighbouring cells then read their
+// k-th entries from different shared-memory banks.
+constexpr int kGridListStride = 72;
+constexpr int kGridListCap = 62;
 
 constexpr int kRasterBandRows = 32;   // k_raster work unit: 32 columns x this many rows of a triangle's bounding box
 

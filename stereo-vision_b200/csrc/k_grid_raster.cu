@@ -73,6 +73,7 @@ __device__ __forceinline__ void grid_diffuse_body(int i, const FrameGeom& g, con
         }
     }
     list[0] = count <= kGridListCap ? (uint16_t)count : (uint16_t)0xFFFF;
+    if (count <= kGridListCap) list[1 + count] = (uint16_t)g.dn;      // sentinel: disp_max + 1
 }
 
 // Disparity planes (elas.cpp:605-680) and the per-triangle set-up of computeDisparity
