@@ -338,7 +338,10 @@ def main():
                        "parallelism": f"frame-sharded x{world}, one NCCL broadcast of the parameter block",
                        "host_cores": cores},
             "e2e": {"value": round(total_pairs / (ms_host_max * 1e-3), 2), "unit": "pairs/s",
-                    "h2d_bytes_per_step": B * 2 * W * H, "d2h_bytes_per_step": B * 2 * W * H * 4,
+                    "h2d_bytes_per_step": B * 2 * W * H,
+                    # D1 as float32; D2 (final after the L/R check: integers or -10) crosses as int16
+                    # and is widened into the caller's float map by the library (elas_b200.cu)
+                    "d2h_bytes_per_step": B * W * H * (4 + 2),
                     "ms_per_step": round(ms_host_max / args.steps, 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right in one launch)",

@@ -109,7 +109,7 @@ void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, in
 // K8 + K9's row step for D1 in one kernel (rows staged in shared memory)
 bool lr_rows_fusable(const FrameGeom& g);
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, float* O2, int32_t* parent, int32_t* size, cudaStream_t s);
+                    float* O1, float* O2, int32_t* parent, int32_t* size, int16_t* O2_i16, cudaStream_t s);
 // K9 apply + K10 + K11 in one tiled kernel (ipol_gap_width <= 3, no add_corners); out must not alias in
 bool post_fusable(const elas_b200_params& p);
 void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,

@@ -22,6 +22,8 @@
 #include <thread>
 #include <vector>
 
+#include <emmintrin.h>
+
 #include "common.cuh"
 #include "host_stage.h"
 
@@ -56,7 +58,14 @@ struct StageTimer {
 struct Slot {
     cudaStream_t stream = nullptr;
     // device
-    uint8_t* d_img[2] = {nullptr, nullptr};
+    uint8_t* d_img[2] = {nullptr, nullptr};    // the image pair of the frame in the pipeline (points into d_img_set)
+    uint8_t* d_img_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // two pairs: the next frame's images are prefetched
+    int img_next = 0;                          // set the next prefetch goes into
+    cudaStream_t h2d_stream = nullptr;         // image prefetch
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
+    int16_t* h_D2_i16 = nullptr;               // pinned landing buffer; expanded to float into the caller's D2 by the worker
+    float* expand_D2 = nullptr;                // caller's D2 awaiting expansion at frame_finish (null: nothing to expand)
     uint4* d_desc[2] = {nullptr, nullptr};
     int32_t* d_tables = nullptr;               // [support n x 3 | tri1 t1 x 3 | tri2 t2 x 3], packed, one copy per frame
     TriRaster* d_tri[2] = {nullptr, nullptr};  // raster records, written by k_planes
@@ -106,6 +115,7 @@ struct elas_b200_ctx {
     size_t flush_bytes = 0;
     bool timing = false;
     bool blocking_sync = false;              // wait on a blocking event instead of spinning in cudaStreamSynchronize
+    bool narrow_d2 = true;                   // host output: D2 crosses PCIe as int16 when that is exact (ELAS_B200_NARROW_D2=0 disables)
     long long launches_at_create = 0;
     // host-side wall time per frame phase, summed over all frames and slots (nanoseconds)
     std::atomic<long long> ns_submit_a{0}, ns_wait_a{0}, ns_host{0}, ns_submit_b{0}, ns_wait_b{0}, frames{0};
@@ -169,11 +179,13 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
 void free_slot(Slot& s)
 {
     for (int k = 0; k < 2; k++) {
-        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
+        cudaFree(s.d_img_set[0][k]); cudaFree(s.d_img_set[1][k]); cudaFree(s.d_desc[k]);
+        if (s.ev_h2d[k]) cudaEventDestroy(s.ev_h2d[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
         cudaFree(s.d_planes[k]);
     }
-    cudaFree(s.d_tables); cudaFree(s.d_view); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
+    cudaFree(s.d_tables); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16);
+    if (s.h2d_stream) cudaStreamDestroy(s.h2d_stream); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
     cudaFree(s.d_parent); cudaFree(s.d_size);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_sync) cudaEventDestroy(s.ev_sync);
@@ -192,12 +204,19 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     const size_t cells = (size_t)g.gw * g.gh * g.gwords;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.h2d_stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&s.d_D2_i16, ND * 2));
+    CK(cudaMallocHost(&s.h_D2_i16, ND * 2));
     const unsigned ev_flags = cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0);
     CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_out, ev_flags));
     for (int k = 0; k < 2; k++) {
-        CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
-        CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
+        for (int set = 0; set < 2; set++) {
+            CK(cudaMalloc(&s.d_img_set[set][k], (size_t)g.bpl * g.H));
+            CK(cudaMemset(s.d_img_set[set][k], 0, (size_t)g.bpl * g.H));   // padding columns stay 0 (elas.cpp:42-43)
+        }
+        s.d_img[k] = s.d_img_set[0][k];
+        CK(cudaEventCreateWithFlags(&s.ev_h2d[k], cudaEventDisableTiming));
         CK(cudaMalloc(&s.d_desc[k], N * 16));
         CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
@@ -298,6 +317,22 @@ int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool devic
     return ELAS_B200_OK;
 }
 
+// int16 -> float, exact (|x| < 2^15); streaming stores: the destination is not read again by this core
+void widen_i16_to_f32(const int16_t* src, float* dst, size_t n)
+{
+    size_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (; i + 8 <= n; i += 8) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+            const __m128i lo = _mm_srai_epi32(_mm_unpacklo_epi16(v, v), 16), hi = _mm_srai_epi32(_mm_unpackhi_epi16(v, v), 16);
+            _mm_stream_ps(dst + i, _mm_cvtepi32_ps(lo));
+            _mm_stream_ps(dst + i + 4, _mm_cvtepi32_ps(hi));
+        }
+        _mm_sfence();
+    }
+    for (; i < n; i++) dst[i] = (float)src[i];
+}
+
 // One frame = phase A (GPU) -> host stage -> phase B (GPU) -> maps out.  The four steps are separate
 // so that a slot's worker can start frame i+1 while the maps of frame i are still on their way out.
 struct FrameIO {
@@ -307,7 +342,20 @@ struct FrameIO {
 };
 
 // ---- phase A: images in, descriptors, support search (lattice lands in pinned host memory) ------
-int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
+// images of a frame into the slot's free image pair, on the prefetch stream; returns the set used
+int32_t images_in(elas_b200_ctx* c, Slot& s, const FrameIO& io, int* set_out)
+{
+    const FrameGeom& g = c->g;
+    const int set = s.img_next;
+    s.img_next ^= 1;
+    if (int32_t rc = copy_image_in(g, s.d_img_set[set][0], io.I1, io.bytes_per_line, s.h2d_stream)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img_set[set][1], io.I2, io.bytes_per_line, s.h2d_stream)) return rc;
+    CK(cudaEventRecord(s.ev_h2d[set], s.h2d_stream));
+    *set_out = set;
+    return ELAS_B200_OK;
+}
+
+int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io, int prefetched_set = -1)
 {
     const FrameGeom& g = c->g;
     const elas_b200_params& p = c->p;
@@ -319,8 +367,14 @@ int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         cudaEventRecord(s.timer.begin, st);
     }
     const long long t0 = now_ns();
-    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
-    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
+    if (prefetched_set >= 0) {
+        // the images were sent ahead on the prefetch stream while the previous frame was in flight
+        CK(cudaStreamWaitEvent(st, s.ev_h2d[prefetched_set], 0));
+        s.d_img[0] = s.d_img_set[prefetched_set][0]; s.d_img[1] = s.d_img_set[prefetched_set][1];
+    } else {
+        if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
+        if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
+    }
     mark(c, s, "copy_in");
     launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
     mark(c, s, "descriptor");
@@ -431,7 +485,18 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
     float* lr_out[2] = {s.d_D[0], s.d_D[1]};
     if (io.device_io && n_post == 1) lr_out[1] = io.D2;
     const bool rows_fused = lr_rows_fusable(g);
-    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], s.d_parent, s.d_size, st);
+    // Host output, D2 final after the L/R check: its values are raw integer disparities or -10, so it
+    // crosses PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
+    bool d2_i16 = !io.device_io && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
+    if (d2_i16) {
+        // the widening runs on the CPU: the caller's D2 must be host memory (a device pointer may be
+        // passed to the host-buffer entry points too; it then takes the plain copy)
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, io.D2) != cudaSuccess) { cudaGetLastError(); d2_i16 = false; }
+        else if (attr.type == cudaMemoryTypeDevice) d2_i16 = false;
+    }
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], s.d_parent, s.d_size,
+                                   d2_i16 ? s.d_D2_i16 : nullptr, st);
     else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], st);          // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
@@ -500,8 +565,16 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         CK(cudaStreamWaitEvent(s.copy_stream, s.ev_done, 0));
         out_stream = s.copy_stream;
     }
-    for (int k = 0; k < 2; k++)
-        if (final_map[k] != user[k]) CK(cudaMemcpyAsync(user[k], final_map[k], ND * 4, cudaMemcpyDefault, out_stream));
+    s.expand_D2 = nullptr;
+    for (int k = 0; k < 2; k++) {
+        if (final_map[k] == user[k]) continue;
+        if (k == 1 && d2_i16) {
+            CK(cudaMemcpyAsync(s.h_D2_i16, s.d_D2_i16, ND * 2, cudaMemcpyDeviceToHost, out_stream));
+            s.expand_D2 = user[1];
+        } else {
+            CK(cudaMemcpyAsync(user[k], final_map[k], ND * 4, cudaMemcpyDefault, out_stream));
+        }
+    }
     mark(c, s, "copy_out");
     CK(cudaEventRecord(s.ev_out, out_stream));
     c->ns_submit_b += now_ns() - t3;
@@ -515,6 +588,10 @@ int32_t frame_finish(elas_b200_ctx* c, Slot& s)
     CK(cudaEventSynchronize(s.ev_out));
     CK(cudaGetLastError());
     c->ns_wait_b += now_ns() - t4; c->frames += 1;
+    if (s.expand_D2) {
+        widen_i16_to_f32(s.h_D2_i16, s.expand_D2, (size_t)c->g.Dw * c->g.Dh);
+        s.expand_D2 = nullptr;
+    }
     if (c->timing) {
         CK(cudaStreamSynchronize(s.stream));
         s.timer.last.clear();
@@ -565,25 +642,39 @@ void worker_main(elas_b200_ctx* c, int slot)
             if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
             job->done.fetch_add(1);
         };
-        // software pipeline over this slot's frames: frame i's maps travel out (copy stream) while frame
-        // i+1 runs phase A and its host stage; frame i is reported once its maps have landed
-        int in_flight = -1;
-        for (;;) {
+        // software pipeline over this slot's frames: frame i's maps travel out (copy stream) and frame
+        // i+1's images travel in (prefetch stream) while the compute stream and the host stage work on
+        // what lies between; frame i is reported once its maps have landed
+        auto claim = [&](FrameIO* io) {
             const int i = job->next.fetch_add(1);
-            if (i >= job->n) break;
-            const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
+            if (i >= job->n) return -1;
+            *io = FrameIO{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
+            return i;
+        };
+        int in_flight = -1;
+        FrameIO io{}, io_next{};
+        int set = -1, set_next = -1;
+        int32_t rc_next = ELAS_B200_OK;
+        int i = claim(&io);
+        if (i >= 0) rc_next = images_in(c, s, io, &set);
+        while (i >= 0) {
             int n = 0;
-            int32_t rc = phase_a_submit(c, s, io);
+            int32_t rc = rc_next;
+            if (!rc) rc = phase_a_submit(c, s, io, set);
+            const int i_next = claim(&io_next);                       // prefetch the next frame's images
+            rc_next = i_next >= 0 ? images_in(c, s, io_next, &set_next) : ELAS_B200_OK;
             if (!rc) rc = phase_a_finish_and_host(c, s, &n);
             if (in_flight >= 0) { report(in_flight, frame_finish(c, s)); in_flight = -1; }
             if (!rc && n < 3) {
                 rc = fill_invalid(c, s, io.D1, io.D2, io.device_io);
                 if (!rc) rc = ELAS_B200_E_FEW_SUPPORT;
-            } else if (!rc) {
-                rc = phase_b_submit(c, s, io);
-                if (!rc) { in_flight = i; continue; }
+                report(i, rc);
+            } else if (!rc && !(rc = phase_b_submit(c, s, io))) {
+                in_flight = i;
+            } else {
+                report(i, rc);
             }
-            report(i, rc);
+            i = i_next; io = io_next; set = set_next;
         }
         if (in_flight >= 0) report(in_flight, frame_finish(c, s));
         {
@@ -702,6 +793,7 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
         const unsigned cores = std::thread::hardware_concurrency();
         c->blocking_sync = cores > 0 && (unsigned)n_slots > cores;
         if (const char* e = std::getenv("ELAS_B200_BLOCKING_SYNC")) c->blocking_sync = std::atoi(e) != 0;
+        if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
     }
     for (int i = 0; i < n_slots; i++) {
         c->slots.emplace_back(new Slot);

@@ -130,7 +130,8 @@ k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__
 __global__ void __launch_bounds__(256)
 k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
           const float* __restrict__ D1, const float* __restrict__ D2,
-          float* __restrict__ O1, float* __restrict__ O2, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+          float* __restrict__ O1, float* __restrict__ O2, int32_t* __restrict__ parent, int32_t* __restrict__ size,
+          int16_t* __restrict__ O2_i16)      // optional: O2 narrowed (exact: raw integer disparities or -10)
 {
     extern __shared__ float s_rows[];          // [3][Dw]: raw D1 row, raw D2 row, checked D1 row
     __shared__ int warp_last[8];
@@ -149,7 +150,8 @@ k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
             if (!(fabsf(__fsub_rn(r2[(int)w1], d1)) > lr_threshold)) o1 = d1;
         if (d2 >= 0.f && w2 >= 0.f && w2 < (float)Dw)                                                       // :1182-1197
             if (!(fabsf(__fsub_rn(r1[(int)w2], d2)) > lr_threshold)) o2 = d2;
-        O1[row + u] = o1; O2[row + u] = o2;
+        O1[row + u] = o1;
+        if (O2_i16) O2_i16[row + u] = (int16_t)o2; else O2[row + u] = o2;
         c1[u] = o1;
     }
     __syncthreads();
@@ -524,7 +526,7 @@ bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 12 <= 160 * 102
 
 // K8 for both maps + the run labelling of D1 (launch_segments(..., rows_done = true) continues from there)
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, float* O2, int32_t* parent, int32_t* size, cudaStream_t s)
+                    float* O1, float* O2, int32_t* parent, int32_t* size, int16_t* O2_i16, cudaStream_t s)
 {
     const size_t smem = (size_t)g.Dw * 12;
     static bool attr_set = false;
@@ -533,7 +535,7 @@ void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* 
         attr_set = true;
     }
     k_lr_rows<<<g.Dh, 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
-                                      D1, D2, O1, O2, parent, size);
+                                      D1, D2, O1, O2, parent, size, O2_i16);
     count_launch();
 }
 
