@@ -470,31 +470,31 @@ constexpr int kPadC = 8, kPadR = 8;
 // point when the count is below incon_min_support; only that comparison is observable, so the
 // count stops as soon as it reaches incon_min_support (rows nearest the centre are visited first).
 // A window row (<= 16 lattice points) is compared with SSE2: lanes d2 in [max(d-thr,0), d+thr].
-void remove_inconsistent_padded(const elas_b200_params& p, int16_t* P, int pitch, int Wc, int Hc)
+// `cells` lists the offsets (into the padded array) of the cells that are valid on entry, in the
+// reference's scan order (u outer, v inner); a filter only ever invalidates the cell it is visiting, so
+// the cells to visit are exactly those and the 65 % invalid cells cost nothing.
+void remove_inconsistent_padded(const elas_b200_params& p, int16_t* P, int pitch, const std::vector<int32_t>& cells)
 {
     const int win = p.incon_window_size, need = p.incon_min_support, thr = p.incon_threshold;
     const int span = 2 * win + 1;                           // lanes of a window row, <= 16 on this path
     const uint32_t lane_mask = span >= 16 ? 0xFFFFFFFFu : ((1u << (2 * span)) - 1u);
-    for (int u = 0; u < Wc; u++) {
-        for (int v = 0; v < Hc; v++) {
-            int16_t* centre = P + (size_t)(v + kPadR) * pitch + kPadC + u;
-            const int d = *centre;
-            if (d < 0) continue;
-            const __m128i lo1 = _mm_set1_epi16((short)(std::max(d - thr, 0) - 1));      // x > lo-1
-            const __m128i hi1 = _mm_set1_epi16((short)std::min(d + thr + 1, 32767));    // x < hi+1
-            int support = 0;
-            for (int k = 0; k <= 2 * win && support < need; k++) {
-                const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);          // v, v+1, v-1, v+2, v-2, ...
-                const int16_t* row = centre + (ptrdiff_t)dv * pitch - win;
-                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row));
-                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row + 8));
-                const __m128i ma = _mm_and_si128(_mm_cmpgt_epi16(a, lo1), _mm_cmpgt_epi16(hi1, a));
-                const __m128i mb = _mm_and_si128(_mm_cmpgt_epi16(b, lo1), _mm_cmpgt_epi16(hi1, b));
-                const uint32_t m = ((uint32_t)_mm_movemask_epi8(ma) | ((uint32_t)_mm_movemask_epi8(mb) << 16)) & lane_mask;
-                support += __builtin_popcount(m) >> 1;
-            }
-            if (support < need) *centre = -1;
+    for (const int32_t off : cells) {
+        int16_t* centre = P + off;
+        const int d = *centre;
+        const __m128i lo1 = _mm_set1_epi16((short)(std::max(d - thr, 0) - 1));      // x > lo-1
+        const __m128i hi1 = _mm_set1_epi16((short)std::min(d + thr + 1, 32767));    // x < hi+1
+        int support = 0;
+        for (int k = 0; k <= 2 * win && support < need; k++) {
+            const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);              // v, v+1, v-1, v+2, v-2, ...
+            const int16_t* row = centre + (ptrdiff_t)dv * pitch - win;
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(row + 8));
+            const __m128i ma = _mm_and_si128(_mm_cmpgt_epi16(a, lo1), _mm_cmpgt_epi16(hi1, a));
+            const __m128i mb = _mm_and_si128(_mm_cmpgt_epi16(b, lo1), _mm_cmpgt_epi16(hi1, b));
+            const uint32_t m = ((uint32_t)_mm_movemask_epi8(ma) | ((uint32_t)_mm_movemask_epi8(mb) << 16)) & lane_mask;
+            support += __builtin_popcount(m) >> 1;
         }
+        if (support < need) *centre = -1;
     }
 }
 
@@ -523,20 +523,19 @@ void remove_inconsistent_scalar(const elas_b200_params& p, int16_t* D, int Wc, i
 // removeRedundantSupportPoints, elas.cpp:213-279 (in place): a point goes when, in BOTH directions along
 // the axis, a valid point with |d - d2| <= thresh lies within max_dist lattice steps.  `step` is the
 // element stride of the axis in the padded array (pitch for the vertical pass, 1 for the horizontal).
-void remove_redundant_padded(int16_t* P, int pitch, int Wc, int Hc, int max_dist, int thresh, ptrdiff_t step)
+void remove_redundant_padded(int16_t* P, const std::vector<int32_t>& cells, int max_dist, int thresh, ptrdiff_t step)
 {
-    for (int u = 0; u < Wc; u++)
-        for (int v = 0; v < Hc; v++) {
-            int16_t* centre = P + (size_t)(v + kPadR) * pitch + kPadC + u;
-            const int d = *centre;
-            if (d < 0) continue;
-            const int lo = std::max(d - thresh, 0), hi = d + thresh;
-            bool back = false, fwd = false;
-            for (int j = 1; j <= max_dist; j++) { const int x = centre[-j * step]; back |= x >= lo && x <= hi; }
-            if (!back) continue;
-            for (int j = 1; j <= max_dist; j++) { const int x = centre[j * step]; fwd |= x >= lo && x <= hi; }
-            if (fwd) *centre = -1;
-        }
+    for (const int32_t off : cells) {
+        int16_t* centre = P + off;
+        const int d = *centre;
+        if (d < 0) continue;                                  // invalidated by an earlier filter
+        const int lo = std::max(d - thresh, 0), hi = d + thresh;
+        bool back = false, fwd = false;
+        for (int j = 1; j <= max_dist; j++) { const int x = centre[-j * step]; back |= x >= lo && x <= hi; }
+        if (!back) continue;
+        for (int j = 1; j <= max_dist; j++) { const int x = centre[j * step]; fwd |= x >= lo && x <= hi; }
+        if (fwd) *centre = -1;
+    }
 }
 
 // removeRedundantSupportPoints without padding (max_dist beyond the padding)
@@ -686,35 +685,44 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
         auto unpad = [&](int16_t* dst) {
             for (int v = 0; v < Hc; v++) std::memcpy(dst + (size_t)v * Wc, P + (size_t)(v + kPadR) * pitch + kPadC, (size_t)Wc * 2);
         };
-        remove_inconsistent_padded(p, P, pitch, Wc, Hc);              // elas.cpp:496
+        // valid cells in scan order (u outer, v inner): rows are read contiguously, counted per column,
+        // and scattered into the prefix-summed column-major layout
+        col_fill_.assign((size_t)Wc + 1, 0);
+        for (int v = 0; v < Hc; v++) {
+            const int16_t* row = dcan + (size_t)v * Wc;
+            for (int u = 0; u < Wc; u++) col_fill_[u + 1] += row[u] >= 0;
+        }
+        for (int u = 1; u <= Wc; u++) col_fill_[u] += col_fill_[u - 1];
+        cells_.resize((size_t)col_fill_[Wc]);
+        for (int v = 0; v < Hc; v++) {
+            const int16_t* row = dcan + (size_t)v * Wc;
+            const int32_t base = (v + kPadR) * pitch + kPadC;
+            for (int u = 0; u < Wc; u++)
+                if (row[u] >= 0) cells_[col_fill_[u]++] = base + u;
+        }
+        remove_inconsistent_padded(p, P, pitch, cells_);              // elas.cpp:496
         if (keep_stages) { dcan_incon.resize((size_t)Wc * Hc); unpad(dcan_incon.data()); }
-        remove_redundant_padded(P, pitch, Wc, Hc, 5, 1, pitch);       // :501 (vertical)
-        remove_redundant_padded(P, pitch, Wc, Hc, 5, 1, 1);           // :502 (horizontal)
+        remove_redundant_padded(P, cells_, 5, 1, pitch);              // :501 (vertical)
+        remove_redundant_padded(P, cells_, 5, 1, 1);                  // :502 (horizontal)
         unpad(dcan);
+        // :505-517: the survivors outside lattice row 0 / column 0, already in u-outer / v-inner order
+        for (const int32_t off : cells_) {
+            const int d = P[off];
+            if (d < 0) continue;
+            const int vc = off / pitch - kPadR, uc = off - (vc + kPadR) * pitch - kPadC;
+            if (uc < 1 || vc < 1) continue;
+            support.push_back(uc * g.step); support.push_back(vc * g.step); support.push_back(d);
+        }
     } else {
         remove_inconsistent_scalar(p, dcan, Wc, Hc);
         if (keep_stages) dcan_incon.assign(dcan, dcan + (size_t)Wc * Hc);
         remove_redundant_scalar(dcan, Wc, Hc, 5, 1, true);
         remove_redundant_scalar(dcan, Wc, Hc, 5, 1, false);
-    }
-
-    // :505-517, u outer / v inner.  Rows are scanned contiguously into per-column counts first, so
-    // the column-major emission is a scatter into a prefix-summed layout.
-    col_fill_.assign((size_t)Wc + 1, 0);
-    for (int vc = 1; vc < Hc; vc++) {
-        const int16_t* row = dcan + (size_t)vc * Wc;
-        for (int uc = 1; uc < Wc; uc++) col_fill_[uc + 1] += row[uc] >= 0;
-    }
-    for (int uc = 1; uc <= Wc; uc++) col_fill_[uc] += col_fill_[uc - 1];
-    support.resize(3 * (size_t)col_fill_[Wc]);
-    for (int vc = 1; vc < Hc; vc++) {
-        const int16_t* row = dcan + (size_t)vc * Wc;
-        for (int uc = 1; uc < Wc; uc++) {
-            const int d = row[uc];
-            if (d < 0) continue;
-            int32_t* o = support.data() + 3 * (size_t)col_fill_[uc]++;
-            o[0] = uc * g.step; o[1] = vc * g.step; o[2] = d;
-        }
+        for (int uc = 1; uc < Wc; uc++)                               // :505-517, u outer / v inner
+            for (int vc = 1; vc < Hc; vc++) {
+                const int d = dcan[vc * Wc + uc];
+                if (d >= 0) { support.push_back(uc * g.step); support.push_back(vc * g.step); support.push_back(d); }
+            }
     }
     if (p.add_corners) add_corners(g.W, g.H, support);            // :520-523
     n_support = (int)support.size() / 3;
@@ -731,18 +739,23 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
         delaunay_.run(px_.data(), py_.data(), n_support, tri[k]);
         // work units: 32-column chunks x kRasterBandRows-row bands of each triangle's bounding box
         const size_t nt = tri[k].size() / 3;
+        const int32_t* tk = tri[k].data();
         for (size_t t = 0; t < nt; t++) {
-            const int a = tri[k][3 * t], b = tri[k][3 * t + 1], c = tri[k][3 * t + 2];
+            const int a = tk[3 * t], b = tk[3 * t + 1], c = tk[3 * t + 2];
             const int u_lo = std::max(std::min(px_[a], std::min(px_[b], px_[c])), 0);
             const int u_hi = std::min(std::max(px_[a], std::max(px_[b], px_[c])), g.W);      // columns [u_lo, u_hi)
             // one row of slack below the smallest corner row: an edge line evaluated in float may truncate to it
             const int v_lo = std::max(std::min(py_[a], std::min(py_[b], py_[c])) - 1, 0);
             const int v_hi = std::min(std::max(py_[a], std::max(py_[b], py_[c])) + 1, g.H);  // rows [v_lo, v_hi)
             const int chunks = (u_hi - u_lo + 31) / 32, bands = (v_hi - v_lo + kRasterBandRows - 1) / kRasterBandRows;
+            if (chunks <= 0 || bands <= 0) continue;
+            const size_t at = units.size();
+            units.resize(at + 2 * (size_t)chunks * bands);
+            int32_t* o = units.data() + at;
             for (int ch = 0; ch < chunks; ch++)
                 for (int bd = 0; bd < bands; bd++) {
-                    units.push_back((int32_t)t | (k << 30));
-                    units.push_back(ch | (bd << 16));
+                    *o++ = (int32_t)t | (k << 30);
+                    *o++ = ch | (bd << 16);
                 }
         }
         if (with_planes) {

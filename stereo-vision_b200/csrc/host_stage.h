@@ -29,13 +29,16 @@ public:
 private:
     struct OTri { int t, o; };
     OTri sym(OTri a) const { int e = nbr_[3 * a.t + a.o]; return {e >> 2, e & 3}; }
-    static OTri lnext(OTri a) { return {a.t, a.o == 2 ? 0 : a.o + 1}; }
-    static OTri lprev(OTri a) { return {a.t, a.o == 0 ? 2 : a.o - 1}; }
-    int org(OTri a) const { return vtx_[3 * a.t + (a.o == 2 ? 0 : a.o + 1)]; }
-    int dest(OTri a) const { return vtx_[3 * a.t + (a.o == 0 ? 2 : a.o - 1)]; }
+    // (o + 1) % 3 and (o + 2) % 3 without a branch or a division: 2-bit fields of a constant
+    static int plus1(int o) { return (0x09 >> (2 * o)) & 3; }     // 0 -> 1, 1 -> 2, 2 -> 0
+    static int minus1(int o) { return (0x12 >> (2 * o)) & 3; }    // 0 -> 2, 1 -> 0, 2 -> 1
+    static OTri lnext(OTri a) { return {a.t, plus1(a.o)}; }
+    static OTri lprev(OTri a) { return {a.t, minus1(a.o)}; }
+    int org(OTri a) const { return vtx_[3 * a.t + plus1(a.o)]; }
+    int dest(OTri a) const { return vtx_[3 * a.t + minus1(a.o)]; }
     int apex(OTri a) const { return vtx_[3 * a.t + a.o]; }
-    void set_org(OTri a, int v) { vtx_[3 * a.t + (a.o == 2 ? 0 : a.o + 1)] = v; }
-    void set_dest(OTri a, int v) { vtx_[3 * a.t + (a.o == 0 ? 2 : a.o - 1)] = v; }
+    void set_org(OTri a, int v) { vtx_[3 * a.t + plus1(a.o)] = v; }
+    void set_dest(OTri a, int v) { vtx_[3 * a.t + minus1(a.o)] = v; }
     void set_apex(OTri a, int v) { vtx_[3 * a.t + a.o] = v; }
     void bond(OTri a, OTri b) { nbr_[3 * a.t + a.o] = (b.t << 2) | b.o; nbr_[3 * b.t + b.o] = (a.t << 2) | a.o; }
     OTri make();
@@ -80,7 +83,7 @@ struct HostStage {
 
 private:
     Triangulator delaunay_;
-    std::vector<int32_t> px_, py_, col_fill_;
+    std::vector<int32_t> px_, py_, col_fill_, cells_;
     std::vector<int16_t> pad_;
 };
 
