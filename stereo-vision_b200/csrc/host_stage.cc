@@ -727,8 +727,9 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
     if (p.add_corners) add_corners(g.W, g.H, support);            // :520-523
     n_support = (int)support.size() / 3;
     for (int k = 0; k < 2; k++) { tri[k].clear(); planes[k].clear(); raster[k].clear(); }
-    units.clear();
-    if (n_support < 3) return n_support;                          // :69-75
+    // units is grown geometrically and trimmed to its final size once (no per-triangle zero fill)
+    size_t n_units_ints = 0;
+    if (n_support < 3) { units.clear(); return n_support; }       // :69-75
 
     px_.resize(n_support); py_.resize(n_support);
     for (int k = 0; k < 2; k++) {                                 // :80-81, :534-559
@@ -749,20 +750,22 @@ int HostStage::run(const FrameGeom& g, const elas_b200_params& p, int16_t* dcan,
             const int v_hi = std::min(std::max(py_[a], std::max(py_[b], py_[c])) + 1, g.H);  // rows [v_lo, v_hi)
             const int chunks = (u_hi - u_lo + 31) / 32, bands = (v_hi - v_lo + kRasterBandRows - 1) / kRasterBandRows;
             if (chunks <= 0 || bands <= 0) continue;
-            const size_t at = units.size();
-            units.resize(at + 2 * (size_t)chunks * bands);
-            int32_t* o = units.data() + at;
+            const size_t need = 2 * (size_t)chunks * bands;
+            if (n_units_ints + need > units.size()) units.resize(std::max(2 * units.size(), n_units_ints + need + 4096));
+            int32_t* o = units.data() + n_units_ints;
             for (int ch = 0; ch < chunks; ch++)
                 for (int bd = 0; bd < bands; bd++) {
                     *o++ = (int32_t)t | (k << 30);
                     *o++ = ch | (bd << 16);
                 }
+            n_units_ints += need;
         }
         if (with_planes) {
             disparity_planes(support, tri[k], planes[k]);         // :87-88
             raster_records(support, tri[k], planes[k], k, raster[k]);
         }
     }
+    units.resize(n_units_ints);
     return n_support;
 }
 
