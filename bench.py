@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=512, help="stereo pairs per GPU per step")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled through the batch")
     ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = from host core count)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
