@@ -191,7 +191,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="stereo pairs per GPU per step")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled through the batch")
-    ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = from host core count)")
+    ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = twice the workers)")
+    ap.add_argument("--workers", type=int, default=0, help="host worker threads per GPU (0 = cores / ranks)")
     ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-4k", action="store_true", help="skip the 4096x2160 roofline point of the matching kernel")
@@ -222,7 +223,10 @@ def main():
     params = sharding.broadcast_params(elas_b200.stereomapper(DMAX), dev, src=0)
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    slots = args.slots or max(2, min(16, cores // max(world, 1)))
+    # host workers: this rank's share of the cores; slots: twice that, so the GPU has phases queued while
+    # every worker runs a host stage (workers are not tied to slots, elas_b200.cu)
+    workers = args.workers or max(1, min(32, cores // max(world, 1) - 2))      # two cores left to the main thread and the driver
+    slots = args.slots or max(2, min(48, 2 * workers))
     B = args.batch
     bpl = W + 15 - (W - 1) % 16
 
@@ -241,7 +245,7 @@ def main():
     def ptrs(t, k):
         return [t[i, k].data_ptr() for i in range(B)]
 
-    engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank)
+    engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank, n_workers=workers)
 
     # pointer tables of the batch, built once: the timed call is the C ABI call and nothing else
     dev_ptrs = (ptrs(d_I, 0), ptrs(d_I, 1), ptrs(d_D, 0), ptrs(d_D, 1))
@@ -337,7 +341,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_dev_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "slots_per_gpu": slots,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "slots_per_gpu": slots, "host_workers_per_gpu": workers,
                        "distinct_pairs": args.distinct, "l2": "512 MiB buffer rewritten between timed steps",
                        "parallelism": f"frame-sharded x{world}, one NCCL broadcast of the parameter block",
                        "host_cores": cores},

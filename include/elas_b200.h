@@ -93,6 +93,11 @@ typedef struct elas_b200_ctx elas_b200_ctx;
 
 int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
                          int32_t width, int32_t height, int32_t n_slots);
+/* Same with an explicit number of host worker threads for the batch calls (0 = one per available
+ * core, never more than slots).  Workers are not tied to slots: give a context more slots than workers
+ * (e.g. 2x) and the GPU stays fed while every worker runs host stages. */
+int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                            int32_t width, int32_t height, int32_t n_slots, int32_t n_workers);
 void    elas_b200_destroy(elas_b200_ctx* ctx);
 
 /* One frame through one slot, synchronous, host buffers (same contract as elas_b200_process). */

@@ -1,14 +1,16 @@
 // C ABI (include/elas_b200.h) + per-device context of the B200 dense-stereo path.
 //
-// A context owns `n_slots` frame slots.  A slot is everything one frame needs -- a CUDA stream, all
-// device buffers (images, descriptors, lattice, tables, triangle-id maps, disparity maps, scratch),
-// pinned host mirrors of the small tables and a HostStage -- allocated once: nothing is allocated
-// per frame (the reference mallocs ~20 buffers per Elas::process call).  Frames are independent
-// (stereothread.cpp:113 builds a fresh Elas per frame), so slots run concurrently: one host worker
-// per slot drives   GPU phase A (copy-in, K1 descriptors, K2 support search, lattice copy-out)
-//                -> host stage (lattice filters, Delaunay, planes; host_stage.cc)
-//                -> GPU phase B (tables in, grid, triangle-id maps, K7 matching, K8-K12, copy-out)
-// and the GPU overlaps the phases of different slots.
+// A context owns `n_slots` frame slots.  A slot is everything one frame needs -- CUDA streams, all
+// device buffers (images, descriptors, tables, triangle-id maps, disparity maps, scratch), pinned host
+// memory for the candidate lattice and the small tables, and a HostStage -- allocated once: nothing is
+// allocated per frame (the reference mallocs ~20 buffers per Elas::process call).  A frame is
+//        GPU phase A (images in, K1 descriptors, K2 support search -> lattice in pinned host memory)
+//     -> host stage  (lattice filters, Delaunay, raster units; host_stage.cc)
+//     -> GPU phase B (tables in, planes, grid, triangle-id maps, K7 matching, K8-K12, maps out)
+// Frames are independent (stereothread.cpp:113 builds a fresh Elas per frame), so the batch calls keep
+// many slots in flight: a pool of host workers (not tied to slots) advances whichever slot can move,
+// see worker_main().
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -23,6 +25,7 @@
 #include <vector>
 
 #include <emmintrin.h>
+#include <sched.h>
 
 #include "common.cuh"
 #include "host_stage.h"
@@ -58,14 +61,15 @@ struct StageTimer {
 struct Slot {
     cudaStream_t stream = nullptr;
     // device
-    uint8_t* d_img[2] = {nullptr, nullptr};    // the image pair of the frame in the pipeline (points into d_img_set)
-    uint8_t* d_img_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // two pairs: the next frame's images are prefetched
-    int img_next = 0;                          // set the next prefetch goes into
-    cudaStream_t h2d_stream = nullptr;         // image prefetch
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    uint8_t* d_img[2] = {nullptr, nullptr};
     int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
     int16_t* h_D2_i16 = nullptr;               // pinned landing buffer; expanded to float into the caller's D2 by the worker
     float* expand_D2 = nullptr;                // caller's D2 awaiting expansion at frame_finish (null: nothing to expand)
+    // batch scheduler state (see worker_main)
+    std::atomic<int> busy{0};                  // a worker is looking at / working on this slot
+    int state = 0;                             // 0 idle, 1 phase A in flight, 2 phase B + copy-out in flight
+    int frame = -1;                            // index of the slot's frame in the current batch
+    cudaEvent_t ev_a = nullptr;                // phase A finished
     uint4* d_desc[2] = {nullptr, nullptr};
     int32_t* d_tables = nullptr;               // [support n x 3 | tri1 t1 x 3 | tri2 t2 x 3], packed, one copy per frame
     TriRaster* d_tri[2] = {nullptr, nullptr};  // raster records, written by k_planes
@@ -115,6 +119,8 @@ struct elas_b200_ctx {
     size_t flush_bytes = 0;
     bool timing = false;
     bool blocking_sync = false;              // wait on a blocking event instead of spinning in cudaStreamSynchronize
+    bool direct_out = false;                 // ELAS_B200_DIRECT_OUT=1: kernels store finished maps straight into pinned host buffers
+                                             // (measured slower end to end than the copy engine: 7.9 k vs 11.4 k pairs/s)
     bool narrow_d2 = true;                   // host output: D2 crosses PCIe as int16 when that is exact (ELAS_B200_NARROW_D2=0 disables)
     long long launches_at_create = 0;
     // host-side wall time per frame phase, summed over all frames and slots (nanoseconds)
@@ -179,17 +185,17 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
 void free_slot(Slot& s)
 {
     for (int k = 0; k < 2; k++) {
-        cudaFree(s.d_img_set[0][k]); cudaFree(s.d_img_set[1][k]); cudaFree(s.d_desc[k]);
-        if (s.ev_h2d[k]) cudaEventDestroy(s.ev_h2d[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
+        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
         cudaFree(s.d_planes[k]);
     }
     cudaFree(s.d_tables); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16);
-    if (s.h2d_stream) cudaStreamDestroy(s.h2d_stream); cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
+ cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
     cudaFree(s.d_parent); cudaFree(s.d_size);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_sync) cudaEventDestroy(s.ev_sync);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.ev_a) cudaEventDestroy(s.ev_a);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
     if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     for (auto& m : s.timer.marks) cudaEventDestroy(m.second);
@@ -204,19 +210,15 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     const size_t cells = (size_t)g.gw * g.gh * g.gwords;
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s.h2d_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&s.d_D2_i16, ND * 2));
     CK(cudaMallocHost(&s.h_D2_i16, ND * 2));
     const unsigned ev_flags = cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0);
     CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.ev_a, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.ev_out, ev_flags));
     for (int k = 0; k < 2; k++) {
-        for (int set = 0; set < 2; set++) {
-            CK(cudaMalloc(&s.d_img_set[set][k], (size_t)g.bpl * g.H));
-            CK(cudaMemset(s.d_img_set[set][k], 0, (size_t)g.bpl * g.H));   // padding columns stay 0 (elas.cpp:42-43)
-        }
-        s.d_img[k] = s.d_img_set[0][k];
-        CK(cudaEventCreateWithFlags(&s.ev_h2d[k], cudaEventDisableTiming));
+        CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
+        CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
         CK(cudaMalloc(&s.d_desc[k], N * 16));
         CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
@@ -342,20 +344,7 @@ struct FrameIO {
 };
 
 // ---- phase A: images in, descriptors, support search (lattice lands in pinned host memory) ------
-// images of a frame into the slot's free image pair, on the prefetch stream; returns the set used
-int32_t images_in(elas_b200_ctx* c, Slot& s, const FrameIO& io, int* set_out)
-{
-    const FrameGeom& g = c->g;
-    const int set = s.img_next;
-    s.img_next ^= 1;
-    if (int32_t rc = copy_image_in(g, s.d_img_set[set][0], io.I1, io.bytes_per_line, s.h2d_stream)) return rc;
-    if (int32_t rc = copy_image_in(g, s.d_img_set[set][1], io.I2, io.bytes_per_line, s.h2d_stream)) return rc;
-    CK(cudaEventRecord(s.ev_h2d[set], s.h2d_stream));
-    *set_out = set;
-    return ELAS_B200_OK;
-}
-
-int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io, int prefetched_set = -1)
+int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
 {
     const FrameGeom& g = c->g;
     const elas_b200_params& p = c->p;
@@ -367,14 +356,8 @@ int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io, int prefetc
         cudaEventRecord(s.timer.begin, st);
     }
     const long long t0 = now_ns();
-    if (prefetched_set >= 0) {
-        // the images were sent ahead on the prefetch stream while the previous frame was in flight
-        CK(cudaStreamWaitEvent(st, s.ev_h2d[prefetched_set], 0));
-        s.d_img[0] = s.d_img_set[prefetched_set][0]; s.d_img[1] = s.d_img_set[prefetched_set][1];
-    } else {
-        if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
-        if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
-    }
+    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
     mark(c, s, "copy_in");
     launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
     mark(c, s, "descriptor");
@@ -482,19 +465,26 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
     const bool fused_post = post_fusable(p);
     // With device-resident output buffers the last kernel that touches a map writes it straight into the
     // caller's buffer.  D2 without post-processing is final after the L/R check.
-    float* lr_out[2] = {s.d_D[0], s.d_D[1]};
-    if (io.device_io && n_post == 1) lr_out[1] = io.D2;
-    const bool rows_fused = lr_rows_fusable(g);
-    // Host output, D2 final after the L/R check: its values are raw integer disparities or -10, so it
-    // crosses PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
-    bool d2_i16 = !io.device_io && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
-    if (d2_i16) {
-        // the widening runs on the CPU: the caller's D2 must be host memory (a device pointer may be
-        // passed to the host-buffer entry points too; it then takes the plain copy)
+    // Where the kernels can store a finished map directly: device buffers and, optionally (direct_out),
+    // PINNED host buffers through their device alias.  A copy kernel reaches 52 GB/s that way
+    // (tools/micro/zerocopy_d2h.cu) but letting k_post_fused / k_lr_rows store across PCIe costs the pipeline
+    // more than the copy engine does, so the default for host buffers is the copy path.
+    float* user[2] = {io.D1, io.D2};
+    float* direct[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; k++) {
+        if (io.device_io) { direct[k] = user[k]; continue; }
+        if (p.filter_median || !c->direct_out) continue;
         cudaPointerAttributes attr{};
-        if (cudaPointerGetAttributes(&attr, io.D2) != cudaSuccess) { cudaGetLastError(); d2_i16 = false; }
-        else if (attr.type == cudaMemoryTypeDevice) d2_i16 = false;
+        if (cudaPointerGetAttributes(&attr, user[k]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (attr.type == cudaMemoryTypeDevice) direct[k] = user[k];
+        else if (attr.type == cudaMemoryTypeHost && attr.devicePointer) direct[k] = static_cast<float*>(attr.devicePointer);
     }
+    float* lr_out[2] = {s.d_D[0], s.d_D[1]};
+    if (direct[1] && n_post == 1) lr_out[1] = direct[1];
+    const bool rows_fused = lr_rows_fusable(g);
+    // Copy path, D2 final after the L/R check: its values are raw integer disparities or -10, so it
+    // crosses PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
+    const bool d2_i16 = !direct[1] && !io.device_io && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
     if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], s.d_parent, s.d_size,
                                    d2_i16 ? s.d_D2_i16 : nullptr, st);
     else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], st);          // elas.cpp:116
@@ -510,7 +500,7 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         for (int k = 0; k < n_post; k++) {
             launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, false, rows_fused && k == 0);
             mark(c, s, k ? "segments2" : "segments");
-            final_map[k] = io.device_io ? (k ? io.D2 : io.D1) : s.d_raw[k];
+            final_map[k] = direct[k] ? direct[k] : s.d_raw[k];
             launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, final_map[k],
                               s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, st);
             if (s.capture) {
@@ -554,12 +544,11 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         if (int32_t rc = grab(s, "D2", final_map[1], ND * 4)) return rc;
     }
     s.last_D1 = final_map[0];
-    // maps out: nothing to do for maps already written in place; the others are copied on the slot's copy
+    // maps out: nothing to do for maps the kernels stored in place; the others are copied on the slot's copy
     // stream so that the compute stream is free for the next frame (stage timing keeps them in line)
-    float* user[2] = {io.D1, io.D2};
+    auto in_place = [&](int k) { return direct[k] && final_map[k] == direct[k]; };
     cudaStream_t out_stream = st;
-    bool copies = false;
-    for (int k = 0; k < 2; k++) copies |= final_map[k] != user[k];
+    const bool copies = !in_place(0) || !in_place(1);
     if (copies && !c->timing) {
         CK(cudaEventRecord(s.ev_done, st));
         CK(cudaStreamWaitEvent(s.copy_stream, s.ev_done, 0));
@@ -567,7 +556,7 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
     }
     s.expand_D2 = nullptr;
     for (int k = 0; k < 2; k++) {
-        if (final_map[k] == user[k]) continue;
+        if (in_place(k)) continue;
         if (k == 1 && d2_i16) {
             CK(cudaMemcpyAsync(s.h_D2_i16, s.d_D2_i16, ND * 2, cudaMemcpyDeviceToHost, out_stream));
             s.expand_D2 = user[1];
@@ -589,8 +578,10 @@ int32_t frame_finish(elas_b200_ctx* c, Slot& s)
     CK(cudaGetLastError());
     c->ns_wait_b += now_ns() - t4; c->frames += 1;
     if (s.expand_D2) {
+        const long long t5 = now_ns();
         widen_i16_to_f32(s.h_D2_i16, s.expand_D2, (size_t)c->g.Dw * c->g.Dh);
         s.expand_D2 = nullptr;
+        c->ns_host += now_ns() - t5;             // counted with the host stage: CPU work of the frame
     }
     if (c->timing) {
         CK(cudaStreamSynchronize(s.stream));
@@ -622,11 +613,65 @@ int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I
     return frame_finish(c, s);
 }
 
-void worker_main(elas_b200_ctx* c, int slot)
+// Batch scheduler.  Workers are not tied to slots: every worker walks over all slots and advances
+// whichever one can move -- an idle slot takes the next frame of the batch and gets its phase A
+// enqueued; a slot whose phase A has finished (event query, no blocking) gets its host stage run and its
+// phase B enqueued; a slot whose maps have landed is widened/reported and becomes idle again.  With more
+// slots than workers the GPU always has phases queued while every core does host stages, and no core
+// ever sits in a blocking wait on one particular frame.
+bool advance_slot(elas_b200_ctx* c, Slot& s, elas_b200_ctx::Job* job)
+{
+    auto report = [&](int i, int32_t rc) {
+        if (job->status) job->status[i] = rc;
+        if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
+        job->done.fetch_add(1);
+    };
+    switch (s.state) {
+    case 0: {
+        if (job->next.load(std::memory_order_relaxed) >= job->n) return false;
+        const int i = job->next.fetch_add(1);
+        if (i >= job->n) return false;
+        s.frame = i;
+        const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
+        int32_t rc = phase_a_submit(c, s, io);
+        if (!rc && cudaEventRecord(s.ev_a, s.stream) != cudaSuccess) rc = ELAS_B200_E_CUDA;
+        if (rc) { report(i, rc); return true; }
+        s.state = 1;
+        return true;
+    }
+    case 1: {
+        const cudaError_t q = cudaEventQuery(s.ev_a);
+        if (q == cudaErrorNotReady) return false;
+        const int i = s.frame;
+        const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
+        int n = 0;
+        int32_t rc = q == cudaSuccess ? phase_a_finish_and_host(c, s, &n) : ELAS_B200_E_CUDA;
+        if (!rc && n < 3) {
+            rc = fill_invalid(c, s, io.D1, io.D2, io.device_io);
+            if (!rc) rc = ELAS_B200_E_FEW_SUPPORT;
+        } else if (!rc && !(rc = phase_b_submit(c, s, io))) {
+            s.state = 2;
+            return true;
+        }
+        s.state = 0;
+        report(i, rc);
+        return true;
+    }
+    default: {
+        const cudaError_t q = cudaEventQuery(s.ev_out);
+        if (q == cudaErrorNotReady) return false;
+        s.state = 0;
+        report(s.frame, q == cudaSuccess ? frame_finish(c, s) : ELAS_B200_E_CUDA);
+        return true;
+    }
+    }
+}
+
+void worker_main(elas_b200_ctx* c, int worker)
 {
     cudaSetDevice(c->device);
     uint64_t seen = 0;
-    Slot& s = *c->slots[slot];
+    const int n_slots = (int)c->slots.size();
     for (;;) {
         elas_b200_ctx::Job* job = nullptr;
         {
@@ -637,46 +682,20 @@ void worker_main(elas_b200_ctx* c, int slot)
             seen = c->job_seq;
             job->active++;
         }
-        auto report = [&](int i, int32_t rc) {
-            if (job->status) job->status[i] = rc;
-            if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
-            job->done.fetch_add(1);
-        };
-        // software pipeline over this slot's frames: frame i's maps travel out (copy stream) and frame
-        // i+1's images travel in (prefetch stream) while the compute stream and the host stage work on
-        // what lies between; frame i is reported once its maps have landed
-        auto claim = [&](FrameIO* io) {
-            const int i = job->next.fetch_add(1);
-            if (i >= job->n) return -1;
-            *io = FrameIO{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
-            return i;
-        };
-        int in_flight = -1;
-        FrameIO io{}, io_next{};
-        int set = -1, set_next = -1;
-        int32_t rc_next = ELAS_B200_OK;
-        int i = claim(&io);
-        if (i >= 0) rc_next = images_in(c, s, io, &set);
-        while (i >= 0) {
-            int n = 0;
-            int32_t rc = rc_next;
-            if (!rc) rc = phase_a_submit(c, s, io, set);
-            const int i_next = claim(&io_next);                       // prefetch the next frame's images
-            rc_next = i_next >= 0 ? images_in(c, s, io_next, &set_next) : ELAS_B200_OK;
-            if (!rc) rc = phase_a_finish_and_host(c, s, &n);
-            if (in_flight >= 0) { report(in_flight, frame_finish(c, s)); in_flight = -1; }
-            if (!rc && n < 3) {
-                rc = fill_invalid(c, s, io.D1, io.D2, io.device_io);
-                if (!rc) rc = ELAS_B200_E_FEW_SUPPORT;
-                report(i, rc);
-            } else if (!rc && !(rc = phase_b_submit(c, s, io))) {
-                in_flight = i;
-            } else {
-                report(i, rc);
+        int idle_scans = 0;
+        while (job->done.load(std::memory_order_acquire) < job->n) {
+            bool progressed = false;
+            for (int k = 0; k < n_slots; k++) {
+                Slot& s = *c->slots[(worker + k) % n_slots];
+                if (s.busy.load(std::memory_order_relaxed) || s.busy.exchange(1, std::memory_order_acquire)) continue;
+                progressed |= advance_slot(c, s, job);
+                s.busy.store(0, std::memory_order_release);
             }
-            i = i_next; io = io_next; set = set_next;
+            if (progressed) { idle_scans = 0; continue; }
+            // nothing could move: back off briefly (the GPU is working), longer if it keeps happening
+            const int spins = ++idle_scans < 16 ? 64 : 512;
+            for (int k = 0; k < spins; k++) _mm_pause();
         }
-        if (in_flight >= 0) report(in_flight, frame_finish(c, s));
         {
             std::lock_guard<std::mutex> lk(c->mu);
             job->active--;
@@ -760,6 +779,12 @@ const char* elas_b200_version(void) { return "elas_b200 0.1 (sm_100a; CUDA kerne
 int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
                          int32_t width, int32_t height, int32_t n_slots)
 {
+    return elas_b200_create_ex(out, device, p, width, height, n_slots, 0);
+}
+
+int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                            int32_t width, int32_t height, int32_t n_slots, int32_t n_workers)
+{
     if (!out || !p || width < 16 || n_slots < 1 || n_slots > 64) return ELAS_B200_E_BAD_ARG;
     *out = nullptr;
     if (p->disp_max < 0 || p->disp_max > 4095 || p->disp_min > p->disp_max || p->candidate_stepsize < 1) return ELAS_B200_E_BAD_ARG;
@@ -794,6 +819,7 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
         c->blocking_sync = cores > 0 && (unsigned)n_slots > cores;
         if (const char* e = std::getenv("ELAS_B200_BLOCKING_SYNC")) c->blocking_sync = std::atoi(e) != 0;
         if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
+        if (const char* e = std::getenv("ELAS_B200_DIRECT_OUT")) c->direct_out = std::atoi(e) != 0;
     }
     for (int i = 0; i < n_slots; i++) {
         c->slots.emplace_back(new Slot);
@@ -803,7 +829,16 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
             return rc;
         }
     }
-    for (int i = 0; i < n_slots; i++) c->workers.emplace_back(worker_main, c.get(), i);
+    {
+        // workers: as many as there are cores to run host stages on, never more than slots
+        int cores = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+        if (n_workers <= 0) n_workers = cores > 0 ? cores : 1;
+        if (const char* e = std::getenv("ELAS_B200_WORKERS")) n_workers = std::atoi(e);
+        n_workers = std::max(1, std::min(n_workers, n_slots));
+    }
+    for (int i = 0; i < n_workers; i++) c->workers.emplace_back(worker_main, c.get(), i * n_slots / n_workers);
     *out = c.release();
     return ELAS_B200_OK;
 }

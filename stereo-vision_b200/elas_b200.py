@@ -53,7 +53,7 @@ _lib = None
 
 EXPORTS = [
     "elas_b200_default_params", "elas_b200_stereomapper_params", "elas_b200_process",
-    "elas_b200_create", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
+    "elas_b200_create", "elas_b200_create_ex", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
@@ -79,6 +79,7 @@ def load_library():
     lib.elas_b200_stereomapper_params.restype = None
     lib.elas_b200_process.argtypes = [P, u8p, u8p, f32p, f32p, i32p]
     lib.elas_b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, P, C.c_int32, C.c_int32, C.c_int32]
+    lib.elas_b200_create_ex.argtypes = [C.POINTER(C.c_void_p), C.c_int32, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.elas_b200_destroy.argtypes = [C.c_void_p]
     lib.elas_b200_destroy.restype = None
     lib.elas_b200_process_ctx.argtypes = [C.c_void_p, C.c_int32, u8p, u8p, f32p, f32p, C.c_int32]
@@ -178,16 +179,16 @@ def host_stage(params, width, height, dcan):
 class ElasB200:
     """A persistent context (elas_b200_create): n_slots frames in flight on one device."""
 
-    def __init__(self, params, width, height, n_slots=1, device=0):
+    def __init__(self, params, width, height, n_slots=1, device=0, n_workers=0):
         self.lib = load_library()
         if self.lib.elas_b200_device_count() < 1:
             raise RuntimeError("elas_b200: no CUDA device; this library has no CPU fallback")
         self.params, self.W, self.H, self.n_slots, self.device = params, width, height, n_slots, device
         self.shape = (height // 2, width // 2) if params.subsampling else (height, width)
         self.ctx = C.c_void_p()
-        rc = self.lib.elas_b200_create(C.byref(self.ctx), device, C.byref(params), width, height, n_slots)
+        rc = self.lib.elas_b200_create_ex(C.byref(self.ctx), device, C.byref(params), width, height, n_slots, n_workers)
         if rc != 0:
-            raise RuntimeError(f"elas_b200_create failed with {rc}")
+            raise RuntimeError(f"elas_b200_create_ex failed with {rc}")
 
     def close(self):
         if self.ctx:

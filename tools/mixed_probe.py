@@ -12,7 +12,7 @@ for i in range(B):
     h_I[i, 0, :, :W] = torch.from_numpy(pairs[i % 8][0]); h_I[i, 1, :, :W] = torch.from_numpy(pairs[i % 8][1])
 h_D = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
 d_I = h_I.cuda(); d_D = torch.empty((B, 2, H, W), dtype=torch.float32, device="cuda")
-e = elas_b200.ElasB200(elas_b200.stereomapper(D), W, H, n_slots=slots)
+e = elas_b200.ElasB200(elas_b200.stereomapper(D), W, H, n_slots=slots, n_workers=int(os.environ.get("PROBE_WORKERS", "0")))
 P = lambda t, k: [t[i, k].data_ptr() for i in range(B)]
 for name, I, Dm in (("dev in,  dev out ", d_I, d_D), ("host in, dev out ", h_I, d_D), ("dev in,  host out", d_I, h_D), ("host in, host out", h_I, h_D)):
     for _ in range(2): e.process_batch_ptrs(P(I, 0), P(I, 1), P(Dm, 0), P(Dm, 1), bpl, device=False)

@@ -21,7 +21,7 @@ for name, fn in (("H2D", lambda: big_d.copy_(big_h, non_blocking=True)), ("D2H",
     torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(4): fn()
     torch.cuda.synchronize(); print(f"PCIe {name}: {4 * 0.268435456 / (time.perf_counter() - t):.1f} GB/s")
-e = elas_b200.ElasB200(elas_b200.stereomapper(D), W, H, n_slots=slots)
+e = elas_b200.ElasB200(elas_b200.stereomapper(D), W, H, n_slots=slots, n_workers=int(os.environ.get("PROBE_WORKERS", "0")))
 P = lambda t, k: [t[i, k].data_ptr() for i in range(B)]
 for dev, I, Dm in ((True, d_I, d_D), (False, h_I, h_D)):
     for _ in range(3): e.process_batch_ptrs(P(I, 0), P(I, 1), P(Dm, 0), P(Dm, 1), bpl, device=dev)
