@@ -61,6 +61,15 @@ __device__ __forceinline__ unsigned sad16(const uint4& a, const uint4& b)
     return s + t;
 }
 
+// same, accumulating into two running sums (several blocks share the chains)
+__device__ __forceinline__ void sad16_acc(const uint4& a, const uint4& b, unsigned& s, unsigned& t)
+{
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.x), "r"(b.x));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(t) : "r"(a.y), "r"(b.y));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.z), "r"(b.z));
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(t) : "r"(a.w), "r"(b.w));
+}
+
 // sum |desc[i] - 128| (elas.cpp:358-362, :851-855)
 __device__ __forceinline__ unsigned texture16(const uint4& a)
 {

@@ -18,28 +18,33 @@
 namespace elasb {
 namespace {
 
-struct Best { int e1, d1, e2; };
+// Per-lane running best / second best in the reference's scan order (elas.cpp:417-428):
+//   if (sum < e1) { e2 = e1; e1 = sum; d1 = d; } else if (sum < e2) e2 = sum;
+// kept as key = (energy << 16 | d): a lane visits its disparities in ascending order, so among equal
+// energies the smaller key is the earlier d, which is what the strict '<' keeps.  Energies stay below
+// 4 * 16 * 255 < 2^15 and d below 2^12 (checked at context creation).
+struct Best { unsigned key; int e2; };
+constexpr unsigned kNoKey = (32767u << 16) | 0xFFFFu;     // nothing evaluated: e1 = 32767 (elas.cpp:378-381)
 
 __device__ __forceinline__ void scan_update(Best& b, int sum, int d)
 {
-    // elas.cpp:417-428
-    if (sum < b.e1) { b.e2 = b.e1; b.e1 = sum; b.d1 = d; }
-    else if (sum < b.e2) { b.e2 = sum; }
+    const unsigned key = ((unsigned)sum << 16) | (unsigned)d;
+    const unsigned loser = max(b.key, key);               // the one that does not become / stay the best
+    b.key = min(b.key, key);
+    b.e2 = min(b.e2, (int)(loser >> 16));
 }
 
-__device__ __forceinline__ Best warp_merge(Best b)
+// Warp-wide (best energy, its disparity, second-best energy) with two REDUX reductions: the best key is
+// the minimum key (ties between lanes: the smaller d, as in the reference's single ascending scan); the
+// second order statistic of all energies is the minimum over lanes of "my second best if I hold the
+// winner, else my best".
+__device__ __forceinline__ void warp_merge(const Best& b, int& e1, int& d1, int& e2)
 {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        int oe1 = __shfl_xor_sync(0xffffffffu, b.e1, off);
-        int od1 = __shfl_xor_sync(0xffffffffu, b.d1, off);
-        int oe2 = __shfl_xor_sync(0xffffffffu, b.e2, off);
-        // d1 == -1 marks "nothing evaluated" and carries e1 = 32767
-        bool other_wins = (oe1 < b.e1) || (oe1 == b.e1 && od1 >= 0 && (b.d1 < 0 || od1 < b.d1));
-        if (other_wins) { b.e2 = min(oe2, b.e1); b.e1 = oe1; b.d1 = od1; }
-        else            { b.e2 = min(b.e2, oe1); }
-    }
-    return b;
+    const unsigned best = __reduce_min_sync(0xffffffffu, b.key);
+    const unsigned mine = b.key == best ? (unsigned)b.e2 : (b.key >> 16);
+    e2 = (int)__reduce_min_sync(0xffffffffu, mine);
+    e1 = (int)(best >> 16);
+    d1 = best == kNoKey ? -1 : (int)(best & 0xFFFFu);
 }
 
 // The four descriptor rows a lattice row needs (rows v-2 and v+2 of both images), staged in shared
@@ -48,10 +53,18 @@ struct Strips {
     const uint4* rowA[2];    // row v-2 of desc1 / desc2
     const uint4* rowB[2];    // row v+2
     int org;                 // column of entry 0 (same for all four strips)
+    int len;                 // columns staged
 };
 
 // computeMatchingDisparity for one (u,v); all lanes of the warp call it with the same arguments.
 // own_img = 0: reference pixel in the left image (forward match), 1: in the right image (reverse).
+//
+// The energy of disparity d adds four block SADs at the other image's columns c-2 and c+2 (rows v-2, v+2),
+// c = u -/+ d (elas.cpp:329-332, :400-414).  Disparities d and d+4 therefore share a column: a lane takes
+// the three disparities d, d+4, d+8 together and loads 4 columns x 2 rows instead of 6 x 2 -- shared-memory
+// bandwidth (LDS.128 = 4 wavefronts per warp) is what bounds this kernel, not the SAD arithmetic.  Lane l
+// of pass p owns d = dmin + 96 p + 12 (l / 4) + (l % 4) + {0, 4, 8}: every quarter warp reads eight
+// columns that are distinct modulo 8, i.e. conflict-free 16-byte accesses.
 __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_params& p, int u, int v,
                                            const uint4* __restrict__ own_center, const Strips& st,
                                            int own_img, int lane)
@@ -69,24 +82,44 @@ __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_p
 
     const uint4* ownA = st.rowA[own_img] - st.org;        // indexable by column
     const uint4* ownB = st.rowB[own_img] - st.org;
-    const uint4* othA = st.rowA[1 - own_img] - st.org;
-    const uint4* othB = st.rowB[1 - own_img] - st.org;
+    const uint4* othA = st.rowA[1 - own_img];             // indexable by column - org (clamped below)
+    const uint4* othB = st.rowB[1 - own_img];
     const uint4 a1 = ownA[u - u_step], a2 = ownA[u + u_step];                        // :369-372
     const uint4 a3 = ownB[u - u_step], a4 = ownB[u + u_step];
 
-    Best b = {32767, -1, 32767};                                                     // :378-381
-    for (int d = dmin + lane; d <= dmax; d += 32) {                                  // :396-429
-        const int uw = right_image ? u + d : u - d;
-        int sum = sad16(a1, othA[uw - u_step]);
-        sum += sad16(a2, othA[uw + u_step]);
-        sum += sad16(a3, othB[uw - u_step]);
-        sum += sad16(a4, othB[uw + u_step]);
-        scan_update(b, sum, d);
+    const int sgn = right_image ? 1 : -1;                 // warped column = u + sgn * d
+    const int lane_off = 12 * (lane >> 2) + (lane & 3);
+    Best b = {kNoKey, 32767};                                                        // :378-381
+    for (int d0 = dmin + lane_off; d0 - lane_off <= dmax; d0 += 96) {                // :396-429
+        // the four columns X_j = (u + sgn*d0) + sgn*(4j - 2), j = 0..3, as strip indices; disparities past
+        // dmax are computed but not counted, their columns are clamped into the staged range
+        const int c0 = u + sgn * d0 - st.org - 2 * sgn;
+        uint4 A[4], B[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = min(max(c0 + 4 * sgn * j, 0), st.len - 1);
+            A[j] = othA[x];
+            B[j] = othB[x];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            // block "u-2" of this disparity is column X_m (right image) or X_{m+1} (left image), block "u+2" the other one
+            const int lo = right_image ? m : m + 1, hi = right_image ? m + 1 : m;
+            unsigned s0 = 0, s1 = 0;
+            sad16_acc(a1, right_image ? A[m] : A[m + 1], s0, s1);
+            sad16_acc(a2, right_image ? A[m + 1] : A[m], s0, s1);
+            sad16_acc(a3, right_image ? B[m] : B[m + 1], s0, s1);
+            sad16_acc(a4, right_image ? B[m + 1] : B[m], s0, s1);
+            (void)lo; (void)hi;
+            const int d = d0 + 4 * m;
+            if (d <= dmax) scan_update(b, (int)(s0 + s1), d);
+        }
     }
-    b = warp_merge(b);
+    int e1, d1, e2;
+    warp_merge(b, e1, d1, e2);
     // :432 -- (float)min_1_E < support_threshold * (float)min_2_E; both minima exist because the
     // range holds at least 11 disparities
-    if (b.d1 >= 0 && (float)b.e1 < __fmul_rn(p.support_threshold, (float)b.e2)) return b.d1;
+    if (d1 >= 0 && (float)e1 < __fmul_rn(p.support_threshold, (float)e2)) return d1;
     return -1;
 }
 
@@ -118,7 +151,7 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
     uint4* s = reinterpret_cast<uint4*>(smem_raw);
     Strips st;
     st.rowA[0] = s; st.rowA[1] = s + cap; st.rowB[0] = s + 2 * cap; st.rowB[1] = s + 3 * cap;
-    st.org = lo;
+    st.org = lo; st.len = len;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
