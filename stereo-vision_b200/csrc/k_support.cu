@@ -54,6 +54,8 @@ struct Strips {
     const uint4* rowB[2];    // row v+2
     int org;                 // column of entry 0 (same for all four strips)
     int len;                 // columns staged
+    const uint4* cen[2];     // row v of desc1 / desc2: the reference pixels' own descriptors (texture test)
+    int cen_org[2];
 };
 
 // computeMatchingDisparity for one (u,v); all lanes of the warp call it with the same arguments.
@@ -66,13 +68,12 @@ struct Strips {
 // of pass p owns d = dmin + 96 p + 12 (l / 4) + (l % 4) + {0, 4, 8}: every quarter warp reads eight
 // columns that are distinct modulo 8, i.e. conflict-free 16-byte accesses.
 __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_params& p, int u, int v,
-                                           const uint4* __restrict__ own_center, const Strips& st,
-                                           int own_img, int lane)
+                                           const Strips& st, int own_img, int lane)
 {
     const int u_step = 2, window = 3, v_step = 2;
     if (!(u >= window + u_step && u <= g.W - window - 1 - u_step &&
           v >= window + v_step && v <= g.H - window - 1 - v_step)) return -1;        // :337
-    if ((int)texture16(__ldg(own_center + (size_t)v * g.W + u)) < p.support_texture) return -1;   // :358-366
+    if ((int)texture16(st.cen[own_img][u - st.cen_org[own_img]]) < p.support_texture) return -1;   // :358-366
 
     const bool right_image = own_img != 0;
     const int dmin = max(p.disp_min, 0);                                             // :384-387
@@ -133,7 +134,7 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int vc = blockIdx.y, uc0 = blockIdx.x * kPointsPerCta;
     const int v = vc * g.step;
     const int npts = min(kPointsPerCta, g.Wc - uc0);
@@ -152,21 +153,33 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
     Strips st;
     st.rowA[0] = s; st.rowA[1] = s + cap; st.rowB[0] = s + 2 * cap; st.rowB[1] = s + 3 * cap;
     st.org = lo; st.len = len;
+    // row v itself is needed only at the reference pixels (texture test): the forward matches start from the
+    // CTA's lattice points in desc1, the reverse matches from (u-d, v) in desc2
+    const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
+    const int c1lo = max(x0 - p.disp_max, 0);
+    uint4* cen0 = s + 4 * cap;
+    uint4* cen1 = cen0 + cen_cap;
+    st.cen[0] = cen0; st.cen[1] = cen1; st.cen_org[0] = x0; st.cen_org[1] = c1lo;
+    __shared__ int s_next;
+    __shared__ int16_t s_result[kPointsPerCta];
     if (threadIdx.x == 0) {
+        s_next = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)len * 16u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(4u * bytes) : "memory");
-        const size_t ra = (size_t)(v - 2) * g.W + lo, rb = (size_t)(v + 2) * g.W + lo;
-        const uint4* src[4] = {desc1 + ra, desc2 + ra, desc1 + rb, desc2 + rb};
-        const uint4* dst[4] = {st.rowA[0], st.rowA[1], st.rowB[0], st.rowB[1]};
+        const uint32_t b0 = (uint32_t)(x1 - x0 + 1) * 16u, b1 = (uint32_t)(x1 - c1lo + 1) * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(4u * bytes + b0 + b1) : "memory");
+        const size_t ra = (size_t)(v - 2) * g.W + lo, rb = (size_t)(v + 2) * g.W + lo, rc = (size_t)v * g.W;
+        const uint4* src[6] = {desc1 + ra, desc2 + ra, desc1 + rb, desc2 + rb, desc1 + rc + x0, desc2 + rc + c1lo};
+        const uint4* dst[6] = {st.rowA[0], st.rowA[1], st.rowB[0], st.rowB[1], cen0, cen1};
+        const uint32_t nbytes[6] = {bytes, bytes, bytes, bytes, b0, b1};
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < 6; k++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(dst[k])), "l"(src[k]), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+                         ::"r"(smem_u32(dst[k])), "l"(src[k]), "r"(nbytes[k]), "r"(smem_u32(&bar)) : "memory");
     }
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -176,16 +189,21 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
 
-    __shared__ int16_t s_result[kPointsPerCta];
-    for (int i = warp; i < npts; i += 8) {
+    // lattice points are handed out dynamically: a point that fails its texture test costs almost
+    // nothing, one that matches costs two full scans, so a fixed assignment leaves warps idle at the end
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&s_next, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= npts) break;
         const int uc = uc0 + i;
         int result = 0;                                       // calloc'ed column 0
         if (uc >= 1) {
             const int u = uc * g.step;
             result = -1;
-            const int d = match_point(g, p, u, v, desc1, st, 0, lane);             // :482
+            const int d = match_point(g, p, u, v, st, 0, lane);                    // :482
             if (d >= 0) {
-                const int d2 = match_point(g, p, u - d, v, desc2, st, 1, lane);    // :486
+                const int d2 = match_point(g, p, u - d, v, st, 1, lane);           // :486
                 if (d2 >= 0 && abs(d - d2) <= p.lr_threshold) result = d;           // :487-490
             }
         }
@@ -208,7 +226,8 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
         attr_set = true;
     }
     const int cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max;
-    const size_t smem = (size_t)4 * cap * 16;
+    const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
+    const size_t smem = ((size_t)4 * cap + 2 * cen_cap + p.disp_max) * 16;
     dim3 grid((g.Wc + kPointsPerCta - 1) / kPointsPerCta, g.Hc);
     k_support<<<grid, 256, smem, s>>>(g, p, desc1, desc2, dcan);
     count_launch();
