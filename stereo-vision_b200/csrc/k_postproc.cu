@@ -258,15 +258,16 @@ __device__ __forceinline__ float masked_abs(float x)
 }
 
 // ((q[(0-r)&3] + q[(1-r)&3]) + q[(2-r)&3]) + q[(3-r)&3]: the reference's lane order for a ring that
-// starts r slots in, without dynamically indexed (local-memory) arrays
+// starts r slots in.  The rotation is two conditional swaps stages (by 1, by 2) on registers: neighbouring
+// pixels of a row have different r, a switch would make the warp walk all four orders.
 __device__ __forceinline__ float ring_sum4(float q0, float q1, float q2, float q3, int r)
 {
-    switch (r & 3) {
-        case 0:  return __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), q2), q3);
-        case 1:  return __fadd_rn(__fadd_rn(__fadd_rn(q3, q0), q1), q2);
-        case 2:  return __fadd_rn(__fadd_rn(__fadd_rn(q2, q3), q0), q1);
-        default: return __fadd_rn(__fadd_rn(__fadd_rn(q1, q2), q3), q0);
-    }
+    const bool r1 = r & 1, r2 = r & 2;
+    // rotate right by 1: (q0,q1,q2,q3) -> (q3,q0,q1,q2)
+    const float a0 = r1 ? q3 : q0, a1 = r1 ? q0 : q1, a2 = r1 ? q1 : q2, a3 = r1 ? q2 : q3;
+    // rotate right by 2
+    const float b0 = r2 ? a2 : a0, b1 = r2 ? a3 : a1, b2 = r2 ? a0 : a2, b3 = r2 ? a1 : a3;
+    return __fadd_rn(__fadd_rn(__fadd_rn(b0, b1), b2), b3);
 }
 
 template <int TAPS>
@@ -489,7 +490,9 @@ k_post_fused(const FuseArgs a)
         const int v = r0 - BACK + y, u = c0 + x;
         const float* centre = sC + y * CW + x + BACK;
         float o = *centre;
-        if (v >= 3 && v < Dh - 3 && u >= BACK && u + FWD < Dw) {
+        // An invalid centre (-10) can only collect weight from other invalid taps (a valid tap is >= 10 away,
+        // weight 0), so its mean is -10 < 0 and the reference keeps the pixel as it is: nothing to compute.
+        if (o >= 0.f && v >= 3 && v < Dh - 3 && u >= BACK && u + FWD < Dw) {
             float r;
             // mean_window indexes line[c * stride]: pass the line origin such that c = u
             if (mean_window<TAPS>(centre - u, 1, u, &r)) o = r;
@@ -503,7 +506,8 @@ k_post_fused(const FuseArgs a)
         const int v = r0 + y, u = c0 + x;
         if (v >= Dh || u >= Dw) continue;
         float o = sC[(y + BACK) * CW + x + BACK];
-        if (u >= 3 && u < Dw - 3 && v >= BACK && v + FWD < Dh) {
+        // the window's centre is the row-pass value; if that is invalid the mean is too (see above)
+        if (sM[(y + BACK) * MW + x] >= 0.f && u >= 3 && u < Dw - 3 && v >= BACK && v + FWD < Dh) {
             float r;
             if (mean_window<TAPS>(sM + (y + BACK) * MW + x - (ptrdiff_t)v * MW, MW, v, &r)) o = r;
         }

@@ -204,3 +204,50 @@ def test_cpp_drop_in_class_matches_oracle(oracle, tmp_path):
         D2 = np.fromfile(str(tmp_path / "d2.out"), np.float32).reshape(H, W)
         _, O1, O2 = oracle.process(L, R, p)
         assert bits_equal(D1, O1) and bits_equal(D2, O2), mode
+
+
+def test_batch_scheduler_more_slots_than_workers_and_a_blank_frame(oracle):
+    """The batch scheduler (workers decoupled from slots): 20 frames over 6 slots driven by 2 workers,
+    one frame without texture (fewer than 3 support points: status 1, maps all -10).  Results must be
+    the per-frame oracle results, in order, whatever slot and worker handled a frame."""
+    p = checkers.stereomapper(95)
+    pairs = [synth.synthetic_pair(416, 200, 95, s)[:2] for s in (21, 22, 23)]
+    blank = (np.full((200, 416), 90, np.uint8), np.full((200, 416), 90, np.uint8))
+    order = [0, 1, 2, 0, 3, 1, 2, 2, 0, 1, 3, 0, 1, 2, 0, 1, 2, 0, 1, 2]
+    frames = [pairs[i] if i < 3 else blank for i in order]
+    e = elas_b200.ElasB200(as_product_params(p), 416, 200, n_slots=6, n_workers=2)
+    try:
+        status, D1, D2 = e.process_batch([a for a, _ in frames], [b for _, b in frames])
+        status2, E1, E2 = e.process_batch([a for a, _ in frames], [b for _, b in frames])   # context reuse
+    finally:
+        e.close()
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    for i, k in enumerate(order):
+        if k == 3:
+            assert status[i] == elas_b200.E_FEW_SUPPORT and (D1[i] == -10).all() and (D2[i] == -10).all()
+        else:
+            assert status[i] == 0 and bits_equal(D1[i], want[k][1]) and bits_equal(D2[i], want[k][2]), f"frame {i}"
+        assert status2[i] == status[i] and bits_equal(E1[i], D1[i]) and bits_equal(E2[i], D2[i])
+
+
+def test_bandwidth_config_4096x2160_properties():
+    """BASELINE.json configs[4] geometry at full size (the oracle would take minutes): size-independent
+    properties -- two slots agree bit for bit, the batch path agrees with the single-frame path, disparities
+    stay inside [0, d_max], invalid pixels are exactly -10, D2 (L/R-checked only) holds integers."""
+    W, H, dmax = 4096, 2160, 256
+    L, R, _ = synth.synthetic_pair(W, H, dmax, 1)
+    e = elas_b200.ElasB200(elas_b200.stereomapper(dmax), W, H, n_slots=2, n_workers=2)
+    try:
+        rc, A1, A2 = e.process(L, R, slot=0)
+        _, B1, B2 = e.process(L, R, slot=1)
+        status, C1, C2 = e.process_batch([L, L], [R, R])
+    finally:
+        e.close()
+    assert rc == 0 and status == [0, 0]
+    assert bits_equal(A1, B1) and bits_equal(A2, B2)
+    for k in range(2):
+        assert bits_equal(C1[k], A1) and bits_equal(C2[k], A2)
+    v1, v2 = A1 >= 0, A2 >= 0
+    assert 0.8 < v1.mean() < 0.99 and 0.8 < v2.mean() < 0.99
+    assert A1.max() <= dmax and A2.max() <= dmax and (A1[~v1] == -10).all() and (A2[~v2] == -10).all()
+    assert (A2[v2] == np.round(A2[v2])).all()
