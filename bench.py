@@ -225,19 +225,36 @@ def main():
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # host workers: this rank's share of the cores; slots: twice that, so the GPU has phases queued while
     # every worker runs a host stage (workers are not tied to slots, elas_b200.cu)
-    workers = args.workers or max(1, min(32, cores // max(world, 1) - 2))      # two cores left to the main thread and the driver
+    share = cores // max(world, 1)
+    # a few cores stay free for the main thread, the driver's threads and (end-to-end path) the copies' completion work
+    workers = args.workers or max(1, min(32, share - (4 if share >= 16 else 2)))
     slots = args.slots or max(2, min(48, 2 * workers))
     B = args.batch
     bpl = W + 15 - (W - 1) % 16
 
     # synthetic inputs: `distinct` seeded pairs per rank, cycled to fill the batch
     pairs = [synth.synthetic_pair(W, H, DMAX, seed=1000 * rank + i)[:2] for i in range(args.distinct)]
-    h_I = torch.zeros((B, 2, H, bpl), dtype=torch.uint8).pin_memory()
+    # pinned host buffers of the end-to-end path; if the box refuses to pin that much, halve the batch
+    # (every rank must take the same decision: weak scaling keeps B equal across ranks)
+    while True:
+        try:
+            h_I = torch.zeros((B, 2, H, bpl), dtype=torch.uint8).pin_memory()
+            h_D = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
+            ok = 1
+        except RuntimeError:
+            h_I = h_D = None
+            ok = 0
+        (all_ok,) = sharding.sum_over_ranks([ok], dev)
+        if int(all_ok) == world:
+            break
+        h_I = h_D = None
+        B //= 2
+        if B < 16:
+            raise SystemExit("bench.py: cannot pin the host buffers of the end-to-end path")
     for i in range(B):
         L, R = pairs[i % args.distinct]
         h_I[i, 0, :, :W] = torch.from_numpy(L)
         h_I[i, 1, :, :W] = torch.from_numpy(R)
-    h_D = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
     d_I = h_I.to(dev)
     d_D = torch.empty((B, 2, H, W), dtype=torch.float32, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # 4x the 126 MB L2
