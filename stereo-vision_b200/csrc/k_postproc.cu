@@ -4,6 +4,9 @@
 // whose per-pixel result depends only on the stage's INPUT, so that pixels can be computed
 // independently (the notes at each kernel say why that is equivalent).  Float expressions use the
 // explicit _rn intrinsics: the reference is x86-64 SSE code without FMA contraction.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace elasb {
@@ -158,37 +161,47 @@ k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
     label_row_runs(c1, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
 }
 
-__global__ void k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
+// k_seg_merge and k_seg_count are chains of dependent L2 accesses (find, CAS): their warps are stalled
+// almost all the time.  They run as a modest grid-stride grid (kSegCtasPerSm CTAs per SM) instead of one
+// thread per pixel, so that they occupy a quarter of an SM's thread slots while the pipeline's other
+// kernels (other slots' frames) use the issue slots they leave idle.
+constexpr int kSegCtasPerSm = 2;
+
+__global__ void __launch_bounds__(256)
+k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-    if (u >= Dw || v + 1 >= Dh) return;
-    const int a = v * Dw + u, b = a + Dw;
-    const float da = D[a], db = D[b];
-    if (!seg_conn(da, db, thr)) return;
-    bool a_start = true, b_start = true;
-    if (u > 0) {
-        const float la = D[a - 1], lb = D[b - 1];
-        a_start = !seg_conn(la, da, thr);
-        b_start = !seg_conn(lb, db, thr);
-        if (!a_start && !b_start && seg_conn(la, lb, thr)) return;   // the pair to the left joins the same runs
+    const int n = Dw * (Dh - 1);
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const int u = a % Dw, b = a + Dw;
+        const float da = D[a], db = D[b];
+        if (!seg_conn(da, db, thr)) continue;
+        bool a_start = true, b_start = true;
+        if (u > 0) {
+            const float la = D[a - 1], lb = D[b - 1];
+            a_start = !seg_conn(la, da, thr);
+            b_start = !seg_conn(lb, db, thr);
+            if (!a_start && !b_start && seg_conn(la, lb, thr)) continue;   // the pair to the left joins the same runs
+        }
+        uf_union(parent, a_start ? a : __ldcg(parent + a), b_start ? b : __ldcg(parent + b));
     }
-    uf_union(parent, a_start ? a : __ldcg(parent + a), b_start ? b : __ldcg(parent + b));
 }
 
-__global__ void k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
-                            int32_t* parent, int32_t* size)
+__global__ void __launch_bounds__(256)
+k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
+            int32_t* parent, int32_t* size)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
-    if (u >= Dw || v >= Dh) return;
-    const int a = v * Dw + u;
-    const float d = D[a];
-    if (!(d >= 0.f)) return;
-    if (u + 1 < Dw && seg_conn(d, D[a + 1], thr)) return;             // not the last pixel of its run
-    const bool is_start = !(u > 0 && seg_conn(D[a - 1], d, thr));
-    const int start = is_start ? a : __ldcg(parent + a);
-    const int root = uf_find(parent, start);
-    __stcg(parent + start, root);                                           // every run ends up one hop from its root
-    if (__ldcg(size + root) < speckle) atomicAdd(size + root, a - start + 1);
+    const int n = Dw * Dh;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const int u = a % Dw;
+        const float d = D[a];
+        if (!(d >= 0.f)) continue;
+        if (u + 1 < Dw && seg_conn(d, D[a + 1], thr)) continue;           // not the last pixel of its run
+        const bool is_start = !(u > 0 && seg_conn(D[a - 1], d, thr));
+        const int start = is_start ? a : __ldcg(parent + a);
+        const int root = uf_find(parent, start);
+        __stcg(parent + start, root);                                           // every run ends up one hop from its root
+        if (__ldcg(size + root) < speckle) atomicAdd(size + root, a - start + 1);
+    }
 }
 
 __global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int32_t* __restrict__ parent,
@@ -551,8 +564,16 @@ void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, in
     if (p.subsampling) speckle = (int)(sqrtf((float)p.speckle_size) * 2);            // :1218
     const float thr = p.speckle_sim_threshold;
     if (!rows_done) { k_seg_rows<<<g.Dh, 256, 0, s>>>(g.Dw, thr, D, parent, size); count_launch(); }
-    k_seg_merge<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent);
-    k_seg_count<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size);
+    static const int seg_ctas = [] {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* e = std::getenv("ELAS_B200_SEG_CTAS_PER_SM");
+        return sms * (e ? std::atoi(e) : kSegCtasPerSm);
+    }();
+    const int seg_grid = std::min(seg_ctas, (n + 255) / 256);
+    k_seg_merge<<<seg_grid, 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent);
+    k_seg_count<<<seg_grid, 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size);
     if (!apply) { count_launch(2); return; }
     k_seg_apply<<<(n + 255) / 256, 256, 0, s>>>(n, speckle, D, parent, size);
     count_launch(3);
