@@ -7,6 +7,12 @@
 // shared memory, derives du/dv for the tile (+2 / +1 halo) in shared memory and writes each
 // pixel's 16 descriptor bytes with a single 16-byte store.  HBM traffic: 1 B/px in, 16 B/px out.
 //
+// Both stages work on groups of four horizontally adjacent pixels per thread: the Sobel stage shares
+// the column sums S = I(v-1)+2I(v)+I(v+1) and T = I(v-1)-I(v+1) between neighbours (6 columns for 4
+// outputs), the gather stage reads each du/dv row it needs as one 8-byte window (two aligned 32-bit
+// loads) and assembles the 16 output words with byte permutes (PRMT) -- 16 loads and ~40 permutes for
+// four pixels instead of 64 byte loads and 48 shift/or.
+//
 // Border rule: pixels outside v in [3,H-3), u in [3,W-3) are zero (the reference leaves
 // them uninitialised); with half resolution only rows 4,6,8,.. < H-3 are computed (descriptor.cpp:54).
 #include "common.cuh"
@@ -15,19 +21,36 @@ namespace elasb {
 namespace {
 
 constexpr int TW = 64, TH = 16;            // output tile
-constexpr int IW = TW + 8, IH = TH + 6;    // image tile: cols u0-4 .. u0+TW+3 (word aligned), rows v0-3 .. v0+TH+2
-constexpr int UW = TW + 4, UH = TH + 4;    // du tile: cols u0-2 .. , rows v0-2 ..
-constexpr int VW = TW + 4, VH = TH + 2;    // dv tile: cols u0-1 .. u0+TW (pitch padded), rows v0-1 ..
+constexpr int IW = TW + 12, IH = TH + 6;   // image tile: cols u0-4 .. u0+TW+7 (word aligned), rows v0-3 .. v0+TH+2
+constexpr int GW = (TW + 4 + 3) / 4;       // du/dv groups of four columns per row: cols u0-2 .. u0-2+4*GW-1
+constexpr int UP = 4 * GW + 4;             // du/dv tile pitch in bytes (cols u0-2 ..), a multiple of 4, plus one spare word
+constexpr int UH = TH + 4;                 // du rows v0-2 .. v0+TH+1; dv is kept for the same rows (v0-1 .. v0+TH used)
 
 __device__ __forceinline__ int sat8(int x) { return min(max(x, 0), 255); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// byte i (0..7) of the 8-byte window {lo, hi}
+struct Win { uint32_t lo, hi; };
+__device__ __forceinline__ Win load_win(const uint8_t* row, int idx)      // idx multiple of 4
+{
+    Win w;
+    w.lo = *reinterpret_cast<const uint32_t*>(row + idx);
+    w.hi = *reinterpret_cast<const uint32_t*>(row + idx + 4);
+    return w;
+}
 
 __global__ void __launch_bounds__(256)
 k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint8_t* __restrict__ img2,
              uint4* __restrict__ desc1, uint4* __restrict__ desc2)
 {
     __shared__ __align__(16) uint8_t sI[IH][IW];
-    __shared__ uint8_t sU[UH][UW];
-    __shared__ uint8_t sV[VH][VW];
+    __shared__ __align__(16) uint8_t sU[UH][UP];
+    __shared__ __align__(16) uint8_t sV[UH][UP];
+    __shared__ uint4 sO[TH][TW];               // finished descriptors, 16-byte chunks XOR-swizzled within 128-byte lines
 
     const uint8_t* __restrict__ img = blockIdx.z ? img2 : img1;
     uint4* __restrict__ desc = blockIdx.z ? desc2 : desc1;
@@ -36,8 +59,8 @@ k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint
 
     // stage the image tile, one aligned 32-bit word per load; outside the padded image = 0
     for (int i = tid; i < IH * (IW / 4); i += 256) {
-        int r = i / (IW / 4), cw = i % (IW / 4);
-        int v = v0 - 3 + r, u = u0 - 4 + 4 * cw;
+        const int r = i / (IW / 4), cw = i - r * (IW / 4);
+        const int v = v0 - 3 + r, u = u0 - 4 + 4 * cw;
         uint32_t w = 0;
         if (v >= 0 && v < g.H && u >= 0 && u < g.bpl)
             w = *reinterpret_cast<const uint32_t*>(img + (size_t)v * g.bpl + u);
@@ -46,41 +69,76 @@ k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint
     __syncthreads();
 
     // du(u,v) = sat8(((S(u-1,v) - S(u+1,v)) >> 2) + 128),  S = I(v-1) + 2 I(v) + I(v+1)
-    for (int i = tid; i < UH * UW; i += 256) {
-        int r = i / UW, c = i % UW;               // (u0-2+c, v0-2+r) -> sI row r+1, col c+2
-        int ir = r + 1, ic = c + 2;
-        int Sl = sI[ir - 1][ic - 1] + 2 * sI[ir][ic - 1] + sI[ir + 1][ic - 1];
-        int Sr = sI[ir - 1][ic + 1] + 2 * sI[ir][ic + 1] + sI[ir + 1][ic + 1];
-        sU[r][c] = (uint8_t)sat8(((Sl - Sr) >> 2) + 128);
-    }
     // dv(u,v) = sat8(((T(u-1,v) + 2 T(u,v) + T(u+1,v)) >> 2) + 128),  T = I(v-1) - I(v+1)
-    for (int i = tid; i < VH * (TW + 2); i += 256) {
-        int r = i / (TW + 2), c = i % (TW + 2);   // (u0-1+c, v0-1+r) -> sI row r+2, col c+3
-        int ir = r + 2, ic = c + 3;
-        int Tl = sI[ir - 1][ic - 1] - sI[ir + 1][ic - 1];
-        int Tc = sI[ir - 1][ic] - sI[ir + 1][ic];
-        int Tr = sI[ir - 1][ic + 1] - sI[ir + 1][ic + 1];
-        sV[r][c] = (uint8_t)sat8(((Tl + 2 * Tc + Tr) >> 2) + 128);
+    // one item = four columns u0-2+4q .. +3 of row v0-2+r: six columns of S and T
+    for (int i = tid; i < UH * GW; i += 256) {
+        const int r = i / GW, q = i - r * GW;
+        const int ir = r + 1, ic = 4 * q + 1;          // column u0-2+4q-1 sits at sI column (u0-3+4q) - (u0-4)
+        int S[6], T[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int a = sI[ir - 1][ic + k], b = sI[ir][ic + k], c = sI[ir + 1][ic + k];
+            S[k] = a + 2 * b + c;
+            T[k] = a - c;
+        }
+        uint32_t du = 0, dv = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            du |= (uint32_t)sat8(((S[k] - S[k + 2]) >> 2) + 128) << (8 * k);
+            dv |= (uint32_t)sat8(((T[k] + 2 * T[k + 1] + T[k + 2]) >> 2) + 128) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(&sU[r][4 * q]) = du;
+        *reinterpret_cast<uint32_t*>(&sV[r][4 * q]) = dv;
     }
     __syncthreads();
 
-    // gather 12 du + 4 dv taps (descriptor.cpp:101-116), one 16-byte store per pixel
-    for (int i = tid; i < TW * TH; i += 256) {
-        int r = i / TW, c = i % TW;
-        int u = u0 + c, v = v0 + r;
-        if (u >= g.W || v >= g.H) continue;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        bool inside = v >= 3 && v < g.H - 3 && u >= 3 && u < g.W - 3;
-        if (half) inside = inside && v >= 4 && !(v & 1);
-        if (inside) {
-            const int ur = r + 2, uc = c + 2;     // this pixel in sU
-            const int vr = r + 1, vc = c + 1;     // this pixel in sV
-            o.x = sU[ur - 2][uc] | (sU[ur - 1][uc - 2] << 8) | (sU[ur - 1][uc] << 16) | (sU[ur - 1][uc + 2] << 24);
-            o.y = sU[ur][uc - 1] | (sU[ur][uc] << 8) | (sU[ur][uc] << 16) | (sU[ur][uc + 1] << 24);
-            o.z = sU[ur + 1][uc - 2] | (sU[ur + 1][uc] << 8) | (sU[ur + 1][uc + 2] << 16) | (sU[ur + 2][uc] << 24);
-            o.w = sV[vr - 1][vc] | (sV[vr][vc - 1] << 8) | (sV[vr][vc + 1] << 16) | (sV[vr + 1][vc] << 24);
+    // gather 12 du + 4 dv taps (descriptor.cpp:101-116) for four pixels (u0+4q .. +3, v0+r); tile column of
+    // pixel k = 4q+2+k, so the window that starts at tile column 4q holds columns u-2 .. u+5 of the group
+    {
+        const int r = tid >> 4, q = tid & 15;
+        const int v = v0 + r, ub = u0 + 4 * q;
+        const int ur = r + 2;                                       // this row in sU / sV
+        const Win um2 = load_win(sU[ur - 2], 4 * q), um1 = load_win(sU[ur - 1], 4 * q), uc = load_win(sU[ur], 4 * q),
+                  up1 = load_win(sU[ur + 1], 4 * q), up2 = load_win(sU[ur + 2], 4 * q);
+        const Win vm1 = load_win(sV[ur - 1], 4 * q), vc = load_win(sV[ur], 4 * q), vp1 = load_win(sV[ur + 1], 4 * q);
+        bool row_ok = v >= 3 && v < g.H - 3;
+        if (half) row_ok = row_ok && v >= 4 && !(v & 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int u = ub + k;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (row_ok && u >= 3 && u < g.W - 3) {
+                // window byte index of column u+dx is k+2+dx; prmt selector nibbles pick bytes 0-3 of the
+                // first operand and 4-7 of the second
+                const uint32_t c = k + 2;
+                // a single byte c of a window comes from its low word (c < 4) or its high word: fixed per k
+#define ELASB_WORD(w) (c < 4 ? (w).lo : (w).hi)
+                // o.x = du(0,-2), du(-2,-1), du(0,-1), du(2,-1)
+                const uint32_t x123 = prmt(um1.lo, um1.hi, (c - 2) << 4 | c << 8 | (c + 2) << 12);      // bytes 1..3
+                o.x = prmt(ELASB_WORD(um2), x123, (c & 3) | 5 << 4 | 6 << 8 | 7 << 12);
+                // o.y = du(-1,0), du(0,0), du(0,0), du(1,0)
+                o.y = prmt(uc.lo, uc.hi, (c - 1) | c << 4 | c << 8 | (c + 1) << 12);
+                // o.z = du(-2,1), du(0,1), du(2,1), du(0,2)
+                const uint32_t z012 = prmt(up1.lo, up1.hi, (c - 2) | c << 4 | (c + 2) << 8);             // bytes 0..2
+                o.z = prmt(z012, ELASB_WORD(up2), 0 | 1 << 4 | 2 << 8 | (4 + (c & 3)) << 12);
+                // o.w = dv(0,-1), dv(-1,0), dv(1,0), dv(0,1)
+                const uint32_t w03 = prmt(ELASB_WORD(vm1), ELASB_WORD(vp1), (c & 3) | (4 + (c & 3)) << 12);  // bytes 0 and 3
+                const uint32_t w12 = prmt(vc.lo, vc.hi, (c - 1) << 4 | (c + 1) << 8);                    // bytes 1..2
+                o.w = prmt(w03, w12, 0 | 5 << 4 | 6 << 8 | 3 << 12);
+#undef ELASB_WORD
+            }
+            // a thread's four descriptors are 64 bytes apart from its neighbour's: stored directly, every
+            // 32-byte sector would be written in two halves by two instructions.  They go through shared
+            // memory instead (chunk index XOR-swizzled: conflict-free both ways) and leave as whole rows.
+            const int pcol = 4 * q + k;
+            sO[r][pcol ^ ((pcol >> 3) & 7)] = o;
         }
-        desc[(size_t)v * g.W + u] = o;
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int r = i / TW, pcol = i - r * TW;
+        const int v = v0 + r, u = u0 + pcol;
+        if (v < g.H && u < g.W) desc[(size_t)v * g.W + u] = sO[r][pcol ^ ((pcol >> 3) & 7)];
     }
 }
 
