@@ -328,19 +328,21 @@ def main():
 
     # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
     # (683 MB algorithmic) does not fit L2, so this is the honest HBM-roofline point of the same kernel
-    roof_4k = None
+    roof_4k = roof_hd = None
     if rank == 0 and world == 1 and not args.no_4k:
-        W4, H4, D4 = 4096, 2160, 256
-        L4, R4, _ = synth.synthetic_pair(W4, H4, D4, seed=0)
-        e4 = elas_b200.ElasB200(elas_b200.stereomapper(D4), W4, H4, n_slots=1, device=local_rank)
-        e4.process(L4, R4)
-        ms4 = e4.time_matching(iters=20, flush_l2=True)
-        e4.close()
-        b4 = algorithmic_bytes_matching(W4, H4, D4)
-        a4 = b4 / (ms4 * 1e-3) / 1e9
-        roof_4k = {"workload": f"synthetic {W4}x{H4}, d_max={D4}", "bound": "hbm", "achieved": round(a4, 1), "peak": peak,
-                   "unit": "GB/s", "frac": round(a4 / peak, 4), "algorithmic_bytes_per_launch": b4,
-                   "ms_per_launch": round(ms4, 5)}
+        def roof_point(Wx, Hx, Dx):
+            Lx, Rx, _ = synth.synthetic_pair(Wx, Hx, Dx, seed=0)
+            ex = elas_b200.ElasB200(elas_b200.stereomapper(Dx), Wx, Hx, n_slots=1, device=local_rank)
+            ex.process(Lx, Rx)
+            msx = ex.time_matching(iters=20, flush_l2=True)
+            ex.close()
+            bx = algorithmic_bytes_matching(Wx, Hx, Dx)
+            ax = bx / (msx * 1e-3) / 1e9
+            return {"workload": f"synthetic {Wx}x{Hx}, d_max={Dx}", "bound": "hbm", "achieved": round(ax, 1), "peak": peak,
+                    "unit": "GB/s", "frac": round(ax / peak, 4), "algorithmic_bytes_per_launch": bx,
+                    "ms_per_launch": round(msx, 5)}
+        roof_hd = roof_point(1920, 1080, 128)       # BASELINE.json configs[2] geometry
+        roof_4k = roof_point(4096, 2160, 256)       # BASELINE.json configs[4] geometry
 
     (launches,) = sharding.sum_over_ranks([launches], dev)      # whole job
 
@@ -375,6 +377,7 @@ def main():
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
+            "roofline_hd_config": roof_hd,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},
