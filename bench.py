@@ -324,6 +324,17 @@ def main():
     b_match = algorithmic_bytes_matching(W, H, DMAX)
     achieved = b_match / (k7_ms * 1e-3) / 1e9
 
+    # the consumers of D1 (colour map, back-projection) on a frame left in HBM:
+    # algorithmic bytes 16 N (4 in, 12 out) and 25 N (1 + 4 in, 20 out)
+    view = None
+    if rank == 0:
+        L0, R0 = pairs[0]
+        engine.process(L0, R0)                      # single-frame path: leaves D1 in the slot's own buffers
+        ms_c, ms_r = engine.time_view(iters=50)
+        n_px = W * H
+        view = {"colormap_us": round(ms_c * 1e3, 2), "colormap_gbs": round(16 * n_px / (ms_c * 1e-3) / 1e9, 1),
+                "reproject_us": round(ms_r * 1e3, 2), "reproject_gbs": round(25 * n_px / (ms_r * 1e-3) / 1e9, 1),
+                "note": "L2-resident at this size (7-12 MB per launch)"}
     engine.close()
 
     # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
@@ -378,6 +389,7 @@ def main():
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
             "roofline_hd_config": roof_hd,
+            "view_kernels": view,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},

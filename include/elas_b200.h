@@ -201,6 +201,11 @@ int32_t elas_b200_host_times(elas_b200_ctx* ctx, double ms_out[5], int64_t* fram
  * launches, outside the timed span).  Negative on error. */
 float   elas_b200_time_matching(elas_b200_ctx* ctx, int32_t slot, int32_t iters, int32_t flush_l2);
 
+/* Bench hook for the consumers of D1: runs k_colormap and k_reproject `iters` times each on the left map
+ * and image the slot's last frame left on the device (nothing crosses PCIe) and returns the mean
+ * milliseconds per launch in ms_out = {colour map, back-projection}. */
+int32_t elas_b200_time_view(elas_b200_ctx* ctx, int32_t slot, int32_t iters, float ms_out[2]);
+
 /* Library / device description (static string, never freed). */
 const char* elas_b200_version(void);
 int32_t     elas_b200_device_count(void);

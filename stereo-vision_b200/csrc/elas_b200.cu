@@ -961,6 +961,36 @@ int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, i
     return ELAS_B200_OK;
 }
 
+int32_t elas_b200_time_view(elas_b200_ctx* c, int32_t slot, int32_t iters, float ms_out[2])
+{
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || iters < 1 || !ms_out || c->p.subsampling) return ELAS_B200_E_BAD_ARG;
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    CK(cudaSetDevice(c->device));
+    Slot& s = *c->slots[slot];
+    if (!s.last_D1) return ELAS_B200_E_BAD_ARG;
+    if (int32_t rc = view_buffers(c, s)) return rc;
+    const FrameGeom& g = c->g;
+    const size_t n = (size_t)g.W * g.H;
+    elas_b200_view view{};
+    view.f = 721.5377f; view.cu = g.W * 0.5f; view.cv = g.H * 0.5f; view.base = 0.54f; view.max_dist = 30.f; view.gain = 1.2f;
+    view.H[0] = view.H[5] = view.H[10] = 1.0;
+    cudaEvent_t e[3];
+    for (auto& x : e) CK(cudaEventCreate(&x));
+    CK(cudaEventRecord(e[0], s.stream));
+    for (int i = 0; i < iters; i++) launch_colormap((int)n, s.last_D1, s.d_view, s.stream);
+    CK(cudaEventRecord(e[1], s.stream));
+    for (int i = 0; i < iters; i++)
+        launch_reproject(g.W, g.H, s.d_img[0], g.bpl, s.last_D1, view, s.d_view, s.d_view + n, s.d_view + 2 * n,
+                         s.d_view + 3 * n, s.d_view + 4 * n, s.stream);
+    CK(cudaEventRecord(e[2], s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaEventElapsedTime(&ms_out[0], e[0], e[1]));
+    CK(cudaEventElapsedTime(&ms_out[1], e[1], e[2]));
+    ms_out[0] /= iters; ms_out[1] /= iters;
+    for (auto& x : e) cudaEventDestroy(x);
+    return ELAS_B200_OK;
+}
+
 int32_t elas_b200_stage_capture(elas_b200_ctx* c, int32_t slot, int32_t enable)
 {
     if (!c || slot < 0 || slot >= (int)c->slots.size()) return ELAS_B200_E_BAD_ARG;

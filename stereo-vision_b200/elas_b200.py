@@ -58,6 +58,7 @@ EXPORTS = [
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
     "elas_b200_version", "elas_b200_device_count", "elas_b200_colormap", "elas_b200_reproject",
+    "elas_b200_time_view",
 ]
 
 
@@ -101,6 +102,7 @@ def load_library():
     lib.elas_b200_time_matching.restype = C.c_float
     lib.elas_b200_colormap.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.elas_b200_reproject.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(View)] + [C.c_void_p] * 5
+    lib.elas_b200_time_view.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     lib.elas_b200_version.restype = C.c_char_p
     lib.elas_b200_device_count.restype = C.c_int32
     _lib = lib
@@ -242,6 +244,14 @@ class ElasB200:
         if rc != 0:
             raise RuntimeError(f"elas_b200_reproject failed with {rc}")
         return outs
+
+    def time_view(self, iters=20, slot=0):
+        """Mean ms per launch of (k_colormap, k_reproject) on the slot's device-resident last frame."""
+        ms = (C.c_float * 2)()
+        rc = self.lib.elas_b200_time_view(self.ctx, slot, iters, ms)
+        if rc != 0:
+            raise RuntimeError(f"elas_b200_time_view failed with {rc}")
+        return float(ms[0]), float(ms[1])
 
     def stage(self, name, slot=0):
         n = self.lib.elas_b200_stage_bytes(self.ctx, slot, name.encode())
