@@ -26,7 +26,7 @@
 namespace elasb {
 namespace {
 
-constexpr int kSegTargetDefault = 448;  // rows wider than this are cut into ~equal segments
+constexpr int kSegTargetDefault = 320;  // rows wider than this are cut into ~equal segments (sweep: tools/k7_sweep*.py)
 
 struct SegPlan { int nseg, segw; };
 
