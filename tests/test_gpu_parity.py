@@ -84,6 +84,12 @@ CASES = [
     ("wide-4096x160-d256-ten-segments", 4096, 160, 256, 12, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255", 1242, 375, 255, 0, lambda d: checkers.stereomapper(d)),
     ("K-1242x375-d255-seed1-demo", 1242, 375, 255, 1, lambda d: checkers.demo(d)),
+    # parameter corners of the fused kernels (same cases as tests/test_oracle.py pins against the reference)
+    ("gap0-nomean", 320, 160, 63, 7, lambda d: checkers.stereomapper(d).copy(ipol_gap_width=0, filter_adaptive_mean=0)),
+    ("gap2-both", 320, 160, 63, 8, lambda d: checkers.demo(d).copy(ipol_gap_width=2)),
+    ("radius3", 320, 160, 63, 9, lambda d: checkers.stereomapper(d).copy(sradius=3.0, match_texture=40)),
+    ("grid16", 320, 160, 63, 10, lambda d: checkers.stereomapper(d).copy(grid_size=16, speckle_size=50)),
+    ("step4-duplicate-vertices", 320, 160, 63, 11, lambda d: checkers.stereomapper(d).copy(candidate_stepsize=4)),
 ]
 
 

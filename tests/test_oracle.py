@@ -48,6 +48,15 @@ CASES = [
     ("middlebury", 320, 160, 63, 4, lambda d: checkers.middlebury().copy(disp_max=d)),
     ("median", 320, 160, 63, 5, lambda d: checkers.demo(d).copy(filter_median=1)),
     ("dmin", 320, 160, 63, 6, lambda d: checkers.stereomapper(d).copy(disp_min=3)),
+    # parameter corners of the fused kernels: no gap filling / no mean, both maps post-processed with a
+    # narrower gap, plane radius 3 with a texture threshold, another grid cell size and speckle size, and a
+    # lattice stride at which two support points can collapse onto one right-image point (duplicate
+    # vertices: Triangle's randomised sort decides which one survives)
+    ("gap0-nomean", 320, 160, 63, 7, lambda d: checkers.stereomapper(d).copy(ipol_gap_width=0, filter_adaptive_mean=0)),
+    ("gap2-both", 320, 160, 63, 8, lambda d: checkers.demo(d).copy(ipol_gap_width=2)),
+    ("radius3", 320, 160, 63, 9, lambda d: checkers.stereomapper(d).copy(sradius=3.0, match_texture=40)),
+    ("grid16", 320, 160, 63, 10, lambda d: checkers.stereomapper(d).copy(grid_size=16, speckle_size=50)),
+    ("step4", 320, 160, 63, 11, lambda d: checkers.stereomapper(d).copy(candidate_stepsize=4)),
 ]
 
 
