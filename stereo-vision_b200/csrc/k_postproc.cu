@@ -405,17 +405,20 @@ struct FuseArgs {
 
 __device__ __forceinline__ float gap_fill(const float* __restrict__ line, int stride, int gap)
 {
-    // line points at the pixel; neighbours at +-j*stride.  Same decisions as k_gap_pass without add_corners.
+    // line points at the pixel; neighbours at +-j*stride.  Same decisions as k_gap_pass without add_corners:
+    // the nearest valid pixel within `gap` on either side, run length (l + r - 1) <= gap.  Written without
+    // loops or branches on the neighbours (gap <= kFuseGap = 3): almost every warp holds an invalid pixel,
+    // so a data-dependent search would be walked by all 32 lanes anyway.
     const float d = line[0];
     if (d >= 0.f) return d;
-    int l = 1, r = 1;
-    while (l <= gap && !(line[-l * stride] >= 0.f)) l++;
-    while (r <= gap && !(line[r * stride] >= 0.f)) r++;
-    if (l <= gap && r <= gap && l + r - 1 <= gap) {
-        const float d1 = line[-l * stride], d2 = line[r * stride];
-        return fabsf(__fsub_rn(d1, d2)) < 3.0f ? __fmul_rn(__fadd_rn(d1, d2), 0.5f) : fminf(d1, d2);   // :1379-1380
-    }
-    return d;
+    const float l1 = line[-stride], l2 = line[-2 * stride], l3 = line[-3 * stride];
+    const float r1 = line[stride], r2 = line[2 * stride], r3 = line[3 * stride];
+    const bool vl1 = l1 >= 0.f && gap >= 1, vl2 = l2 >= 0.f && gap >= 2, vl3 = l3 >= 0.f && gap >= 3;
+    const bool vr1 = r1 >= 0.f && gap >= 1, vr2 = r2 >= 0.f && gap >= 2, vr3 = r3 >= 0.f && gap >= 3;
+    const int l = vl1 ? 1 : vl2 ? 2 : vl3 ? 3 : 8, r = vr1 ? 1 : vr2 ? 2 : vr3 ? 3 : 8;
+    if (l + r - 1 > gap) return d;                              // no bounding pair within reach (8 = none)
+    const float d1 = vl1 ? l1 : vl2 ? l2 : l3, d2 = vr1 ? r1 : vr2 ? r2 : r3;
+    return fabsf(__fsub_rn(d1, d2)) < 3.0f ? __fmul_rn(__fadd_rn(d1, d2), 0.5f) : fminf(d1, d2);   // :1379-1380
 }
 
 template <int TAPS, bool MEAN>
