@@ -227,7 +227,7 @@ def main():
     # every worker runs a host stage (workers are not tied to slots, elas_b200.cu)
     share = cores // max(world, 1)
     # a few cores stay free for the main thread, the driver's threads and (end-to-end path) the copies' completion work
-    workers = args.workers or max(1, min(32, share - (4 if share >= 16 else 2)))
+    workers = args.workers or max(1, min(32, share - (4 if share >= 16 else 2 if share >= 12 else 1)))
     slots = args.slots or max(2, min(48, 2 * workers))
     B = args.batch
     bpl = W + 15 - (W - 1) % 16
