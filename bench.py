@@ -335,6 +335,23 @@ def main():
         view = {"colormap_us": round(ms_c * 1e3, 2), "colormap_gbs": round(16 * n_px / (ms_c * 1e-3) / 1e9, 1),
                 "reproject_us": round(ms_r * 1e3, 2), "reproject_gbs": round(25 * n_px / (ms_r * 1e-3) / 1e9, 1),
                 "note": "L2-resident at this size (7-12 MB per launch)"}
+    # the synchronous drop-in call itself (what Elas::process forwards to, one frame at a time, pageable host
+    # buffers, nothing pipelined): the latency-bound number a caller like StereoThread::run sees
+    drop_in = None
+    if rank == 0:
+        import ctypes as C
+        lib = elas_b200.load_library()
+        o1 = np.empty((H, W), np.float32); o2 = np.empty((H, W), np.float32)
+        dims = (C.c_int32 * 3)(W, H, W)
+        call = lambda Lx, Rx: lib.elas_b200_process(C.byref(params), Lx.ctypes.data, Rx.ctypes.data, o1.ctypes.data, o2.ctypes.data, dims)
+        assert call(*pairs[0]) == 0                             # creates and caches the single-slot context
+        t0 = time.perf_counter()
+        n_calls = 40
+        for i in range(n_calls):
+            call(*pairs[i % args.distinct])
+        dt = time.perf_counter() - t0
+        drop_in = {"value": round(n_calls / dt, 1), "unit": "pairs/s", "ms_per_call": round(1e3 * dt / n_calls, 3),
+                   "note": "elas_b200_process, synchronous, one frame in flight, pageable numpy buffers"}
     engine.close()
 
     # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
@@ -390,6 +407,7 @@ def main():
             "roofline_bandwidth_config": roof_4k,
             "roofline_hd_config": roof_hd,
             "view_kernels": view,
+            "drop_in_call": drop_in,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},
