@@ -62,6 +62,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     // device
     uint8_t* d_img[2] = {nullptr, nullptr};
+    uint8_t* h_img[2] = {nullptr, nullptr};    // pinned staging for images that arrive in pageable host memory
     int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
     int16_t* h_D2_i16 = nullptr;               // pinned landing buffer; expanded to float into the caller's D2 by the worker
     float* expand_D2 = nullptr;                // caller's D2 awaiting expansion at frame_finish (null: nothing to expand)
@@ -185,7 +186,7 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
 void free_slot(Slot& s)
 {
     for (int k = 0; k < 2; k++) {
-        cudaFree(s.d_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
+        cudaFree(s.d_img[k]); cudaFreeHost(s.h_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
         cudaFree(s.d_planes[k]);
     }
@@ -219,6 +220,8 @@ int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
     for (int k = 0; k < 2; k++) {
         CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
         CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
+        CK(cudaMallocHost(&s.h_img[k], (size_t)g.bpl * g.H));
+        std::memset(s.h_img[k], 0, (size_t)g.bpl * g.H);
         CK(cudaMalloc(&s.d_desc[k], N * 16));
         CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
         CK(cudaMalloc(&s.d_grid[k], cells * 4));
@@ -298,8 +301,23 @@ int32_t wait_stream(elas_b200_ctx* c, Slot& s)
 
 // elas.cpp:35-56: W bytes of every row go into the 16-byte-aligned zero-padded copy; when the caller's
 // pitch already equals that padded pitch the reference memcpy's the whole block (:44-48) -- one 1-D copy
-int32_t copy_image_in(const FrameGeom& g, uint8_t* dst, const uint8_t* src, int pitch, cudaStream_t st)
+int32_t copy_image_in(const FrameGeom& g, uint8_t* dst, const uint8_t* src, int pitch, cudaStream_t st,
+                      uint8_t* staging = nullptr)
 {
+    if (staging) {
+        // Pageable host memory (stereomapper's IplImage buffers are malloc'ed): the driver would stage such a
+        // copy itself at a few GB/s; rows go into the slot's pinned staging image instead (padding columns
+        // stay 0 unless the caller's pitch is the padded pitch, elas.cpp:44-55) and leave as one pinned copy
+        cudaPointerAttributes attr{};
+        const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) {
+            if (pitch == g.bpl) std::memcpy(staging, src, (size_t)g.bpl * g.H);
+            else for (int v = 0; v < g.H; v++) std::memcpy(staging + (size_t)v * g.bpl, src + (size_t)v * pitch, (size_t)g.W);
+            CK(cudaMemcpyAsync(dst, staging, (size_t)g.bpl * g.H, cudaMemcpyHostToDevice, st));
+            return ELAS_B200_OK;
+        }
+    }
     if (pitch == g.bpl) CK(cudaMemcpyAsync(dst, src, (size_t)g.bpl * g.H, cudaMemcpyDefault, st));
     else CK(cudaMemcpy2DAsync(dst, g.bpl, src, pitch, g.W, g.H, cudaMemcpyDefault, st));
     return ELAS_B200_OK;
@@ -356,8 +374,8 @@ int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         cudaEventRecord(s.timer.begin, st);
     }
     const long long t0 = now_ns();
-    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st)) return rc;
-    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st)) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[0])) return rc;
+    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[1])) return rc;
     mark(c, s, "copy_in");
     launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
     mark(c, s, "descriptor");
