@@ -110,7 +110,10 @@ __device__ __forceinline__ void label_row_runs(const float* row, int Dw, int bas
             for (int w = warp - 1; w >= 0 && last < 0; w--) last = warp_last[w];
             if (last < 0) last = carry;
         }
-        if (u < Dw) { parent[base + u] = valid ? base + last : -1; size[base + u] = 0; }
+        if (u < Dw) {
+            parent[base + u] = valid ? base + last : -1;
+            if (start) size[base + u] = 0;          // sizes are only ever read and accumulated at run starts (roots)
+        }
         __syncthreads();
         if (threadIdx.x == 255) *carry_s = last >= 0 ? last : carry;     // runs never span an invalid pixel
         __syncthreads();
