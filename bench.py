@@ -46,12 +46,17 @@ def algorithmic_bytes_matching(w, h, dmax, grid_size=20):
     return 72 * w * h + 8 * gw * gh * (dmax + 2)
 
 
-def ncu_traffic_k7():
-    """DRAM bytes per launch of the matching kernel from the committed ncu --set full capture."""
+def ncu_traffic_k7(which=None):
+    """DRAM bytes per launch of the matching kernel from the committed ncu --set full captures
+    (which = None: the 1242x375 workload; "bandwidth_config": 4096x2160)."""
     path = os.path.join(ROOT, "profiles", "r01_k7_traffic.json")
     if not os.path.exists(path):
         return None
     rec = json.load(open(path))
+    if which:
+        rec = rec.get(which)
+        if not rec:
+            return None
     return int(rec["dram_bytes_read_per_launch"]) + int(rec["dram_bytes_write_per_launch"])
 
 
@@ -371,6 +376,7 @@ def main():
                     "ms_per_launch": round(msx, 5)}
         roof_hd = roof_point(1920, 1080, 128)       # BASELINE.json configs[2] geometry
         roof_4k = roof_point(4096, 2160, 256)       # BASELINE.json configs[4] geometry
+        roof_4k["traffic"] = ncu_traffic_k7("bandwidth_config")
 
     (launches,) = sharding.sum_over_ranks([launches], dev)      # whole job
 
