@@ -491,11 +491,13 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
     float* direct[2] = {nullptr, nullptr};
     for (int k = 0; k < 2; k++) {
         if (io.device_io) { direct[k] = user[k]; continue; }
-        if (p.filter_median || !c->direct_out) continue;
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, user[k]) != cudaSuccess) { cudaGetLastError(); continue; }
+        // a device pointer handed to the host-buffer entry points is written in place like any device buffer
+        // (and must never reach the CPU-side widening below)
         if (attr.type == cudaMemoryTypeDevice) direct[k] = user[k];
-        else if (attr.type == cudaMemoryTypeHost && attr.devicePointer) direct[k] = static_cast<float*>(attr.devicePointer);
+        else if (attr.type == cudaMemoryTypeHost && attr.devicePointer && c->direct_out && !p.filter_median)
+            direct[k] = static_cast<float*>(attr.devicePointer);
     }
     float* lr_out[2] = {s.d_D[0], s.d_D[1]};
     if (direct[1] && n_post == 1) lr_out[1] = direct[1];

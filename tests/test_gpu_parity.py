@@ -257,3 +257,27 @@ def test_bandwidth_config_4096x2160_properties():
     assert 0.8 < v1.mean() < 0.99 and 0.8 < v2.mean() < 0.99
     assert A1.max() <= dmax and A2.max() <= dmax and (A1[~v1] == -10).all() and (A2[~v2] == -10).all()
     assert (A2[v2] == np.round(A2[v2])).all()
+
+
+def test_device_pointers_through_the_host_buffer_entry_point():
+    """elas_b200_process_batch (the host-buffer entry) must also accept device pointers for any of the four
+    buffers (cudaMemcpyDefault semantics): the int16 transfer + CPU widening of D2 applies to host memory only."""
+    torch = pytest.importorskip("torch")
+    W, H, dmax = 416, 200, 95
+    L, R, _ = synth.synthetic_pair(W, H, dmax, 31)
+    p = elas_b200.stereomapper(dmax)
+    dI = torch.stack([torch.from_numpy(L), torch.from_numpy(R)]).cuda()
+    dD = torch.full((2, 2, H, W), -77.0, dtype=torch.float32, device="cuda")
+    hD = torch.full((2, H, W), -77.0, dtype=torch.float32).pin_memory()
+    e = elas_b200.ElasB200(p, W, H, n_slots=2, n_workers=1)
+    try:
+        rc, D1, D2 = e.process(L, R)
+        # frame 0: device in, device out; frame 1: device in, pinned host out
+        st = e.process_batch_ptrs([dI[0].data_ptr(), dI[0].data_ptr()], [dI[1].data_ptr(), dI[1].data_ptr()],
+                                  [dD[0, 0].data_ptr(), hD[0].data_ptr()], [dD[0, 1].data_ptr(), hD[1].data_ptr()], W, device=False)
+        torch.cuda.synchronize()
+    finally:
+        e.close()
+    assert rc == 0 and st == [0, 0]
+    assert bits_equal(dD[0, 0].cpu().numpy(), D1) and bits_equal(dD[0, 1].cpu().numpy(), D2)
+    assert bits_equal(hD[0].numpy(), D1) and bits_equal(hD[1].numpy(), D2)
