@@ -331,9 +331,9 @@ int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool devic
     // leaves the caller with uninitialised maps; the defined behaviour here is "all invalid".
     const size_t nd = (size_t)c->g.Dw * c->g.Dh;
     std::vector<float> fill(nd, (float)kInvalid);
-    const cudaMemcpyKind kind = device_io ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
-    CK(cudaMemcpy(D1, fill.data(), nd * 4, kind));
-    CK(cudaMemcpy(D2, fill.data(), nd * 4, kind));
+    (void)device_io;                              // the destination may be host or device memory either way
+    CK(cudaMemcpy(D1, fill.data(), nd * 4, cudaMemcpyDefault));
+    CK(cudaMemcpy(D2, fill.data(), nd * 4, cudaMemcpyDefault));
     return ELAS_B200_OK;
 }
 
