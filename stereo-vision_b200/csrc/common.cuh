@@ -108,6 +108,7 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4*
                      const int32_t* prior, float* D1, float* D2, int map_tag_bits, int map_tag_shift,
                      cudaStream_t s);
 size_t matching_smem_bytes(const FrameGeom& g, int grid_size);
+size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
 // K8  left/right consistency (elas.cpp:1122-1204)
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
                      float* O1, float* O2, cudaStream_t s);

@@ -825,7 +825,10 @@ int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200
     c->map_tag_max = (1 << (30 - c->map_tag_shift)) - 1;
     if (c->map_tag_max < 1) return ELAS_B200_E_UNSUPPORTED;
     c->unit_cap = 2 * c->tri_cap + 8 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
-    if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
+    // both SAD kernels stage their descriptor strips (segment + disparity range) in shared memory: at most
+    // 200 KB per CTA, i.e. disp_max up to ~700 for the support search
+    if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || support_smem_bytes(c->g, *p) > 200 * 1024 ||
+        c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
     // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15
     for (int k = 0; k <= c->g.plane_radius && k < c->g.dn; k++)

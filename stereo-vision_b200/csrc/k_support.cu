@@ -217,6 +217,13 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
 
 }  // namespace
 
+size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p)
+{
+    const int cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max;
+    const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
+    return ((size_t)4 * cap + 2 * cen_cap + p.disp_max) * 16;
+}
+
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                     const uint4* desc2, int16_t* dcan, cudaStream_t s)
 {
@@ -225,9 +232,7 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
         cudaFuncSetAttribute(k_support, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const int cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max;
-    const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
-    const size_t smem = ((size_t)4 * cap + 2 * cen_cap + p.disp_max) * 16;
+    const size_t smem = support_smem_bytes(g, p);
     dim3 grid((g.Wc + kPointsPerCta - 1) / kPointsPerCta, g.Hc);
     k_support<<<grid, 256, smem, s>>>(g, p, desc1, desc2, dcan);
     count_launch();
