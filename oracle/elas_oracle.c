@@ -10,7 +10,8 @@
  * Parity pinning: the reference holds no tests or golden vectors for this path, so
  * this restatement is pinned against the reference itself: oracle/_ref/libelas_ref.so (the
  * unmodified sources compiled by oracle/Makefile) must agree with it bit for bit, stage by stage
- * (tests/test_oracle_vs_reference.py), and against vectors generated from that build and
+ * (tests/test_oracle.py: seeded synthetic pairs, the seven `./elas demo` pairs of libelas/img,
+ * the 4096x2160 configuration and 120 degenerate point sets for the triangulator), and against vectors generated from that build and
  * committed under tests/golden/ (tests/golden/make_golden.py).
  *
  * Every function cites the reference lines it restates.  No SIMD, no threads, one frame at a

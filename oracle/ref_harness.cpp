@@ -86,8 +86,9 @@ void ref_default_params(elas_b200_params* p, int32_t setting)
     p->postprocess_only_left = q.postprocess_only_left; p->subsampling = q.subsampling;
 }
 
-// The reference through its public API only.  Returns 0, or 1 when the reference took its
-// "fewer than 3 support points" early return (detected by D1 staying at the sentinel fill).
+// The reference through its public API only.  Always returns 0: Elas::process is void, its "fewer than
+// 3 support points" early return (elas.cpp:69-75) is visible to the caller only through D1/D2 keeping
+// whatever they held before the call (checkers.py pre-fills them with a sentinel).
 int32_t ref_process(const elas_b200_params* p, const uint8_t* I1, const uint8_t* I2,
                     float* D1, float* D2, const int32_t* dims)
 {

@@ -5,9 +5,12 @@ The reference holds no golden vectors of its own for Elas::process (SURVEY.md se
 outputs of the reference itself, committed so that the GPU box (which has no /root/reference) can
 pin both the oracle restatement and the CUDA path.
 
-Cases (kept small so the fixtures stay well under 1 MB in total):
+Cases:
   synth_320x120_d63   seeded synthetic pair (regenerated from the seed, inputs not stored)
   urban1_crop         a 480x160 crop of libelas/img/urban1 (inputs stored, it is reference DATA)
+  full/urban{1..4}    the four 1344x391 street-scene pairs of libelas/img at full size (the reference's
+                      KITTI-size real images, main.cpp:105-113), stereomapper's parameter set, d_max 255:
+                      inputs, integer stages, raw / final maps (integer-valued maps stored as int16)
 """
 import os
 import sys
@@ -35,9 +38,38 @@ def cases():
     yield "urban1_crop", np.ascontiguousarray(l), np.ascontiguousarray(r), checkers.stereomapper(127), True
 
 
+FULL_INT16 = ["D1_raw", "D2_raw", "D2"]          # integer-valued maps (or -10 / -1): exact as int16
+FULL_KEEP = ["dcan", "support", "tri1", "tri2", "D1"]
+
+
+def full_cases():
+    for k in (1, 2, 3, 4):
+        img = "/root/reference/libelas/img/urban%d_%%s.pgm" % k
+        yield "urban%d" % k, synth.read_pgm(img % "left"), synth.read_pgm(img % "right"), checkers.stereomapper(255)
+
+
+def main_full(ref):
+    os.makedirs(os.path.join(HERE, "full"), exist_ok=True)
+    for name, L, R, p in full_cases():
+        rc, D1, D2, st = ref.run_stages(L, R, p)
+        rc2, E1, E2 = ref.process(L, R, p)
+        assert rc == 0 and np.array_equal(D1, E1) and np.array_equal(D2, E2)
+        out = {k: st[k] for k in FULL_KEEP}
+        for k in FULL_INT16:
+            assert np.array_equal(st[k], st[k].astype(np.int16).astype(np.float32))
+            out[k] = st[k].astype(np.int16)
+        out["params"] = np.frombuffer(bytes(p), np.uint8)
+        out["I1"], out["I2"] = L, R
+        path = os.path.join(HERE, "full", name + ".npz")
+        np.savez_compressed(path, **out)
+        print("full/" + name, "support", len(st["support"]) // 3, "tri", len(st["tri1"]) // 3, len(st["tri2"]) // 3,
+              "valid D1 %.3f" % (D1 >= 0).mean(), os.path.getsize(path), "bytes")
+
+
 def main():
     checkers.build("ref")
     ref = checkers.RefElas()
+    main_full(ref)
     for name, L, R, p, store_inputs in cases():
         rc, D1, D2, st = ref.run_stages(L, R, p)
         rc2, E1, E2 = ref.process(L, R, p)

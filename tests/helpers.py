@@ -29,6 +29,21 @@ def load_golden(name):
     return L, R, p, g
 
 
+def full_golden_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "full", "*.npz")))
+
+
+def load_full_golden(name):
+    """Full-size real pairs (libelas/img/urban1..4, 1344x391): inputs, parameter block and the reference's
+    outputs; integer-valued maps are stored as int16 and widened back to float32 here (exact)."""
+    g = dict(np.load(os.path.join(GOLDEN, "full", name + ".npz")))
+    p = checkers.Params.from_buffer_copy(g.pop("params").tobytes())
+    L, R = g.pop("I1"), g.pop("I2")
+    for k in ("D1_raw", "D2_raw", "D2"):
+        g[k] = g[k].astype(np.float32)
+    return L, R, p, g
+
+
 def bits_equal(a, b):
     a, b = np.asarray(a), np.asarray(b)
     if a.shape != b.shape:

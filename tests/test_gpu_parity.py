@@ -14,7 +14,8 @@ import pytest
 import checkers
 import elas_b200
 import synth
-from helpers import bits_equal, disparity_report, golden_cases, load_golden
+from helpers import (bits_equal, disparity_report, full_golden_cases, golden_cases, load_full_golden,
+                     load_golden)
 
 pytestmark = pytest.mark.gpu
 
@@ -69,6 +70,21 @@ def test_cuda_matches_reference_golden(name):
         rep = disparity_report(st[k], g[k])
         assert rep["mask_mismatch"] == 0 and rep["over_tol"] == 0, f"{name}: {k}: {rep}"
         assert bits_equal(st[k], g[k]), f"{name}: {k} not bit-exact: {rep}"
+
+
+@pytest.mark.parametrize("name", full_golden_cases())
+def test_cuda_matches_reference_on_full_size_real_pairs(name):
+    """libelas/img/urban1..4 at full size (1344x391; SURVEY 8(d): the KITTI stand-ins): committed outputs
+    of the unmodified reference.  Integer stages bit-exact incl. order; maps within +-1 and bit-exact."""
+    L, R, p, g = load_full_golden(name)
+    rc, D1, D2, st = run_cuda(L, R, p)
+    assert rc == 0
+    for k in ["dcan", "support", "tri1", "tri2"]:
+        assert bits_equal(st[k], g[k].ravel()), f"{name}: {k}"
+    for k, got in (("D1_raw", st["D1_raw"]), ("D2_raw", st["D2_raw"]), ("D1", D1.ravel()), ("D2", D2.ravel())):
+        rep = disparity_report(got, g[k])
+        assert rep["mask_mismatch"] == 0 and rep["over_tol"] == 0, f"{name}: {k}: {rep}"
+        assert bits_equal(got, g[k].ravel()), f"{name}: {k} not bit-exact: {rep}"
 
 
 CASES = [
@@ -236,16 +252,21 @@ def test_batch_scheduler_more_slots_than_workers_and_a_blank_frame(oracle):
         assert status2[i] == status[i] and bits_equal(E1[i], D1[i]) and bits_equal(E2[i], D2[i])
 
 
-def test_bandwidth_config_4096x2160_properties():
-    """BASELINE.json configs[4] geometry at full size (the oracle would take minutes): size-independent
-    properties -- two slots agree bit for bit, the batch path agrees with the single-frame path, disparities
-    stay inside [0, d_max], invalid pixels are exactly -10, D2 (L/R-checked only) holds integers."""
+def test_bandwidth_config_4096x2160_all_stages(oracle):
+    """BASELINE.json configs[4] geometry at full size (the oracle takes ~10 s): every stage against the
+    oracle, then the size-independent properties -- two slots agree bit for bit, the batch path agrees with
+    the single-frame path, D2 (L/R-checked only) holds integers."""
     W, H, dmax = 4096, 2160, 256
     L, R, _ = synth.synthetic_pair(W, H, dmax, 1)
+    p = checkers.stereomapper(dmax)
+    rc_o, _, _, st_o = oracle.run_stages(L, R, p)
+    rc, A1, A2, st = run_cuda(L, R, p)
+    assert rc == rc_o == 0
+    check_against(st, st_o, A1, A2, "4096x2160")
+    del st, st_o
     e = elas_b200.ElasB200(elas_b200.stereomapper(dmax), W, H, n_slots=2, n_workers=2)
     try:
-        rc, A1, A2 = e.process(L, R, slot=0)
-        _, B1, B2 = e.process(L, R, slot=1)
+        rc, B1, B2 = e.process(L, R, slot=1)
         status, C1, C2 = e.process_batch([L, L], [R, R])
     finally:
         e.close()

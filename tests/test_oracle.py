@@ -11,7 +11,10 @@ import pytest
 
 import checkers
 import synth
-from helpers import INT_STAGES, FLOAT_STAGES, bits_equal, golden_cases, load_golden
+import os
+
+from helpers import (INT_STAGES, FLOAT_STAGES, bits_equal, full_golden_cases, golden_cases, load_full_golden,
+                     load_golden)
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -22,6 +25,44 @@ def test_oracle_matches_golden(oracle, name):
     for k in INT_STAGES + FLOAT_STAGES:
         assert bits_equal(st[k], g[k]), f"{name}: stage {k} differs from the reference's golden vector"
     assert bits_equal(D1.ravel(), g["D1"]) and bits_equal(D2.ravel(), g["D2"])
+
+
+@pytest.mark.parametrize("name", full_golden_cases())
+def test_oracle_matches_full_size_real_pairs(oracle, name):
+    """libelas/img/urban1..4 at full size (1344x391, the reference's KITTI-size real images): the
+    restatement against the committed outputs of the reference."""
+    L, R, p, g = load_full_golden(name)
+    rc, D1, D2, st = oracle.run_stages(L, R, p)
+    assert rc == 0
+    for k in ("dcan", "support", "tri1", "tri2", "D1_raw", "D2_raw", "D1", "D2"):
+        assert bits_equal(st[k], g[k].ravel()), f"{name}: stage {k} differs from the reference's golden vector"
+
+
+REF_IMG = "/root/reference/libelas/img"
+DEMO_PAIRS = ["cones", "aloe", "raindeer", "urban1", "urban2", "urban3", "urban4"]      # main.cpp:105-113
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_IMG), reason="the reference's demo images are only present in the build container")
+@pytest.mark.parametrize("name", DEMO_PAIRS)
+def test_oracle_equals_reference_on_the_demo_pairs(ref, oracle, name):
+    """`./elas demo` (libelas/src/main.cpp:105-113) runs these seven pairs; every stage of the restatement
+    is bit-identical to the compiled reference on each, with the demo's parameter set (main.cpp:61-62)
+    and, for the street scenes, stereomapper's (stereothread.cpp:76-80)."""
+    L = synth.read_pgm(f"{REF_IMG}/{name}_left.pgm")
+    R = synth.read_pgm(f"{REF_IMG}/{name}_right.pgm")
+    sets = [checkers.demo(255)] + ([checkers.stereomapper(255)] if name.startswith("urban") else [])
+    for p in sets:
+        rc, st = _all_stages_equal(ref, oracle, L, R, p)
+        assert rc == 0 and len(st["support"]) // 3 > 500
+
+
+def test_bandwidth_config_4096x2160(ref, oracle):
+    """BASELINE config 4 geometry (4096x2160, d_max 256): final maps bit-identical to the reference."""
+    L, R, _ = synth.synthetic_pair(4096, 2160, 256, 1)
+    p = checkers.stereomapper(256)
+    _, R1, R2 = ref.process(L, R, p)
+    _, O1, O2 = oracle.process(L, R, p)
+    assert bits_equal(R1, O1) and bits_equal(R2, O2)
 
 
 def test_oracle_process_equals_run_stages(oracle):
