@@ -137,6 +137,22 @@ void launch_colormap(int n, const float* D1, float* out, cudaStream_t s);
 void launch_reproject(int W, int H, const uint8_t* img, int pitch, const float* D1, const elas_b200_view& view,
                       float* I, float* D, float* X, float* Y, float* Z, cudaStream_t s);
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to (kernel, DEVICE): a
+// process may own contexts on several GPUs, so it is set once per device the kernel is launched on
+// (idempotent, so concurrent first launches from several worker threads are harmless).
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* done_mask)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err == cudaSuccess) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+    return err;
+}
+
 // number of kernel launches issued through the launchers above (process-wide, relaxed)
 long long launches_issued();
 void count_launch(int n = 1);

@@ -309,8 +309,11 @@ int32_t copy_image_in(const FrameGeom& g, uint8_t* dst, const uint8_t* src, int 
         // copy itself at a few GB/s; rows go into the slot's pinned staging image instead (padding columns
         // stay 0 unless the caller's pitch is the padded pitch, elas.cpp:44-55) and leave as one pinned copy
         cudaPointerAttributes attr{};
-        const bool pageable = cudaPointerGetAttributes(&attr, src) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
-        cudaGetLastError();
+        // (launch errors are checked where the launches are issued, so clearing the error of a failed
+        // attribute query here cannot swallow one)
+        const bool query_failed = cudaPointerGetAttributes(&attr, src) != cudaSuccess;
+        if (query_failed) cudaGetLastError();
+        const bool pageable = query_failed || attr.type == cudaMemoryTypeUnregistered;
         if (pageable) {
             if (pitch == g.bpl) std::memcpy(staging, src, (size_t)g.bpl * g.H);
             else for (int v = 0; v < g.H; v++) std::memcpy(staging + (size_t)v * g.bpl, src + (size_t)v * pitch, (size_t)g.W);
@@ -381,6 +384,7 @@ int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
     mark(c, s, "descriptor");
     launch_support(g, p, s.d_desc[0], s.d_desc[1], s.h_dcan, st);
     mark(c, s, "support");
+    CK(cudaGetLastError());                      // launch-configuration errors are not sticky: report them with THIS frame
     c->ns_submit_a += now_ns() - t0;
     return ELAS_B200_OK;
 }
@@ -471,6 +475,7 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
                     s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1],
                     tag_bits, c->map_tag_shift, st);
     mark(c, s, "matching");
+    CK(cudaGetLastError());
     s.tables_valid = true;
     if (s.capture) {
         const size_t cells = (size_t)g.gw * g.gh * g.gwords;
@@ -563,6 +568,7 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         if (int32_t rc = grab(s, "D1", final_map[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2", final_map[1], ND * 4)) return rc;
     }
+    CK(cudaGetLastError());
     s.last_D1 = final_map[0];
     // maps out: nothing to do for maps the kernels stored in place; the others are copied on the slot's copy
     // stream so that the compute stream is free for the next frame (stage timing keeps them in line)

@@ -367,11 +367,8 @@ k_matching(const __grid_constant__ MatchArgs a)
 template <int RADIUS, int THREADS, bool SUB>
 void launch_sub(dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_matching<RADIUS, THREADS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static unsigned long long optin = 0;
+    if (ensure_dynamic_smem(k_matching<RADIUS, THREADS, SUB>, 200 * 1024, &optin) != cudaSuccess) return;   // launch error stays pending
     k_matching<RADIUS, THREADS, SUB><<<grid, THREADS, smem, s>>>(a);
 }
 

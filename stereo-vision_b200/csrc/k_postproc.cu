@@ -552,11 +552,8 @@ void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* 
                     float* O1, float* O2, int32_t* parent, int32_t* size, int16_t* O2_i16, cudaStream_t s)
 {
     const size_t smem = (size_t)g.Dw * 12;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_lr_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
+    static unsigned long long optin = 0;
+    if (ensure_dynamic_smem(k_lr_rows, 160 * 1024, &optin) != cudaSuccess) return;
     k_lr_rows<<<g.Dh, 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
                                       D1, D2, O1, O2, parent, size, O2_i16);
     count_launch();

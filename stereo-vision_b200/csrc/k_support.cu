@@ -227,11 +227,8 @@ size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p)
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
                     const uint4* desc2, int16_t* dcan, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_support, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static unsigned long long optin = 0;
+    if (ensure_dynamic_smem(k_support, 200 * 1024, &optin) != cudaSuccess) return;
     const size_t smem = support_smem_bytes(g, p);
     dim3 grid((g.Wc + kPointsPerCta - 1) / kPointsPerCta, g.Hc);
     k_support<<<grid, 256, smem, s>>>(g, p, desc1, desc2, dcan);
