@@ -100,14 +100,22 @@ void launch_diffuse_raster(const FrameGeom& g, int subsampling, const uint32_t* 
                            uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
                            const TriRaster* tri1, const TriRaster* tri2, const int32_t* units, int n_units,
                            int32_t* map1, int32_t* map2, int tag_bits, cudaStream_t s);
-// K7  dense matching, both images (elas.cpp:814-955, :960-1118)
-void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
-                     const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
-                     const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
-                     const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
-                     const int32_t* prior, float* D1, float* D2, int map_tag_bits, int map_tag_shift,
-                     cudaStream_t s);
-size_t matching_smem_bytes(const FrameGeom& g, int grid_size);
+// K7  dense matching, both images (elas.cpp:814-955, :960-1118), n_frames frames per launch (blockIdx.z):
+// every pointer addresses frame 0 of a group, *_stride = elements between consecutive frames
+struct MatchBuffers {
+    const uint4* desc[2];
+    const TriRaster* tri[2];
+    const int32_t* map[2];
+    const uint32_t* grid[2];
+    const uint16_t* lists[2];
+    const int32_t* prior;
+    float* D[2];
+    size_t desc_stride, tri_stride, map_stride, grid_stride, lists_stride, D_stride;
+    int rows_per_cta;                    // set by launch_matching
+};
+void launch_matching(const FrameGeom& g, const elas_b200_params& p, const MatchBuffers& b, int n_frames,
+                     int map_tag_bits, int map_tag_shift, cudaStream_t s);
+size_t matching_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
 size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
 // K8  left/right consistency (elas.cpp:1122-1204)
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,

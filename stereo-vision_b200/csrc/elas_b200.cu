@@ -434,6 +434,17 @@ int32_t phase_a_finish_and_host(elas_b200_ctx* c, Slot& s, int* n_out)
     return ELAS_B200_OK;
 }
 
+MatchBuffers match_buffers(const elas_b200_ctx* c, const Slot& s)
+{
+    MatchBuffers b{};
+    for (int k = 0; k < 2; k++) {
+        b.desc[k] = s.d_desc[k]; b.tri[k] = s.d_tri[k]; b.map[k] = s.d_map[k]; b.grid[k] = s.d_grid[k];
+        b.lists[k] = s.d_lists[k]; b.D[k] = s.d_raw[k];
+    }
+    b.prior = c->d_prior;
+    return b;
+}
+
 // ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------------
 int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
 {
@@ -471,9 +482,7 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
                           s.d_lists[1], s.d_tri[0], s.d_tri[1], s.d_tables + units_at, n_units, s.d_map[0],
                           s.d_map[1], tag_bits, st);                                        // :732-775, :1074-1114
     mark(c, s, "diffuse+raster");
-    launch_matching(g, p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                    s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1],
-                    tag_bits, c->map_tag_shift, st);
+    launch_matching(g, p, match_buffers(c, s), 1, tag_bits, c->map_tag_shift, st);
     mark(c, s, "matching");
     CK(cudaGetLastError());
     s.tables_valid = true;
@@ -833,12 +842,13 @@ int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200
     c->unit_cap = 2 * c->tri_cap + 8 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
     // both SAD kernels stage their descriptor strips (segment + disparity range) in shared memory: at most
     // 200 KB per CTA, i.e. disp_max up to ~700 for the support search
-    if (matching_smem_bytes(c->g, p->grid_size) > 200 * 1024 || support_smem_bytes(c->g, *p) > 200 * 1024 ||
+    if (matching_smem_bytes(c->g, *p) > 200 * 1024 || support_smem_bytes(c->g, *p) > 200 * 1024 ||
         c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
     std::vector<int32_t> prior = make_prior(*p, c->g.dn);
     // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15
+    // and relies on the prior never being positive (-log(1 + e/gamma)/beta <= 0 for gamma, beta > 0; k_matching.cu)
     for (int k = 0; k <= c->g.plane_radius && k < c->g.dn; k++)
-        if (prior[k] > 5000 || prior[k] < -5000) return ELAS_B200_E_UNSUPPORTED;
+        if (prior[k] > 0 || prior[k] < -5000) return ELAS_B200_E_UNSUPPORTED;
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
     c->launches_at_create = launches_issued();
@@ -1133,9 +1143,7 @@ float elas_b200_time_matching(elas_b200_ctx* c, int32_t slot, int32_t iters, int
     for (int i = 0; i < iters; i++) {
         if (flush_l2) cudaMemsetAsync(c->d_flush, i & 0xff, c->flush_bytes, s.stream);
         cudaEventRecord(e0, s.stream);
-        launch_matching(c->g, c->p, s.d_desc[0], s.d_desc[1], s.d_tri[0], s.d_tri[1], s.d_map[0], s.d_map[1],
-                        s.d_grid[0], s.d_grid[1], s.d_lists[0], s.d_lists[1], c->d_prior, s.d_raw[0], s.d_raw[1],
-                        s.map_tag << c->map_tag_shift, c->map_tag_shift, s.stream);
+        launch_matching(c->g, c->p, match_buffers(c, s), 1, s.map_tag << c->map_tag_shift, c->map_tag_shift, s.stream);
         cudaEventRecord(e1, s.stream);
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { total = -1; break; }
         float ms = 0;

@@ -2,23 +2,38 @@
 //
 // Reference: Elas::computeDisparity (elas.cpp:960-1118) scan-converts every triangle and calls
 // Elas::findMatch (elas.cpp:814-955) per covered pixel, once for the left and once for the right
-// image.  Here the scan conversion has already produced a triangle-id map per image (k_raster), so
-// the work is a flat per-pixel pass.
+// image.  Here the scan conversion has already produced a triangle-id map per image (k_diffuse_raster),
+// so the work is a flat per-pixel pass.
 //
-// Decomposition: one CTA per (image row v, column segment of ~420 pixels).  Both matching
-// directions of a row read the SAME two descriptor rows (left image: own = desc1, other = desc2;
-// right image: the reverse), so the CTA stages the desc1 strip and the desc2 strip of row
-// clamp(v,2,H-3) (elas.cpp:834) in shared memory ONCE -- two TMA bulk copies (cp.async.bulk,
-// contiguous 16 B/pixel rows) completing on one mbarrier -- and then produces the D1 and the D2
-// pixels of the segment from shared memory.  While the copies are in flight the warps turn the
-// candidate-grid bitmasks of the ~22 cells under the segment into short ascending disparity lists in
-// shared memory.  Every candidate SAD is then an LDS.128 + 4 VABSDIFF4.  HBM sees each descriptor
-// byte about once per row (neighbouring segments overlap by disp_max columns, absorbed by L2), the
-// triangle-id maps once and the two output rows once.
+// Decomposition (v7): one CTA of 256 threads per (ROW PAIR v0, v0+1; column segment of 256 pixels; frame).
+// Both matching directions of a row read the SAME two descriptor rows (left image: own = desc1,
+// other = desc2; right image: the reverse), so the CTA stages, once, the desc1 strip
+// [x0, x1 + disp_max) and the desc2 strip [x0 - disp_max, x1) of both rows plus the candidate lists of
+// the ~14 grid cells under the segment (both images): six TMA bulk copies (cp.async.bulk, contiguous
+// 16 B/pixel rows) completing on one mbarrier.  While they are in flight every thread fetches, for its
+// own column, the four triangle-id entries (2 rows x 2 images) and the planes behind them and turns
+// them into d_plane / validity in registers -- the only global-memory latency of the kernel, hidden
+// behind the TMA latency.  Thread t then runs findMatch for the pixels (x0+t, v0) and (x0+t, v0+1) of
+// the left image TOGETHER, then of the right image: the two pixels lie in the same grid cell
+// (grid_size even), so they share the candidate list, the list loads and the address arithmetic, and
+// the two SAD chains give the instruction-level parallelism.  Every candidate SAD is one LDS.128 + 4
+// VABSDIFF4.U8.ACC from shared memory.
 //
 // Per pixel (findMatch): candidates = the grid cell's disparities OUTSIDE the plane window in
 // ascending order (cost = SAD), then the plane window d_plane-r..d_plane+r ascending
 // (cost = SAD + prior if the triangle is valid); strict '<' keeps the first minimum (elas.cpp:790,805).
+//
+// Candidates are ranked by the key (cost << 8 | evaluation order): the minimum key is the lowest cost
+// and, among equal costs, the candidate the reference evaluates first.  The inner loop carries NO
+// per-candidate window test: every list entry is evaluated with its plain SAD (order = list position)
+// and every window tap with SAD + prior (order = 64 + tap).  The prior is never positive
+// (-log(1 + e/gamma)/beta, elas.cpp:984-992; checked at context creation), so a list entry that lies
+// inside the window can only come out as the overall minimum when its window tap has the SAME cost
+// (prior 0: invalid triangle).  The overall minimum is therefore exact unless it is such an entry --
+// one test per pixel after the loops -- and only then the list pass is redone with the reference's
+// window exclusion (elas.cpp:893).  The range test "warped column inside [2, W-2)" (elas.cpp:896-899,
+// :907-910) is likewise hoisted: a warp whose columns all satisfy it for every disparity runs loops
+// without it.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -26,25 +41,8 @@
 namespace elasb {
 namespace {
 
-constexpr int kSegTargetDefault = 320;  // rows wider than this are cut into ~equal segments (sweep: tools/k7_sweep*.py)
-
-struct SegPlan { int nseg, segw; };
-
-inline int env_int(const char* name, int dflt)
-{
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
-
-inline SegPlan plan_segments(int W)
-{
-    static const int kSegTarget = env_int("ELAS_B200_K7_SEG", kSegTargetDefault);
-    SegPlan s;
-    s.nseg = (W + kSegTarget - 1) / kSegTarget;
-    s.segw = ((W + s.nseg - 1) / s.nseg + 31) & ~31;
-    s.nseg = (W + s.segw - 1) / s.segw;
-    return s;
-}
+constexpr int kThreads = 256;        // = pixels per column segment: thread t owns column x0 + t
+constexpr int kSegW = kThreads;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -60,10 +58,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 }
 
 // TMA bulk copy global -> shared (contiguous bytes, multiple of 16), completes on the mbarrier
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
@@ -79,25 +77,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 
 struct MatchArgs {
     FrameGeom g;
-    int disp_max, match_texture, grid_size, subsampling;
-    int segw, max_cells, map_pitch, variant;
+    int disp_max, match_texture, grid_size, max_cells, map_pitch;
     int map_tag_bits, map_tag_mask;      // triangle-id map entries are tag_bits | index; other tags = stale = uncovered
     uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
-    const uint4* desc[2];
-    const TriRaster* tri[2];
-    const int32_t* map[2];
-    const uint32_t* grid[2];
-    const uint16_t* lists[2];
-    const int32_t* prior;
-    float* D[2];
+    MatchBuffers b;
 };
 
-// Candidates are ranked by the key (cost << 8 | evaluation order): the minimum key is the lowest cost
-// and, among equal costs, the candidate the reference evaluates first -- its strict '<' (elas.cpp:790,
-// :805) -- so candidates need no sequential compare-and-select chain.  A candidate the reference
-// skips (inside the plane window during the grid pass, or warped column outside [2, W-2),
-// elas.cpp:896-899, :907-910) gets the initial key instead of a branch.  Costs stay below 2^15.
-constexpr int kInitKey = (10000 << 8) | 255;
+constexpr int kInitKey = (10000 << 8) | 255;     // elas.cpp:878-879: min_val = 10000, nothing found
 constexpr int kPad = 4;     // strip entries before/after the addressed range: window taps may step outside [0, disp_max]
 
 // ---- shared-memory access by 32-bit shared address (no generic-pointer conversion in the loops) ----
@@ -120,16 +106,11 @@ __device__ __forceinline__ int lds_u16(uint32_t addr)
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return (int)v;
 }
-__device__ __forceinline__ int lds_s32(uint32_t addr)
+// SAD of two 16-byte descriptors on top of `init` (the prior of a window tap, 0 otherwise): one chain of
+// four VABSDIFF4.U8.ACC; the two pixels of a thread give two independent chains
+__device__ __forceinline__ int sad16_from(const uint4& a, const uint4& b, int init)
 {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");   // ordered after plane_pass()'s stores
-    return v;
-}
-// one accumulation chain: the candidate loops run two candidates per trip, which is the ILP
-__device__ __forceinline__ int sad16_chain(const uint4& a, const uint4& b)
-{
-    unsigned s = 0;
+    unsigned s = (unsigned)init;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.x), "r"(b.x));
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.y), "r"(b.y));
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(s) : "r"(a.z), "r"(b.z));
@@ -149,298 +130,365 @@ __device__ __noinline__ int scan_cell_bitmask(const uint32_t* __restrict__ cell,
             const int d = 32 * w + __ffs(m) - 1;
             m &= m - 1;
             if ((d >= dlo && d <= dhi) || d > hi_ok) continue;
-            const int val = sad16_chain(own, lds128(oth_addr + step16 * d));
+            const int val = sad16_from(own, lds128(oth_addr + step16 * d), 0);
             if (val < min_val) { min_val = val; min_d = d; }
         }
     }
     return min_d < 0 ? -1 : ((min_val << 16) | min_d);
 }
 
-// Shared-memory image of one row segment (32-bit shared addresses)
-struct RowCtx {
-    uint32_t strip[2];      // strip[k] + 16*(column - org[k]) = descriptor k at that column
-    int org[2];
-    uint32_t lists;         // [2][max_cells][kGridListStride] u16
-    uint32_t tmap;          // [2][segw] i32: triangle-id map entries, replaced in place by packed (d_plane, valid, covered)
-    int x0, n, v, c0, gy;
+// rare path: the list pass exactly as the reference runs it (entries inside the plane window and entries
+// whose warped column leaves [2, W-2) are skipped, elas.cpp:893-899); used when the fast pass's minimum is a
+// list entry inside the window (see the header)
+__device__ __noinline__ int exact_list_pass(uint32_t list, int cnt, uint4 own, uint32_t oth, int step16,
+                                            int dlo, int dhi, int hi_ok)
+{
+    int best = kInitKey;
+    for (int k = 1; k <= cnt; k++) {
+        const int d = lds_u16(list + 2u * k);
+        if ((d >= dlo && d <= dhi) || d > hi_ok) continue;
+        best = min(best, sad16_from(own, lds128(oth + step16 * d), 0) * 256 + k);
+    }
+    return best;
+}
+
+// Packed per-pixel triangle state (registers): bit 0 = covered by a triangle of THIS frame, bit 1 = valid
+// (elas.cpp:1072), bits 2.. = d_plane + kPlaneBias with d_plane = (int32_t)(plane_a*u + plane_b*v + plane_c)
+// (elas.cpp:861, evaluated left to right with separate roundings).  d_plane is clamped to
+// [-kPlaneBias, 2*kPlaneBias]: beyond [-radius-1, disp_max+radius+1] every value behaves the same (empty window).
+constexpr int kPlaneBias = 16384;
+
+__device__ __forceinline__ int pack_plane(const float4& pl, bool covered, float fu, float fv)
+{
+    const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, fu), __fmul_rn(pl.y, fv)), pl.z);
+    const int d_plane = min(max(__float2int_rz(dp), -kPlaneBias), 2 * kPlaneBias);     // cvt.rzi saturates, NaN -> 0
+    const int valid = __float_as_int(pl.w) != 0;
+    return covered ? (((d_plane + kPlaneBias) << 2) | (valid << 1) | 1) : 0;
+}
+
+// plane window of one pixel (elas.cpp:904-913, :934-943): taps d_plane-R..d_plane+R at consecutive shared
+// addresses from wbase, cost = SAD + prior (the accumulation starts from the prior), order 64 + tap.
+// CHECK = false: every tap is known to lie in [0, hi_ok].
+template <int IMG, int RADIUS, bool CHECK>
+__device__ __forceinline__ int window_taps(const uint4& own, uint32_t wbase, int d_plane, int hi_ok,
+                                           int pr0, int pr1, int pr2, int pr3)
+{
+    constexpr int step16 = IMG ? 16 : -16;
+    int best = kInitKey;
+#define ELASB_TAP(K, PRIOR)                                                                                     \
+    {                                                                                                            \
+        const int val = sad16_from(own, lds128_off<step16 * (K)>(wbase), (PRIOR));                               \
+        int key = val * 256 + (64 + (K) + RADIUS);                                                               \
+        if (CHECK) key = (unsigned)(d_plane + (K)) > (unsigned)hi_ok ? kInitKey : key;                           \
+        best = min(best, key);                                                                                   \
+    }
+    if (RADIUS >= 3) ELASB_TAP(-3, pr3)
+    ELASB_TAP(-2, pr2) ELASB_TAP(-1, pr1) ELASB_TAP(0, pr0) ELASB_TAP(1, pr1) ELASB_TAP(2, pr2)
+    if (RADIUS >= 3) ELASB_TAP(3, pr3)
+#undef ELASB_TAP
+    return best;
+}
+
+// generic plane radius (RADIUS template argument 0): priors from the table, every tap tested
+template <int IMG>
+__device__ __noinline__ int window_generic(const int32_t* __restrict__ prior, uint4 own, uint32_t oth, int d_plane, int radius,
+                                           int dlo, int dhi, int hi_ok, bool valid)
+{
+    constexpr int step16 = IMG ? 16 : -16;
+    int best = kInitKey;
+    for (int d = dlo; d <= dhi; d++) {
+        const int val = sad16_from(own, lds128(oth + step16 * d), valid ? __ldg(prior + abs(d - d_plane)) : 0);
+        const int key = d > hi_ok ? kInitKey : val * 256 + (64 + d - (d_plane - radius));
+        best = min(best, key);
+    }
+    return best;
+}
+
+struct SegCtx {
+    uint32_t strip[2];      // shared address of strip k, row 0, AT COLUMN 0: + 16*column (+ row_stride for row 1)
+    uint32_t row_stride;    // bytes between the two rows of a strip
+    uint32_t lists;         // [2][max_cells][kGridListStride] u16, AT CELL COLUMN 0 of the grid row
 };
 
-// Turns the triangle-id entries of the row segment (both images) into what findMatch needs from the
-// triangle: d_plane = (int32_t)(plane_a*u + plane_b*v + plane_c) (elas.cpp:861, evaluated left to right
-// with separate roundings) and the triangle's validity flag (elas.cpp:1072).  Each thread fetches the
-// planes of all its pixels together (independent 16-byte loads in flight at once, the only global-memory
-// latency of the kernel after the TMA prologue) and writes the packed result back over the entry:
-//   bit 0 = covered by a triangle of THIS frame, bit 1 = valid, bits 2.. = d_plane + kPlaneBias.
-// d_plane is clamped to [-kPlaneBias, 2*kPlaneBias]: beyond [-radius-1, disp_max+radius+1] every value
-// behaves the same (empty plane window).  A thread reads back only entries it wrote: no block barrier.
-constexpr int kPlaneBias = 16384;
-constexpr int kPlaneBatch = 4;
-
-template <int kThreads>
-__device__ __forceinline__ void plane_pass(const MatchArgs& a, int32_t* tmap, int n, int x0, int v)
+// findMatch (elas.cpp:814-955) for the pixels (u, vA) and (u, vA+1) of image IMG; pkA / pkB = pack_plane()
+// (0 = nothing to match: uncovered, outside [2, W-2), or the row does not exist).
+// NPX = 1: only the first pixel exists (odd grid sizes, subsampling).
+// Every thread of the warp runs through this function to the end (one warp-wide vote); lanes without an
+// active pixel run the same instructions on harmless operands (an empty list, disqualified taps).
+template <int IMG, int RADIUS, int NPX>
+__device__ __forceinline__ void match_pair(const MatchArgs& a, const SegCtx& r, int u, int pkA, int pkB,
+                                           bool warp_range_safe, int p0, int p1, int p2, int p3,
+                                           float& outA, float& outB)
 {
-    const float fv = (float)v;
-#pragma unroll
-    for (int img = 0; img < 2; img++) {
-        const TriRaster* __restrict__ tris = a.tri[img];
-        int32_t* row = tmap + img * a.segw;
-        for (int i0 = threadIdx.x; i0 < n; i0 += kPlaneBatch * kThreads) {
-            float4 pl[kPlaneBatch];
-            bool covered[kPlaneBatch];
-#pragma unroll
-            for (int j = 0; j < kPlaneBatch; j++) {
-                const int i = i0 + j * kThreads;
-                const int e = i < n ? row[i] : -1;
-                covered[j] = (e & ~a.map_tag_mask) == a.map_tag_bits;     // stale entries = other frames = uncovered
-                pl[j] = covered[j] ? __ldg(reinterpret_cast<const float4*>(&tris[e & a.map_tag_mask].pa))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < kPlaneBatch; j++) {
-                const int i = i0 + j * kThreads;
-                if (i >= n) continue;
-                const float fu = (float)(x0 + i);
-                const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl[j].x, fu), __fmul_rn(pl[j].y, fv)), pl[j].z);
-                const int d_plane = __float2int_rz(fminf(fmaxf(dp, (float)-kPlaneBias), (float)(2 * kPlaneBias)));
-                const int valid = __float_as_int(pl[j].w) != 0;
-                row[i] = covered[j] ? (((d_plane + kPlaneBias) << 2) | (valid << 1) | 1) : 0;
-            }
-        }
-    }
-}
-
-// findMatch (elas.cpp:814-955) for the pixels of one image in this row segment
-template <int IMG, int RADIUS, int kThreads, bool SUB>
-__device__ __forceinline__ void match_row(const MatchArgs& a, const RowCtx& r, int p0, int p1, int p2, int p3)
-{
-    const FrameGeom& g = a.g;
     constexpr int step16 = IMG ? 16 : -16;                        // warped column = u + step * d, 16 bytes per column
-    const int radius = RADIUS ? RADIUS : g.plane_radius;
-    float* __restrict__ Drow = a.D[IMG] + (SUB ? (size_t)(r.v >> 1) * g.Dw : (size_t)r.v * g.W);
-    const uint32_t own_base = r.strip[IMG] - 16u * (uint32_t)r.org[IMG];          // + 16*u
-    const uint32_t oth_base = r.strip[1 - IMG] - 16u * (uint32_t)r.org[1 - IMG];  // + 16*u + step16*d
-    const uint32_t tmap = r.tmap + (uint32_t)IMG * a.segw * 4u;
-    const uint32_t lists = r.lists + (uint32_t)IMG * a.max_cells * (kGridListStride * 2);
+    const int radius = RADIUS ? RADIUS : a.g.plane_radius;
+    const uint32_t S = r.row_stride;
+    const uint32_t own_addr = r.strip[IMG] + 16u * (uint32_t)u;
+    const uint32_t oth = r.strip[1 - IMG] + 16u * (uint32_t)u;    // other descriptor at disparity d: oth + step16*d
 
-    for (int i = threadIdx.x; i < r.n; i += kThreads) {
-        const int u = r.x0 + i;
-        if (SUB && ((u & 1) || (u >> 1) >= g.Dw)) continue;                // elas.cpp:1079
-        const int e = lds_s32(tmap + 4u * i);                              // packed by plane_pass()
-        float out = (float)kInvalid;                                       // elas.cpp:977-980
-        if ((e & 1) && u >= 2 && u < g.W - 2) {                            // covered by a triangle; elas.cpp:828
-            const uint4 own = lds128(own_base + 16u * u);
-            const uint4 mid = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-            if (sad16_chain(own, mid) >= a.match_texture) {                // elas.cpp:851-859
-                const bool valid = (e & 2) != 0;
-                const int d_plane = (e >> 2) - kPlaneBias;
-                const int dlo = max(d_plane - radius, 0);
-                const int dhi = min(d_plane + radius, a.disp_max);
-                const uint32_t oth = oth_base + 16u * u;                   // other descriptor at disparity d: oth + step16*d
-                // the warped column stays inside [2, W-2) and d inside [0, disp_max]  <=>  0 <= d <= hi_ok
-                const int hi_ok = min(a.disp_max, IMG ? g.W - 3 - u : u - 2);
+    outA = outB = (float)kInvalid;                                             // elas.cpp:977-980
+    if (!__any_sync(0xffffffffu, (pkA | pkB) & 1)) return;                     // warp-uniform: nothing covered here
+    const uint4 mid = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    const uint4 ownA = lds128(own_addr);
+    const uint4 ownB = NPX == 2 ? lds128(own_addr + S) : ownA;
+    const bool actA = (pkA & 1) && sad16_from(ownA, mid, 0) >= a.match_texture;             // elas.cpp:851-859
+    const bool actB = NPX == 2 && (pkB & 1) && sad16_from(ownB, mid, 0) >= a.match_texture;
 
-                int best = kInitKey;                                       // elas.cpp:878-879
-                // (i) grid candidates outside the plane window, ascending (elas.cpp:890-903, :919-932)
-                const int c = (int)__umulhi((uint32_t)u, a.grid_magic) - r.c0;        // u / grid_size - c0
-                const uint32_t list = lists + (uint32_t)c * (kGridListStride * 2);
-                const int cnt = lds_u16(list);
-                int wide = -1;
-                if (cnt != 0xFFFF) {
-                    const unsigned span = dhi >= dlo ? (unsigned)(dhi - dlo) : 0u;
-                    const int wlo = dhi >= dlo ? dlo : -1 - a.disp_max;    // empty window: nothing matches
-                    // two entries per trip; the entry after the last is a sentinel (disp_max + 1 > hi_ok)
+    // the warped column stays inside [2, W-2) and d inside [0, disp_max]  <=>  0 <= d <= hi_ok
+    const int hi_ok = min(a.disp_max, IMG ? a.g.W - 3 - u : u - 2);
+    const int dpA = (pkA >> 2) - kPlaneBias, dpB = (pkB >> 2) - kPlaneBias;
+
+    // (i) the grid cell's candidate list (elas.cpp:890-903, :919-932), plain SAD, both pixels per entry
+    const uint32_t list = r.lists + (__umulhi((uint32_t)u, a.grid_magic) + (uint32_t)(IMG * a.max_cells)) * (kGridListStride * 2);
+    const int cnt_raw = lds_u16(list);
+    const bool wide = cnt_raw == 0xFFFF;
+    const int cnt = (actA || actB) && !wide ? cnt_raw : 0;
+    int bestA = kInitKey, bestB = kInitKey;
+    if (warp_range_safe) {
 #pragma unroll 1
-                    for (int k = 1; k <= cnt; k += 2) {
-                        const int da = lds_u16(list + 2u * k), db = lds_u16(list + 2u * k + 2u);
-                        const int va = sad16_chain(own, lds128(oth + step16 * da));
-                        const int vb = sad16_chain(own, lds128(oth + step16 * db));
-                        const bool bad_a = (da > hi_ok) | ((unsigned)(da - wlo) <= span);
-                        const bool bad_b = (db > hi_ok) | ((unsigned)(db - wlo) <= span);
-                        const int ka = bad_a ? kInitKey : va * 256 + k;
-                        const int kb = bad_b ? kInitKey : vb * 256 + k + 1;
-                        best = min(best, min(ka, kb));
-                    }
-                } else {
-                    wide = scan_cell_bitmask(a.grid[IMG] + ((size_t)r.gy * g.gw + r.c0 + c) * g.gwords, g.gwords,
-                                             dlo, dhi, hi_ok, own, oth, step16);
-                }
-                // (ii) the plane window with the prior (elas.cpp:904-913, :934-943)
-                if (RADIUS) {
-                    // taps d_plane-R .. d_plane+R sit at consecutive addresses; a d_plane far outside
-                    // [0, disp_max] is clamped for addressing only (every tap is then disqualified)
-                    const int dc = min(max(d_plane, RADIUS - kPad), a.disp_max + kPad - RADIUS);
-                    const uint32_t wbase = oth + step16 * dc;
-                    const int pr0 = valid ? p0 : 0, pr1 = valid ? p1 : 0, pr2 = valid ? p2 : 0, pr3 = valid ? p3 : 0;
-#define ELASB_TAP(K, PRIOR)                                                                                   \
-                    {                                                                                          \
-                        const int val = sad16_chain(own, lds128_off<step16 * (K)>(wbase)) + (PRIOR);           \
-                        const int key = (unsigned)(d_plane + (K)) > (unsigned)hi_ok ? kInitKey                 \
-                                                                                    : val * 256 + (64 + (K) + RADIUS); \
-                        best = min(best, key);                                                                 \
-                    }
-                    if (RADIUS >= 3) ELASB_TAP(-3, pr3)
-                    ELASB_TAP(-2, pr2) ELASB_TAP(-1, pr1) ELASB_TAP(0, pr0) ELASB_TAP(1, pr1) ELASB_TAP(2, pr2)
-                    if (RADIUS >= 3) ELASB_TAP(3, pr3)
-#undef ELASB_TAP
-                } else {
-                    for (int d = dlo; d <= dhi; d++) {
-                        const int val = sad16_chain(own, lds128(oth + step16 * d)) + (valid ? __ldg(a.prior + abs(d - d_plane)) : 0);
-                        const int key = d > hi_ok ? kInitKey : val * 256 + (64 + d - (d_plane - radius));
-                        best = min(best, key);
-                    }
-                }
-                // decode: evaluation order -> disparity
-                int min_d = -1;
-                if (best < kInitKey) {
-                    const int ord = best & 255;
-                    min_d = ord < 64 ? lds_u16(list + 2u * ord) : d_plane - radius + (ord - 64);
-                }
-                if (wide >= 0) {
+        for (int k = 1; k <= cnt; k++) {
+            const uint32_t at = oth + step16 * lds_u16(list + 2u * k);
+            bestA = min(bestA, sad16_from(ownA, lds128(at), 0) * 256 + k);
+            if (NPX == 2) bestB = min(bestB, sad16_from(ownB, lds128(at + S), 0) * 256 + k);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 1; k <= cnt; k++) {
+            const int d = lds_u16(list + 2u * k);
+            const uint32_t at = oth + step16 * d;
+            const int kk = d > hi_ok ? kInitKey : k;                         // disqualified: the key lands at or above kInitKey
+            bestA = min(bestA, sad16_from(ownA, lds128(at), 0) * 256 + kk);
+            if (NPX == 2) bestB = min(bestB, sad16_from(ownB, lds128(at + S), 0) * 256 + kk);
+        }
+    }
+
+    // (ii) the plane windows with the prior (elas.cpp:904-913, :934-943)
+    int winA = kInitKey, winB = kInitKey;
+    if (RADIUS) {
+        // all taps of the warp's active pixels inside [0, hi_ok]: no per-tap test
+        const bool tapsA = !actA || (dpA >= RADIUS && dpA + RADIUS <= hi_ok);
+        const bool tapsB = !actB || (dpB >= RADIUS && dpB + RADIUS <= hi_ok);
+        const int mA = (pkA & 2) ? -1 : 0, mB = (pkB & 2) ? -1 : 0;           // triangle valid: prior applies (elas.cpp:1072)
+        // taps are addressed around a centre clamped into the padded strip (an inactive pixel, or a d_plane
+        // far outside [0, disp_max], computes harmless taps that are all disqualified)
+        const int dcA = min(max(dpA, RADIUS - kPad), a.disp_max + kPad - RADIUS);
+        const int dcB = min(max(dpB, RADIUS - kPad), a.disp_max + kPad - RADIUS);
+        const uint32_t wA = oth + step16 * dcA, wB = oth + S + step16 * dcB;
+        if (__all_sync(0xffffffffu, tapsA && tapsB)) {
+            winA = window_taps<IMG, RADIUS, false>(ownA, wA, dpA, hi_ok, p0 & mA, p1 & mA, p2 & mA, p3 & mA);
+            if (NPX == 2) winB = window_taps<IMG, RADIUS, false>(ownB, wB, dpB, hi_ok, p0 & mB, p1 & mB, p2 & mB, p3 & mB);
+        } else {
+            winA = window_taps<IMG, RADIUS, true>(ownA, wA, dcA == dpA ? dpA : -64, hi_ok, p0 & mA, p1 & mA, p2 & mA, p3 & mA);
+            if (NPX == 2) winB = window_taps<IMG, RADIUS, true>(ownB, wB, dcB == dpB ? dpB : -64, hi_ok, p0 & mB, p1 & mB, p2 & mB, p3 & mB);
+        }
+    }
+
+    // (iii) per pixel: overall minimum, the exactness test of the header, decode evaluation order -> disparity
+#pragma unroll
+    for (int px = 0; px < NPX; px++) {
+        const bool act = px ? actB : actA;
+        const int d_plane = px ? dpB : dpA;
+        int bl = px ? bestB : bestA;
+        int bw = px ? winB : winA;
+        const int wlo = d_plane - radius;
+        if (!RADIUS || wide) {
+            // generic plane radius / a cell with more candidates than a list holds: rare, per pixel
+            if (act) {
+                const uint4 own = px ? ownB : ownA;
+                const uint32_t othp = px ? oth + S : oth;
+                const int dlo = max(wlo, 0), dhi = min(d_plane + radius, a.disp_max);
+                if (!RADIUS) bw = window_generic<IMG>(a.b.prior, own, othp, d_plane, radius, dlo, dhi, hi_ok, ((px ? pkB : pkA) & 2) != 0);
+                if (wide) {
+                    const int cell = (int)__umulhi((uint32_t)u, a.grid_magic);
+                    const int v = (int)(a.b.rows_per_cta * blockIdx.y) + px;
+                    const uint32_t* bits = a.b.grid[IMG] + (size_t)blockIdx.z * a.b.grid_stride + ((size_t)(v / a.grid_size) * a.g.gw + cell) * a.g.gwords;
+                    const int wide_res = scan_cell_bitmask(bits, a.g.gwords, dlo, dhi, hi_ok, own, othp, step16);
                     // the bitmask path ran first in evaluation order: it wins ties
-                    const int wval = wide >> 16, wd = wide & 0xFFFF;
-                    if (min_d < 0 || wval <= (best >> 8)) min_d = wd;
+                    int min_d = bw < kInitKey ? wlo + (bw & 255) - 64 : -1;
+                    if (wide_res >= 0 && (min_d < 0 || (wide_res >> 16) <= (bw >> 8))) min_d = wide_res & 0xFFFF;
+                    (px ? outB : outA) = min_d >= 0 ? (float)min_d : -1.0f;
+                    continue;
                 }
-                out = min_d >= 0 ? (float)min_d : -1.0f;                   // elas.cpp:947-954
             }
         }
-        Drow[SUB ? (u >> 1) : u] = out;
+        // the minimum is a list entry: exact unless it lies inside the plane window
+        int d_list = lds_u16(list + 2u * (uint32_t)(bl & 255));              // position 255 (nothing found) is never used below
+        if (bl < bw && (unsigned)(d_list - max(wlo, 0)) <= (unsigned)(min(d_plane + radius, a.disp_max) - max(wlo, 0)) &&
+            min(d_plane + radius, a.disp_max) >= max(wlo, 0)) {
+            bl = exact_list_pass(list, cnt, px ? ownB : ownA, px ? oth + S : oth, step16, max(wlo, 0),
+                                 min(d_plane + radius, a.disp_max), hi_ok);
+            d_list = lds_u16(list + 2u * (uint32_t)(bl & 255));
+        }
+        const int best = min(bl, bw);
+        const int min_d = best >= kInitKey ? -1 : (best & 255) < 64 ? d_list : wlo + (best & 255) - 64;   // elas.cpp:947-954
+        if (act) (px ? outB : outA) = (float)min_d;
     }
 }
 
-template <int RADIUS, int kThreads, bool SUB>     // plane_radius (elas.cpp:993); 0 = generic
-__global__ void __launch_bounds__(kThreads)
+// ROWS = image rows per CTA: 2 = a thread matches (u, v0) and (u, v0+1) together (needs an even grid_size:
+// both lie in one grid cell); 1 = one row per CTA (odd grid sizes; subsampling, where only even rows exist)
+template <int RADIUS, int ROWS, bool SUB>     // plane_radius (elas.cpp:993); 0 = generic
+__global__ void __launch_bounds__(kThreads, 4)
 k_matching(const __grid_constant__ MatchArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
     const FrameGeom& g = a.g;
-    const int v = blockIdx.y;
-    if (SUB && ((v & 1) || (v >> 1) >= g.Dh)) return;                     // elas.cpp:1085
-    const int x0 = blockIdx.x * a.segw, x1 = min(x0 + a.segw, g.W);
+    const MatchBuffers& b = a.b;
+    const int z = blockIdx.z;
+    const int v0 = SUB ? 2 * blockIdx.y : ROWS * blockIdx.y;              // elas.cpp:1085: only even rows when subsampling
+    if (SUB && (v0 >> 1) >= g.Dh) return;
+    const bool rowB = ROWS == 2 && v0 + 1 < g.H;
+    const int x0 = blockIdx.x * kSegW, x1 = min(x0 + kSegW, g.W);
     // strip 0 holds desc1 columns from x0 - kPad, strip 1 holds desc2 columns from x0 - disp_max - kPad,
-    // cap = segw + disp_max + 2*kPad entries each; only the part inside the image is copied, the rest
-    // is addressable garbage that is never selected (its candidates are disqualified)
-    const int cap = a.segw + a.disp_max + 2 * kPad;
-    uint4* strip0 = reinterpret_cast<uint4*>(smem_raw);
-    uint4* strip1 = strip0 + cap;
-    uint16_t* lists = reinterpret_cast<uint16_t*>(strip1 + cap);           // [2][max_cells][kGridListStride]
-    int32_t* tmap = reinterpret_cast<int32_t*>(lists + 2 * a.max_cells * kGridListStride);   // [2][segw]
-    RowCtx r;
-    r.org[0] = x0 - kPad; r.org[1] = x0 - a.disp_max - kPad;
-    r.strip[0] = smem_u32(strip0); r.strip[1] = smem_u32(strip1);
-    r.lists = smem_u32(lists); r.tmap = smem_u32(tmap);
-    r.x0 = x0; r.n = x1 - x0; r.v = v;
-    r.gy = v / a.grid_size;                                                // elas.cpp:867
-    r.c0 = x0 / a.grid_size;
-    const int ncell = (x1 - 1) / a.grid_size - r.c0 + 1;
+    // cap = kSegW + disp_max + 2*kPad entries per row; only the part inside the image is copied, the rest
+    // is addressable garbage that is never selected (loops that could reach it test the range)
+    const int cap = kSegW + a.disp_max + 2 * kPad;
+    const uint32_t row_stride = (uint32_t)cap * 16u;
+    const uint32_t strip0 = smem_u32(smem_raw), strip1 = strip0 + ROWS * row_stride;
+    const uint32_t lists = strip1 + ROWS * row_stride;                     // [2][max_cells][kGridListStride]
+    const int org0 = x0 - kPad, org1 = x0 - a.disp_max - kPad;
+    const int gy = (int)__umulhi((uint32_t)v0, a.grid_magic);              // v0 / grid_size, elas.cpp:867
+    const int c0 = (int)__umulhi((uint32_t)x0, a.grid_magic);
+    const int ncell = (int)__umulhi((uint32_t)(x1 - 1), a.grid_magic) - c0 + 1;
 
-    const int vrow = max(min(v, g.H - 3), 2);                              // elas.cpp:834
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        // six TMA bulk copies on one mbarrier: two descriptor strips, two runs of candidate lists, two
-        // triangle-id row segments
+        // TMA bulk copies on one mbarrier: per row the desc1 strip [x0, x1+disp_max) and the desc2 strip
+        // [x0-disp_max, x1), and the two runs of candidate lists.  Descriptor rows outside [3, H-3) are all
+        // zero (k_descriptor.cu), so the reference's row clamp max(min(v, H-3), 2) (elas.cpp:834) reads the
+        // same bytes as row v itself.
         const int s0hi = min(x1 + a.disp_max, g.W), s1lo = max(x0 - a.disp_max, 0);
         const uint32_t b0 = (uint32_t)(s0hi - x0) * 16u, b1 = (uint32_t)(x1 - s1lo) * 16u;
         const uint32_t bl = (uint32_t)ncell * kGridListStride * 2u;
-        const uint32_t bm = (uint32_t)((r.n + 3) & ~3) * 4u;
-        mbar_expect_tx(&bar, b0 + b1 + 2 * bl + 2 * bm);
-        // the triangle-id rows first: the plane gather below starts from them
-        tma_bulk_g2s(tmap, a.map[0] + (size_t)v * a.map_pitch + x0, bm, &bar);
-        tma_bulk_g2s(tmap + a.segw, a.map[1] + (size_t)v * a.map_pitch + x0, bm, &bar);
-        tma_bulk_g2s(strip0 + kPad, a.desc[0] + (size_t)vrow * g.W + x0, b0, &bar);
-        tma_bulk_g2s(strip1 + (s1lo - r.org[1]), a.desc[1] + (size_t)vrow * g.W + s1lo, b1, &bar);
-        const size_t cell0 = ((size_t)r.gy * g.gw + r.c0) * kGridListStride;
-        tma_bulk_g2s(lists, a.lists[0] + cell0, bl, &bar);
-        tma_bulk_g2s(lists + a.max_cells * kGridListStride, a.lists[1] + cell0, bl, &bar);
+        mbar_expect_tx(&bar, (rowB ? 2u : 1u) * (b0 + b1) + 2 * bl);
+        const uint4* d1 = b.desc[0] + (size_t)z * b.desc_stride + (size_t)v0 * g.W;
+        const uint4* d2 = b.desc[1] + (size_t)z * b.desc_stride + (size_t)v0 * g.W;
+        tma_bulk_g2s(strip0 + kPad * 16u, d1 + x0, b0, &bar);
+        tma_bulk_g2s(strip1 + (uint32_t)(s1lo - org1) * 16u, d2 + s1lo, b1, &bar);
+        if (rowB) {
+            tma_bulk_g2s(strip0 + row_stride + kPad * 16u, d1 + g.W + x0, b0, &bar);
+            tma_bulk_g2s(strip1 + row_stride + (uint32_t)(s1lo - org1) * 16u, d2 + g.W + s1lo, b1, &bar);
+        }
+        const size_t cell0 = ((size_t)gy * g.gw + c0) * kGridListStride;
+        tma_bulk_g2s(lists, b.lists[0] + (size_t)z * b.lists_stride + cell0, bl, &bar);
+        tma_bulk_g2s(lists + (uint32_t)a.max_cells * kGridListStride * 2u, b.lists[1] + (size_t)z * b.lists_stride + cell0, bl, &bar);
+    }
+
+    // while the copies fly: this thread's four triangle-id entries -> planes -> packed (d_plane, valid, covered)
+    const int u = x0 + threadIdx.x;
+    // columns that are matched at all: inside the segment, inside [2, W-2) (elas.cpp:828), even when subsampling (:1079)
+    const bool col = u < x1 && u >= 2 && u < g.W - 2 && !(SUB && ((u & 1) || (u >> 1) >= g.Dw));
+    int pk[2][2] = {{0, 0}, {0, 0}};
+    {
+        // 32-bit element indices from the group's base pointers (a group's arrays stay far below 2^31 elements)
+        const uint32_t mrow = (uint32_t)z * (uint32_t)b.map_stride + (uint32_t)v0 * (uint32_t)a.map_pitch + (uint32_t)u;
+        const uint32_t tbase = (uint32_t)z * (uint32_t)b.tri_stride;
+        int e[2][2];
+        float4 pl[2][2];
+#pragma unroll
+        for (int row = 0; row < ROWS; row++) {
+            const bool on = col && (row == 0 || rowB);
+            e[0][row] = on ? __ldg(b.map[0] + (mrow + row * a.map_pitch)) : -1;
+            e[1][row] = on ? __ldg(b.map[1] + (mrow + row * a.map_pitch)) : -1;
+        }
+#pragma unroll
+        for (int img = 0; img < 2; img++)
+#pragma unroll
+            for (int row = 0; row < ROWS; row++) {
+                // stale entries = other frames = uncovered
+                const bool covered = (e[img][row] & ~a.map_tag_mask) == a.map_tag_bits;
+                e[img][row] = covered ? (int)(tbase + (uint32_t)(e[img][row] & a.map_tag_mask)) : -1;
+                pl[img][row] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (covered) pl[img][row] = __ldg(reinterpret_cast<const float4*>(&b.tri[img][(uint32_t)e[img][row]].pa));
+            }
+        const float fu = (float)u;
+#pragma unroll
+        for (int img = 0; img < 2; img++)
+#pragma unroll
+            for (int row = 0; row < ROWS; row++)
+                pk[img][row] = pack_plane(pl[img][row], e[img][row] >= 0, fu, (float)(v0 + row));
     }
     // prior of the plane window offsets 0..3 (elas.cpp:984-992), in registers
-    const int p0 = __ldg(a.prior), p1 = g.dn > 1 ? __ldg(a.prior + 1) : 0, p2 = g.dn > 2 ? __ldg(a.prior + 2) : 0,
-              p3 = g.dn > 3 ? __ldg(a.prior + 3) : 0;
+    const int p0 = __ldg(b.prior), p1 = g.dn > 1 ? __ldg(b.prior + 1) : 0, p2 = g.dn > 2 ? __ldg(b.prior + 2) : 0,
+              p3 = g.dn > 3 ? __ldg(b.prior + 3) : 0;
+    // warp-uniform: every column of this warp keeps every disparity's warped column inside [2, W-2)
+    const int uw0 = x0 + (threadIdx.x & ~31), uw1 = uw0 + 31;
+    const bool safe0 = uw0 - 2 >= a.disp_max, safe1 = g.W - 3 - uw1 >= a.disp_max;
+    SegCtx r;
+    r.row_stride = row_stride;
+    r.strip[0] = strip0 - 16u * (uint32_t)org0;          // wraps modulo 2^32; + 16*column lands inside the strip
+    r.strip[1] = strip1 - 16u * (uint32_t)org1;
+    r.lists = lists - (uint32_t)c0 * (kGridListStride * 2);
+
     mbar_wait(&bar, 0);
-    plane_pass<kThreads>(a, tmap, r.n, x0, v);
-    match_row<0, RADIUS, kThreads, SUB>(a, r, p0, p1, p2, p3);
-    match_row<1, RADIUS, kThreads, SUB>(a, r, p0, p1, p2, p3);
+    float o[2][2];
+    match_pair<0, RADIUS, ROWS>(a, r, u, pk[0][0], pk[0][1], safe0, p0, p1, p2, p3, o[0][0], o[0][1]);
+    match_pair<1, RADIUS, ROWS>(a, r, u, pk[1][0], pk[1][1], safe1, p0, p1, p2, p3, o[1][0], o[1][1]);
+    if (u >= x1 || (SUB && ((u & 1) || (u >> 1) >= g.Dw))) return;
+    const uint32_t at = SUB ? (uint32_t)(v0 >> 1) * g.Dw + (u >> 1) : (uint32_t)v0 * g.W + u;
+#pragma unroll
+    for (int img = 0; img < 2; img++) {
+        float* __restrict__ D = b.D[img] + (size_t)z * b.D_stride + at;
+        D[0] = o[img][0];
+        if (ROWS == 2 && rowB) D[g.W] = o[img][1];
+    }
 }
 
-template <int RADIUS, int THREADS, bool SUB>
-void launch_sub(dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
+int max_cells_per_segment(int grid_size) { return (kSegW + grid_size - 1) / grid_size + 1; }
+
+size_t smem_bytes_for(const FrameGeom& g, int grid_size, int rows)
+{
+    const int dmax = g.dn - 1;
+    // + 512: a thread without any candidate decodes list position 255 of its cell (value unused)
+    return 2 * (size_t)rows * (kSegW + dmax + 2 * kPad) * 16 + 2 * (size_t)max_cells_per_segment(grid_size) * kGridListStride * 2 + 512;
+}
+
+template <int RADIUS, int ROWS, bool SUB>
+void launch_inst(dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
 {
     static unsigned long long optin = 0;
-    if (ensure_dynamic_smem(k_matching<RADIUS, THREADS, SUB>, 200 * 1024, &optin) != cudaSuccess) return;   // launch error stays pending
-    k_matching<RADIUS, THREADS, SUB><<<grid, THREADS, smem, s>>>(a);
+    if (ensure_dynamic_smem(k_matching<RADIUS, ROWS, SUB>, 200 * 1024, &optin) != cudaSuccess) return;   // the error stays pending
+    k_matching<RADIUS, ROWS, SUB><<<grid, kThreads, smem, s>>>(a);
 }
 
-template <int RADIUS, int THREADS>
-void launch_one(dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
+template <int RADIUS>
+void launch_radius(int rows, bool sub, dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
 {
-    if (a.subsampling) launch_sub<RADIUS, THREADS, true>(grid, smem, s, a);
-    else               launch_sub<RADIUS, THREADS, false>(grid, smem, s, a);
+    if (sub)            launch_inst<RADIUS, 1, true>(grid, smem, s, a);
+    else if (rows == 2) launch_inst<RADIUS, 2, false>(grid, smem, s, a);
+    else                launch_inst<RADIUS, 1, false>(grid, smem, s, a);
 }
 
-template <int THREADS>
-void launch_radius(int radius, dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
-{
-    if (radius == 2)      launch_one<2, THREADS>(grid, smem, s, a);      // ROBOTICS
-    else if (radius == 3) launch_one<3, THREADS>(grid, smem, s, a);      // MIDDLEBURY
-    else                  launch_one<0, THREADS>(grid, smem, s, a);
-}
-
-void launch_variant(int radius, int threads, dim3 grid, size_t smem, cudaStream_t s, const MatchArgs& a)
-{
-    if (threads == 256)      launch_radius<256>(radius, grid, smem, s, a);
-    else if (threads == 64)  launch_radius<64>(radius, grid, smem, s, a);
-    else                     launch_radius<128>(radius, grid, smem, s, a);
-}
-
-int max_cells_per_segment(const FrameGeom& g, int grid_size, int segw) { return (segw + grid_size - 1) / grid_size + 1; }
-
-size_t smem_bytes_for(const FrameGeom& g, int grid_size)
-{
-    const SegPlan s = plan_segments(g.W);
-    const int dmax = g.dn - 1;
-    const size_t strip = (size_t)((s.segw + dmax) < g.W ? (s.segw + dmax) : g.W);
-    const size_t cells = (size_t)max_cells_per_segment(g, grid_size, s.segw);
-    (void)strip;
-    return 2 * (size_t)(s.segw + dmax + 2 * kPad) * 16 + 2 * cells * kGridListStride * 2 + 2 * (size_t)s.segw * 4;
-}
+// two rows per CTA needs both rows of a pair in one grid-cell row
+int rows_per_cta(const elas_b200_params& p) { return (!p.subsampling && p.grid_size % 2 == 0) ? 2 : 1; }
 
 }  // namespace
 
-size_t matching_smem_bytes(const FrameGeom& g, int grid_size) { return smem_bytes_for(g, grid_size); }
+size_t matching_smem_bytes(const FrameGeom& g, const elas_b200_params& p) { return smem_bytes_for(g, p.grid_size, rows_per_cta(p)); }
 
-void launch_matching(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
-                     const uint4* desc2, const TriRaster* tri1, const TriRaster* tri2,
-                     const int32_t* map1, const int32_t* map2, const uint32_t* grid1,
-                     const uint32_t* grid2, const uint16_t* lists1, const uint16_t* lists2,
-                     const int32_t* prior, float* D1, float* D2, int map_tag_bits, int map_tag_shift,
-                     cudaStream_t s)
+void launch_matching(const FrameGeom& g, const elas_b200_params& p, const MatchBuffers& b, int n_frames,
+                     int map_tag_bits, int map_tag_shift, cudaStream_t s)
 {
-    const SegPlan sp = plan_segments(g.W);
     MatchArgs a;
     a.g = g;
     a.disp_max = p.disp_max; a.match_texture = p.match_texture; a.grid_size = p.grid_size;
-    a.subsampling = p.subsampling;
-    a.segw = sp.segw;
-    a.max_cells = max_cells_per_segment(g, p.grid_size, sp.segw);
+    a.max_cells = max_cells_per_segment(p.grid_size);
     a.map_pitch = map_pitch(g);
     a.map_tag_bits = map_tag_bits;
     a.map_tag_mask = (1 << map_tag_shift) - 1;
-    static const int variant = env_int("ELAS_B200_K7_VARIANT", 1);
-    a.variant = variant;
     a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;
-    a.desc[0] = desc1; a.desc[1] = desc2;
-    a.tri[0] = tri1; a.tri[1] = tri2;
-    a.map[0] = map1; a.map[1] = map2;
-    a.grid[0] = grid1; a.grid[1] = grid2;
-    a.lists[0] = lists1; a.lists[1] = lists2;
-    a.prior = prior;
-    a.D[0] = D1; a.D[1] = D2;
-    dim3 grid(sp.nseg, g.H, 1);
-    const size_t smem = smem_bytes_for(g, p.grid_size);
-    static const int threads = env_int("ELAS_B200_K7_THREADS", 128);
-    launch_variant(g.plane_radius, threads, grid, smem, s, a);
+    a.b = b;
+    const int rows = rows_per_cta(p);
+    a.b.rows_per_cta = p.subsampling ? 2 : rows;
+    const int items = p.subsampling ? (g.H + 1) / 2 : (g.H + rows - 1) / rows;
+    dim3 grid((g.W + kSegW - 1) / kSegW, items, n_frames);
+    const size_t smem = smem_bytes_for(g, p.grid_size, rows);
+    if (g.plane_radius == 2)      launch_radius<2>(rows, p.subsampling != 0, grid, smem, s, a);      // ROBOTICS
+    else if (g.plane_radius == 3) launch_radius<3>(rows, p.subsampling != 0, grid, smem, s, a);      // MIDDLEBURY
+    else                          launch_radius<0>(rows, p.subsampling != 0, grid, smem, s, a);
     count_launch();
 }
 
