@@ -98,6 +98,18 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
  * (e.g. 2x) and the GPU stays fed while every worker runs host stages. */
 int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
                             int32_t width, int32_t height, int32_t n_slots, int32_t n_workers);
+/* Frame groups: a context owns n_groups groups of frames_per_group frames each (at most 8; 0 = chosen from the
+ * frame size).  The frames of a group share one chain of kernel launches -- every kernel takes the frame as a
+ * grid dimension -- so small frames still fill the GPU and the launch cost per frame shrinks.  The whole path of
+ * a frame runs on the device (for the parameter sets the device mesh stage covers, which include both presets'
+ * ROBOTICS family; others use the host stage of section 3), so n_workers host threads only enqueue chains and
+ * collect results.  elas_b200_create[_ex] = groups of one frame ("slots"). */
+int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                                 int32_t width, int32_t height, int32_t n_groups, int32_t frames_per_group,
+                                 int32_t n_workers);
+int32_t elas_b200_frames_per_group(elas_b200_ctx* ctx);
+/* 1 when lattice filters and Delaunay triangulation run on the GPU for this context, 0 when they use the host stage */
+int32_t elas_b200_mesh_on_device(elas_b200_ctx* ctx);
 void    elas_b200_destroy(elas_b200_ctx* ctx);
 
 /* One frame through one slot, synchronous, host buffers (same contract as elas_b200_process). */
@@ -192,7 +204,8 @@ int32_t elas_b200_stage_times(elas_b200_ctx* ctx, int32_t slot,
                               const char** names_out, float* ms_out, int32_t cap);
 
 /* Host-side wall time spent per frame phase, summed over all frames since the last reset, in
- * milliseconds: {submit phase A, wait phase A, host stage, submit phase B, wait phase B}. */
+ * milliseconds: {enqueueing launch chains, waiting for results, host stage (contexts that use it), collecting
+ * results incl. widening D2, 0}. */
 int32_t elas_b200_host_times(elas_b200_ctx* ctx, double ms_out[5], int64_t* frames, int32_t reset);
 
 /* Bench hook: runs only the dense matching kernel (left+right, elas.cpp:960-1118) `iters` times
@@ -200,6 +213,9 @@ int32_t elas_b200_host_times(elas_b200_ctx* ctx, double ms_out[5], int64_t* fram
  * (CUDA events on the slot's stream; flush_l2 != 0 rewrites a >L2-sized buffer between
  * launches, outside the timed span).  Negative on error. */
 float   elas_b200_time_matching(elas_b200_ctx* ctx, int32_t slot, int32_t iters, int32_t flush_l2);
+/* Same; *frames_per_launch receives the number of frames one launch processes (the group's last chain). */
+float   elas_b200_time_matching_ex(elas_b200_ctx* ctx, int32_t slot, int32_t iters, int32_t flush_l2,
+                                   int32_t* frames_per_launch);
 
 /* Bench hook for the consumers of D1: runs k_colormap and k_reproject `iters` times each on the left map
  * and image the slot's last frame left on the device (nothing crosses PCIe) and returns the mean

@@ -48,6 +48,22 @@ struct __align__(16) TriRaster {
 };
 static_assert(sizeof(TriRaster) == 64, "TriRaster is one 64-byte record");
 
+// Per-frame results of the mesh stage, in device memory (kernels downstream size their loops from it) and
+// copied to pinned host memory with the frame's maps (status, statistics).
+struct FrameHeader {
+    int32_t n_support;       // support points (elas.cpp:505-517); < 3: the frame has no triangulation (elas.cpp:69-75)
+    int32_t n_tri[2];        // triangles of the left / right image
+    int32_t n_units[2];      // scan-conversion work units of each image
+    int32_t ovf_from[2];     // triangles [ovf_from, n_tri) did not fit the unit list: one warp scan-converts each on its own
+    int32_t status;          // 0, or an ELAS_B200_E_* code raised on the device
+};
+static_assert(sizeof(FrameHeader) == 32, "FrameHeader is 32 bytes");
+
+// Element strides between consecutive frames of a group (frames batched per launch, blockIdx.z / .y)
+struct GroupStrides {
+    size_t img, desc, dcan, support, tri, units, traster, planes, scratch, grid, lists, map, D, mesh_scratch;
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned sad16(const uint4& a, const uint4& b)
 {
@@ -81,25 +97,40 @@ __device__ __forceinline__ unsigned texture16(const uint4& a)
 __host__ __device__ inline int map_pitch(const FrameGeom& g) { return map_pitch_of(g.W); }
 
 // ---- kernel launchers (one translation unit each) --------------------------------------------
+// Every launcher takes the pointers of FRAME 0 of a frame group, the group's strides and the number of frames
+// batched into the launch (a grid dimension): one launch chain serves up to kMaxGroupFrames frames.
+constexpr int kMaxGroupFrames = 8;
+struct OutTable { float* p[kMaxGroupFrames]; };      // where each frame's finished map goes (group buffer or the caller's)
+OutTable out_table(float* base, size_t stride, int n_frames);
+
 // K1  Sobel + descriptor, both images (filter.cpp:408-416, descriptor.cpp:48-121)
 void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const uint8_t* img2,
-                       uint4* desc1, uint4* desc2, cudaStream_t s);
+                       uint4* desc1, uint4* desc2, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K2  support matching on the candidate lattice, forward + reverse (elas.cpp:322-445, :471-493)
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
-                    const uint4* desc2, int16_t* dcan, cudaStream_t s);
+                    const uint4* desc2, int16_t* dcan, const GroupStrides& st, int n_frames, cudaStream_t s);
+// K3  lattice filters + support list (elas.cpp:174-279, :496-517), one CTA per frame; fills hdr[f].n_support
+bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p);
+void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
+                    int32_t* support, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s);
+// K4  Delaunay triangulation of both images + scan-conversion work units (elas.cpp:534-600, triangle.cpp), one CTA
+//     per frame and image; fills hdr[f].n_tri / n_units / ovf_from
+void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, int32_t* tri2, int32_t* units1, int32_t* units2,
+                     int unit_cap, FrameHeader* hdr, int32_t* scratch, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K5 + K6 scatter: disparity planes + per-triangle raster records (elas.cpp:605-680, :1006-1072) and the
 // support points' d-1..d+1 marks in the candidate-grid scatter planes (elas.cpp:697-727), one launch.
 // scratch = this frame's scatter planes [2][gh*gw][gwords], all zero on entry.
-void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                           const int32_t* tri1, int nt1, const int32_t* tri2, int nt2, TriRaster* out1,
-                           TriRaster* out2, float* planes1, float* planes2, uint32_t* scratch, cudaStream_t s);
+void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const FrameHeader* hdr, const int32_t* support,
+                           const int32_t* tri1, const int32_t* tri2, TriRaster* out1, TriRaster* out2,
+                           float* planes1, float* planes2, uint32_t* scratch, const GroupStrides& st, int n_frames,
+                           cudaStream_t s);
 // K6 diffusion (elas.cpp:732-775) + triangle-id maps by scan conversion with last-writer-wins
-// (elas.cpp:1074-1114), one launch.  scratch_next (the slot's other scatter buffer) is zeroed for the
+// (elas.cpp:1074-1114), one launch.  scratch_next (the group's other scatter buffer) is zeroed for the
 // next frame.  Map entries are tag_bits | triangle index (see k_grid_raster.cu).
-void launch_diffuse_raster(const FrameGeom& g, int subsampling, const uint32_t* scratch, uint32_t* scratch_next,
-                           uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
-                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units, int n_units,
-                           int32_t* map1, int32_t* map2, int tag_bits, cudaStream_t s);
+void launch_diffuse_raster(const FrameGeom& g, int subsampling, const FrameHeader* hdr, const uint32_t* scratch,
+                           uint32_t* scratch_next, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units1, const int32_t* units2,
+                           int32_t* map1, int32_t* map2, int tag_bits, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K7  dense matching, both images (elas.cpp:814-955, :960-1118), n_frames frames per launch (blockIdx.z):
 // every pointer addresses frame 0 of a group, *_stride = elements between consecutive frames
 struct MatchBuffers {
@@ -117,28 +148,30 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const MatchB
                      int map_tag_bits, int map_tag_shift, cudaStream_t s);
 size_t matching_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
 size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
-// K8  left/right consistency (elas.cpp:1122-1204)
+// K8  left/right consistency (elas.cpp:1122-1204); O2 = per-frame destination of the checked right map
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                     float* O1, float* O2, cudaStream_t s);
+                     float* O1, const OutTable& O2, size_t D_stride, int n_frames, cudaStream_t s);
 // K9  speckle removal (elas.cpp:1208-1326)
 // apply = false: stop after the component sizes are known; launch_post_fused then applies them
 void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, cudaStream_t s, bool apply = true, bool rows_done = false);
+                     int32_t* size, size_t D_stride, int n_frames, cudaStream_t s, bool apply = true, bool rows_done = false);
 // K8 + K9's row step for D1 in one kernel (rows staged in shared memory)
 bool lr_rows_fusable(const FrameGeom& g);
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, float* O2, int32_t* parent, int32_t* size, int16_t* O2_i16, cudaStream_t s);
+                    float* O1, const OutTable& O2, int32_t* parent, int32_t* size, int16_t* O2_i16, size_t D_stride,
+                    int n_frames, cudaStream_t s);
 // K9 apply + K10 + K11 in one tiled kernel (ipol_gap_width <= 3, no add_corners); out must not alias in
 bool post_fusable(const elas_b200_params& p);
 void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
-                       const int32_t* size, float* out, float* dump_seg, float* dump_gap, cudaStream_t s);
-// K10 gap interpolation (elas.cpp:1330-1530)
-void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, cudaStream_t s);
-// K11 adaptive mean (elas.cpp:1535-1754)
-void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp,
-                          cudaStream_t s);
-// K12 median (elas.cpp:1758-1838)
-void launch_median(const FrameGeom& g, float* D, float* tmp, cudaStream_t s);
+                       const int32_t* size, const OutTable& out, float* dump_seg, float* dump_gap, size_t D_stride,
+                       int n_frames, cudaStream_t s);
+// K10 gap interpolation (elas.cpp:1330-1530), K11 adaptive mean (elas.cpp:1535-1754), K12 median (elas.cpp:1758-1838):
+// in place on D with one scratch plane per frame
+void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, size_t D_stride, size_t tmp_stride,
+                int n_frames, cudaStream_t s);
+void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, size_t D_stride,
+                          size_t tmp_stride, int n_frames, cudaStream_t s);
+void launch_median(const FrameGeom& g, float* D, float* tmp, size_t D_stride, size_t tmp_stride, int n_frames, cudaStream_t s);
 
 // D1's consumers in StereoThread: colour map (stereothread.cpp:116-147), back-projection (:180-255)
 void launch_colormap(int n, const float* D1, float* out, cudaStream_t s);

@@ -58,50 +58,63 @@ struct StageTimer {
     std::vector<std::pair<std::string, float>> last;          // (stage, ms)
 };
 
-struct Slot {
+// One frame of a call: the caller's four buffers
+struct FrameIO {
+    const uint8_t* I1; const uint8_t* I2;
+    float* D1; float* D2;
+    int bytes_per_line; bool device_io;
+};
+
+// A frame group: everything up to `cap` frames need, allocated once.  The frames of a group go through ONE
+// launch chain (every kernel takes the frame as a grid dimension), on the group's stream.
+struct Group {
+    int cap = 1;
     cudaStream_t stream = nullptr;
-    // device
+    cudaStream_t copy_stream = nullptr;        // disparity maps go out here
+    cudaEvent_t ev_done = nullptr;             // kernels finished
+    cudaEvent_t ev_out = nullptr;              // the group's maps and headers are in the caller's / pinned buffers
+    // device, [cap] frames each (strides: elas_b200_ctx::st)
     uint8_t* d_img[2] = {nullptr, nullptr};
-    uint8_t* h_img[2] = {nullptr, nullptr};    // pinned staging for images that arrive in pageable host memory
-    int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
-    int16_t* h_D2_i16 = nullptr;               // pinned landing buffer; expanded to float into the caller's D2 by the worker
-    float* expand_D2 = nullptr;                // caller's D2 awaiting expansion at frame_finish (null: nothing to expand)
-    // batch scheduler state (see worker_main)
-    std::atomic<int> busy{0};                  // a worker is looking at / working on this slot
-    int state = 0;                             // 0 idle, 1 phase A in flight, 2 phase B + copy-out in flight
-    int frame = -1;                            // index of the slot's frame in the current batch
-    cudaEvent_t ev_a = nullptr;                // phase A finished
     uint4* d_desc[2] = {nullptr, nullptr};
-    int32_t* d_tables = nullptr;               // [support n x 3 | tri1 t1 x 3 | tri2 t2 x 3], packed, one copy per frame
-    TriRaster* d_tri[2] = {nullptr, nullptr};  // raster records, written by k_planes
-    float* d_planes[2] = {nullptr, nullptr};   // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle, written by k_planes
+    int16_t* d_dcan_raw = nullptr;             // K2's candidate lattice
+    int16_t* d_dcan = nullptr;                 // after the lattice filters
+    int16_t* d_dcan_incon = nullptr;           // after the inconsistency filter (allocated when stages are captured)
+    int32_t* d_support = nullptr;              // (u,v,d) triples
+    int32_t* d_tri[2] = {nullptr, nullptr};    // (c1,c2,c3) triples
+    int32_t* d_units[2] = {nullptr, nullptr};  // scan-conversion work units
+    int32_t* d_mesh_scratch = nullptr;         // k_delaunay working memory beyond shared memory
+    FrameHeader* d_hdr = nullptr;
+    TriRaster* d_traster[2] = {nullptr, nullptr};
+    float* d_planes[2] = {nullptr, nullptr};   // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle
     uint32_t* d_grid_scratch = nullptr;
     uint32_t* d_grid[2] = {nullptr, nullptr};      // candidate grid, bitmask form [gh*gw][gwords]
     uint16_t* d_lists[2] = {nullptr, nullptr};     // candidate grid, list form [gh*gw][kGridListStride]
     int32_t* d_map[2] = {nullptr, nullptr};
-    float* d_raw[2] = {nullptr, nullptr};      // K7 output
+    float* d_raw[2] = {nullptr, nullptr};      // K7 output; plane 0 is reused for the final left map
     float* d_D[2] = {nullptr, nullptr};        // after the L/R check and post-processing
-    float* d_tmp = nullptr;                    // two planes of scratch
+    float* d_tmp = nullptr;                    // two planes of scratch per frame
     int32_t* d_parent = nullptr;
     int32_t* d_size = nullptr;
+    int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
     // pinned host
-    int16_t* h_dcan = nullptr;
-    int32_t* h_tables = nullptr;
-    cudaEvent_t ev_sync = nullptr;             // blocking wait (no spinning) when slots outnumber host cores
-    cudaStream_t copy_stream = nullptr;        // disparity maps go out here while the slot starts its next frame
-    cudaEvent_t ev_done = nullptr;             // phase B kernels finished
-    cudaEvent_t ev_out = nullptr;              // the frame's maps are in the caller's buffers
-    // host stage + tables of the last frame (kept for elas_b200_time_matching)
-    HostStage host;
-    int n_tri[2] = {0, 0};
-    int n_units = 0;
-    size_t units_at = 0;
+    uint8_t* h_img[2] = {nullptr, nullptr};    // staging for images that arrive in pageable host memory
+    int16_t* h_D2_i16 = nullptr;               // landing buffer; widened to float into the caller's D2 by the worker
+    FrameHeader* h_hdr = nullptr;
+    int16_t* h_dcan = nullptr;                 // host-stage path only
+    int32_t* h_tables = nullptr;               // host-stage path only: [support | tri1 | tri2 | units] of one frame
+    HostStage host;                            // host-stage path only
+    // the call in flight
+    int n = 0;                                 // frames in this launch chain
+    int first_frame = -1;                      // index of frame 0 in the batch
+    std::vector<FrameIO> io;
+    std::vector<float*> expand_D2;             // caller's D2 awaiting widening at finish (null: nothing to do)
+    int last_n = 0;                            // frames of the last completed chain (elas_b200_time_matching)
     float* d_view = nullptr;                   // colour map / back-projection outputs (5 planes), allocated on first use
-    float* last_D1 = nullptr;                  // where the last frame's final left map lives on the device
+    float* last_D1 = nullptr;                  // frame 0's final left map of the last chain, if it lives in the group's buffers
     int map_tag = 0;                           // frame tag of the triangle-id map entries (k_grid_raster.cu)
-    int scratch_phase = 0;                     // which of the two grid scatter buffers this frame uses
+    int scratch_phase = 0;                     // which of the two grid scatter buffers this chain uses
     bool tables_valid = false;
-    // introspection
+    // introspection (single-frame calls)
     bool capture = false;
     std::map<std::string, std::vector<uint8_t>> stages;
     StageTimer timer;
@@ -113,22 +126,21 @@ struct elas_b200_ctx {
     int device = 0;
     elas_b200_params p{};
     FrameGeom g{};
+    GroupStrides st{};
     int support_cap = 0, tri_cap = 0, unit_cap = 0;
     int map_tag_shift = 0, map_tag_max = 0;  // map entry = tag << shift | triangle index
+    bool mesh_device = true;                 // lattice filters + Delaunay on the GPU (k_mesh.cu); false: host stage (host_stage.cc)
     int32_t* d_prior = nullptr;
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
     bool timing = false;
-    bool blocking_sync = false;              // wait on a blocking event instead of spinning in cudaStreamSynchronize
-    bool direct_out = false;                 // ELAS_B200_DIRECT_OUT=1: kernels store finished maps straight into pinned host buffers
-                                             // (measured slower end to end than the copy engine: 7.9 k vs 11.4 k pairs/s)
     bool narrow_d2 = true;                   // host output: D2 crosses PCIe as int16 when that is exact (ELAS_B200_NARROW_D2=0 disables)
     long long launches_at_create = 0;
-    // host-side wall time per frame phase, summed over all frames and slots (nanoseconds)
-    std::atomic<long long> ns_submit_a{0}, ns_wait_a{0}, ns_host{0}, ns_submit_b{0}, ns_wait_b{0}, frames{0};
-    std::vector<std::unique_ptr<Slot>> slots;
+    // host-side wall time, summed over all groups (nanoseconds)
+    std::atomic<long long> ns_submit{0}, ns_host{0}, ns_wait{0}, ns_finish{0}, frames{0};
+    std::vector<std::unique_ptr<Group>> groups;
 
-    // worker pool: one thread per slot, fed by process_batch
+    // batch calls: a pool of workers, worker w drives groups w, w + W, w + 2W, ...
     struct Job {
         int n = 0;
         const uint8_t* const* I1 = nullptr; const uint8_t* const* I2 = nullptr;
@@ -143,7 +155,7 @@ struct elas_b200_ctx {
     Job* job = nullptr;
     uint64_t job_seq = 0;
     bool stopping = false;
-    std::mutex batch_mu;                     // one batch at a time
+    std::mutex batch_mu;                     // one call at a time
 };
 
 namespace {
@@ -183,20 +195,18 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
     return P;
 }
 
-void free_slot(Slot& s)
+void free_group(Group& s)
 {
     for (int k = 0; k < 2; k++) {
-        cudaFree(s.d_img[k]); cudaFreeHost(s.h_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
-        cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]);
-        cudaFree(s.d_planes[k]);
+        cudaFree(s.d_img[k]); cudaFreeHost(s.h_img[k]); cudaFree(s.d_desc[k]); cudaFree(s.d_tri[k]); cudaFree(s.d_units[k]);
+        cudaFree(s.d_traster[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
+        cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]); cudaFree(s.d_planes[k]);
     }
-    cudaFree(s.d_tables); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16);
- cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp);
-    cudaFree(s.d_parent); cudaFree(s.d_size);
+    cudaFree(s.d_dcan_raw); cudaFree(s.d_dcan); cudaFree(s.d_dcan_incon); cudaFree(s.d_support); cudaFree(s.d_mesh_scratch);
+    cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16); cudaFreeHost(s.h_hdr);
+    cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp); cudaFree(s.d_parent); cudaFree(s.d_size);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
-    if (s.ev_sync) cudaEventDestroy(s.ev_sync);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
-    if (s.ev_a) cudaEventDestroy(s.ev_a);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
     if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
     for (auto& m : s.timer.marks) cudaEventDestroy(m.second);
@@ -204,51 +214,62 @@ void free_slot(Slot& s)
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
-int32_t alloc_slot(elas_b200_ctx* c, Slot& s)
+// ints of one frame's host-path tables: [support | tri1 | tri2 | units]
+size_t table_ints(const elas_b200_ctx* c) { return 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap) + 2 * (size_t)c->unit_cap + 8; }
+
+int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
 {
     const FrameGeom& g = c->g;
-    const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
-    const size_t cells = (size_t)g.gw * g.gh * g.gwords;
+    const GroupStrides& st = c->st;
+    const size_t n = (size_t)cap;
+    s.cap = cap;
+    s.io.resize(cap); s.expand_D2.assign(cap, nullptr);
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&s.d_D2_i16, ND * 2));
-    CK(cudaMallocHost(&s.h_D2_i16, ND * 2));
-    const unsigned ev_flags = cudaEventDisableTiming | (c->blocking_sync ? cudaEventBlockingSync : 0);
     CK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&s.ev_a, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&s.ev_out, ev_flags));
+    // a worker waits for a group's maps in cudaEventSynchronize: blocking, so that it leaves its core to the others
+    CK(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming | cudaEventBlockingSync));
     for (int k = 0; k < 2; k++) {
-        CK(cudaMalloc(&s.d_img[k], (size_t)g.bpl * g.H));
-        CK(cudaMemset(s.d_img[k], 0, (size_t)g.bpl * g.H));                // padding columns stay 0 (elas.cpp:42-43)
-        CK(cudaMallocHost(&s.h_img[k], (size_t)g.bpl * g.H));
-        std::memset(s.h_img[k], 0, (size_t)g.bpl * g.H);
-        CK(cudaMalloc(&s.d_desc[k], N * 16));
-        CK(cudaMalloc(&s.d_tri[k], (size_t)c->tri_cap * sizeof(TriRaster)));
-        CK(cudaMalloc(&s.d_grid[k], cells * 4));
-        CK(cudaMalloc(&s.d_lists[k], (size_t)g.gw * g.gh * kGridListStride * 2));
-        CK(cudaMalloc(&s.d_map[k], (size_t)map_pitch(g) * g.H * 4));
-        CK(cudaMemset(s.d_map[k], 0xFF, (size_t)map_pitch(g) * g.H * 4));   // -1 = not covered by any triangle
-        CK(cudaMalloc(&s.d_raw[k], ND * 4));
-        CK(cudaMalloc(&s.d_D[k], ND * 4));
-        CK(cudaMalloc(&s.d_planes[k], (size_t)c->tri_cap * 24));
+        CK(cudaMalloc(&s.d_img[k], n * st.img));
+        CK(cudaMemset(s.d_img[k], 0, n * st.img));                          // padding columns stay 0 (elas.cpp:42-43)
+        CK(cudaMallocHost(&s.h_img[k], n * st.img));
+        std::memset(s.h_img[k], 0, n * st.img);
+        CK(cudaMalloc(&s.d_desc[k], n * st.desc * 16));
+        CK(cudaMalloc(&s.d_tri[k], n * st.tri * 4));
+        CK(cudaMalloc(&s.d_units[k], n * st.units * 4));
+        CK(cudaMalloc(&s.d_traster[k], n * st.traster * sizeof(TriRaster)));
+        CK(cudaMalloc(&s.d_planes[k], n * st.planes * 4));
+        CK(cudaMalloc(&s.d_grid[k], n * st.grid * 4));
+        CK(cudaMalloc(&s.d_lists[k], n * st.lists * 2));
+        CK(cudaMalloc(&s.d_map[k], n * st.map * 4));
+        CK(cudaMemset(s.d_map[k], 0xFF, n * st.map * 4));                   // -1 = not covered by any triangle
+        CK(cudaMalloc(&s.d_raw[k], n * st.D * 4));
+        CK(cudaMalloc(&s.d_D[k], n * st.D * 4));
     }
-    const size_t table_ints = 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap) + 2 * (size_t)c->unit_cap;
-    CK(cudaMalloc(&s.d_tables, table_ints * 4));
-    CK(cudaMallocHost(&s.h_tables, table_ints * 4));
-    CK(cudaEventCreateWithFlags(&s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
-    CK(cudaMalloc(&s.d_grid_scratch, 4 * cells * 4));                      // two buffers of [2][cells] words
-    CK(cudaMemset(s.d_grid_scratch, 0, 4 * cells * 4));
-    CK(cudaMalloc(&s.d_tmp, 2 * ND * 4));
-    CK(cudaMalloc(&s.d_parent, ND * 4));
-    CK(cudaMalloc(&s.d_size, ND * 4));
-    // the candidate lattice lives in pinned host memory only: K2 writes it across PCIe (k_support.cu)
-    CK(cudaHostAlloc(&s.h_dcan, (size_t)g.Wc * g.Hc * 2, cudaHostAllocMapped));
+    CK(cudaMalloc(&s.d_dcan_raw, n * st.dcan * 2));
+    CK(cudaMalloc(&s.d_dcan, n * st.dcan * 2));
+    CK(cudaMalloc(&s.d_support, n * st.support * 4));
+    CK(cudaMalloc(&s.d_hdr, n * sizeof(FrameHeader)));
+    CK(cudaMemset(s.d_hdr, 0, n * sizeof(FrameHeader)));
+    CK(cudaMallocHost(&s.h_hdr, n * sizeof(FrameHeader)));
+    if (c->mesh_device) CK(cudaMalloc(&s.d_mesh_scratch, n * 2 * st.mesh_scratch * 4));
+    else {
+        CK(cudaMallocHost(&s.h_dcan, n * st.dcan * 2));
+        CK(cudaMallocHost(&s.h_tables, table_ints(c) * 4));
+    }
+    CK(cudaMalloc(&s.d_grid_scratch, n * st.scratch * 4));                  // per frame two buffers of [2][cells] words
+    CK(cudaMemset(s.d_grid_scratch, 0, n * st.scratch * 4));
+    CK(cudaMalloc(&s.d_tmp, n * 2 * st.D * 4));
+    CK(cudaMalloc(&s.d_parent, n * st.D * 4));
+    CK(cudaMalloc(&s.d_size, n * st.D * 4));
+    CK(cudaMalloc(&s.d_D2_i16, n * st.D * 2));
+    CK(cudaMallocHost(&s.h_D2_i16, n * st.D * 2));
     return ELAS_B200_OK;
 }
 
 // ---- introspection helpers -------------------------------------------------------------------
 
-int32_t grab(Slot& s, const char* name, const void* dptr, size_t bytes)
+int32_t grab(Group& s, const char* name, const void* dptr, size_t bytes)
 {
     std::vector<uint8_t>& v = s.stages[name];
     v.resize(bytes);
@@ -257,13 +278,13 @@ int32_t grab(Slot& s, const char* name, const void* dptr, size_t bytes)
     return ELAS_B200_OK;
 }
 
-void grab_host(Slot& s, const char* name, const void* ptr, size_t bytes)
+void grab_host(Group& s, const char* name, const void* ptr, size_t bytes)
 {
     std::vector<uint8_t>& v = s.stages[name];
     v.assign((const uint8_t*)ptr, (const uint8_t*)ptr + bytes);
 }
 
-void mark(elas_b200_ctx* c, Slot& s, const char* name)
+void mark(elas_b200_ctx* c, Group& s, const char* name)
 {
     if (!c->timing) return;
     cudaEvent_t e = nullptr;
@@ -288,55 +309,38 @@ std::vector<uint8_t> expand_grid(const FrameGeom& g, const std::vector<uint8_t>&
     return out;
 }
 
-int32_t wait_stream(elas_b200_ctx* c, Slot& s)
+// what kind of memory a caller's pointer is (launch errors are checked where the launches are issued, so
+// clearing the error of a failed query here cannot swallow one)
+struct PtrKind { bool pageable, device, mapped_host; void* device_alias; };
+PtrKind classify(const void* ptr, int device)
 {
-    if (c->blocking_sync) {
-        CK(cudaEventRecord(s.ev_sync, s.stream));
-        CK(cudaEventSynchronize(s.ev_sync));
-    } else {
-        CK(cudaStreamSynchronize(s.stream));
-    }
-    return ELAS_B200_OK;
+    PtrKind k{false, false, false, nullptr};
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); k.pageable = true; return k; }
+    k.pageable = attr.type == cudaMemoryTypeUnregistered;
+    // only memory of THIS device is written in place by the kernels; anything else takes the copy path
+    k.device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.device == device;
+    k.mapped_host = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+    k.device_alias = attr.devicePointer;
+    return k;
 }
 
 // elas.cpp:35-56: W bytes of every row go into the 16-byte-aligned zero-padded copy; when the caller's
 // pitch already equals that padded pitch the reference memcpy's the whole block (:44-48) -- one 1-D copy
-int32_t copy_image_in(const FrameGeom& g, uint8_t* dst, const uint8_t* src, int pitch, cudaStream_t st,
-                      uint8_t* staging = nullptr)
+int32_t copy_image_in(const elas_b200_ctx* c, uint8_t* dst, const uint8_t* src, int pitch, cudaStream_t st, uint8_t* staging)
 {
-    if (staging) {
+    const FrameGeom& g = c->g;
+    if (staging && classify(src, c->device).pageable) {
         // Pageable host memory (stereomapper's IplImage buffers are malloc'ed): the driver would stage such a
-        // copy itself at a few GB/s; rows go into the slot's pinned staging image instead (padding columns
+        // copy itself at a few GB/s; rows go into the group's pinned staging image instead (padding columns
         // stay 0 unless the caller's pitch is the padded pitch, elas.cpp:44-55) and leave as one pinned copy
-        cudaPointerAttributes attr{};
-        // (launch errors are checked where the launches are issued, so clearing the error of a failed
-        // attribute query here cannot swallow one)
-        const bool query_failed = cudaPointerGetAttributes(&attr, src) != cudaSuccess;
-        if (query_failed) cudaGetLastError();
-        const bool pageable = query_failed || attr.type == cudaMemoryTypeUnregistered;
-        if (pageable) {
-            if (pitch == g.bpl) std::memcpy(staging, src, (size_t)g.bpl * g.H);
-            else for (int v = 0; v < g.H; v++) std::memcpy(staging + (size_t)v * g.bpl, src + (size_t)v * pitch, (size_t)g.W);
-            CK(cudaMemcpyAsync(dst, staging, (size_t)g.bpl * g.H, cudaMemcpyHostToDevice, st));
-            return ELAS_B200_OK;
-        }
+        if (pitch == g.bpl) std::memcpy(staging, src, (size_t)g.bpl * g.H);
+        else for (int v = 0; v < g.H; v++) std::memcpy(staging + (size_t)v * g.bpl, src + (size_t)v * pitch, (size_t)g.W);
+        CK(cudaMemcpyAsync(dst, staging, (size_t)g.bpl * g.H, cudaMemcpyHostToDevice, st));
+        return ELAS_B200_OK;
     }
     if (pitch == g.bpl) CK(cudaMemcpyAsync(dst, src, (size_t)g.bpl * g.H, cudaMemcpyDefault, st));
     else CK(cudaMemcpy2DAsync(dst, g.bpl, src, pitch, g.W, g.H, cudaMemcpyDefault, st));
-    return ELAS_B200_OK;
-}
-
-// ---- one frame through one slot ----------------------------------------------------------------
-
-int32_t fill_invalid(elas_b200_ctx* c, Slot& s, float* D1, float* D2, bool device_io)
-{
-    // fewer than 3 support points: the reference returns without writing D (elas.cpp:69-75), which
-    // leaves the caller with uninitialised maps; the defined behaviour here is "all invalid".
-    const size_t nd = (size_t)c->g.Dw * c->g.Dh;
-    std::vector<float> fill(nd, (float)kInvalid);
-    (void)device_io;                              // the destination may be host or device memory either way
-    CK(cudaMemcpy(D1, fill.data(), nd * 4, cudaMemcpyDefault));
-    CK(cudaMemcpy(D2, fill.data(), nd * 4, cudaMemcpyDefault));
     return ELAS_B200_OK;
 }
 
@@ -356,133 +360,156 @@ void widen_i16_to_f32(const int16_t* src, float* dst, size_t n)
     for (; i < n; i++) dst[i] = (float)src[i];
 }
 
-// One frame = phase A (GPU) -> host stage -> phase B (GPU) -> maps out.  The four steps are separate
-// so that a slot's worker can start frame i+1 while the maps of frame i are still on their way out.
-struct FrameIO {
-    const uint8_t* I1; const uint8_t* I2;
-    float* D1; float* D2;
-    int bytes_per_line; bool device_io;
-};
+MatchBuffers match_buffers(const elas_b200_ctx* c, const Group& s)
+{
+    MatchBuffers b{};
+    for (int k = 0; k < 2; k++) {
+        b.desc[k] = s.d_desc[k]; b.tri[k] = s.d_traster[k]; b.map[k] = s.d_map[k]; b.grid[k] = s.d_grid[k];
+        b.lists[k] = s.d_lists[k]; b.D[k] = s.d_raw[k];
+    }
+    b.prior = c->d_prior;
+    b.desc_stride = c->st.desc; b.tri_stride = c->st.traster; b.map_stride = c->st.map; b.grid_stride = c->st.grid;
+    b.lists_stride = c->st.lists; b.D_stride = c->st.D;
+    return b;
+}
 
-// ---- phase A: images in, descriptors, support search (lattice lands in pinned host memory) ------
-int32_t phase_a_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
+// ---- host-stage path (parameters the device mesh stage does not take): lattice to the host, filters +
+// Delaunay on the CPU (host_stage.cc), tables and header back.  One frame after the other.
+int32_t mesh_on_host(elas_b200_ctx* c, Group& s)
 {
     const FrameGeom& g = c->g;
     const elas_b200_params& p = c->p;
+    const size_t lat = (size_t)g.Wc * g.Hc;
+    CK(cudaMemcpyAsync(s.h_dcan, s.d_dcan_raw, (size_t)s.n * c->st.dcan * 2, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    const long long t0 = now_ns();
+    for (int f = 0; f < s.n; f++) {
+        int16_t* dcan = s.h_dcan + (size_t)f * c->st.dcan;
+        if (s.capture) grab_host(s, "dcan_raw", dcan, lat * 2);
+        const int n = s.host.run(g, p, dcan, s.capture, false);
+        if (s.capture) grab_host(s, "dcan_incon", s.host.dcan_incon.data(), s.host.dcan_incon.size() * 2);
+        FrameHeader h{};
+        h.n_support = n;
+        if (n >= 3) {
+            const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
+            if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap) return ELAS_B200_E_UNSUPPORTED;
+            h.n_tri[0] = nt1; h.n_tri[1] = nt2;
+            // the host lists the units of both images in one array (the image is a bit of the unit): they go into
+            // the left image's list; if there are too many, every triangle is scan-converted by a warp of its own
+            const int n_units = (int)s.host.units.size() / 2;
+            const bool fits = n_units <= 2 * c->unit_cap;
+            h.n_units[0] = fits ? std::min(n_units, c->unit_cap) : 0;
+            h.n_units[1] = fits ? n_units - h.n_units[0] : 0;
+            h.ovf_from[0] = fits ? nt1 : 0; h.ovf_from[1] = fits ? nt2 : 0;
+            int32_t* t = s.h_tables;
+            std::memcpy(t, s.host.support.data(), (size_t)n * 12);
+            std::memcpy(t + 3 * (size_t)c->support_cap, s.host.tri[0].data(), (size_t)nt1 * 12);
+            std::memcpy(t + 3 * ((size_t)c->support_cap + c->tri_cap), s.host.tri[1].data(), (size_t)nt2 * 12);
+            CK(cudaMemcpyAsync(s.d_support + (size_t)f * c->st.support, t, (size_t)n * 12, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(s.d_tri[0] + (size_t)f * c->st.tri, t + 3 * (size_t)c->support_cap, (size_t)nt1 * 12, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(s.d_tri[1] + (size_t)f * c->st.tri, t + 3 * ((size_t)c->support_cap + c->tri_cap), (size_t)nt2 * 12, cudaMemcpyHostToDevice, s.stream));
+            if (fits) {
+                int32_t* u = t + 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap);
+                std::memcpy(u, s.host.units.data(), (size_t)n_units * 8);
+                CK(cudaMemcpyAsync(s.d_units[0] + (size_t)f * c->st.units, u, (size_t)h.n_units[0] * 8, cudaMemcpyHostToDevice, s.stream));
+                if (h.n_units[1]) CK(cudaMemcpyAsync(s.d_units[1] + (size_t)f * c->st.units, u + 2 * (size_t)h.n_units[0], (size_t)h.n_units[1] * 8, cudaMemcpyHostToDevice, s.stream));
+            }
+        }
+        s.h_hdr[f] = h;
+        CK(cudaMemcpyAsync(s.d_dcan + (size_t)f * c->st.dcan, dcan, lat * 2, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_hdr + f, s.h_hdr + f, sizeof(FrameHeader), cudaMemcpyHostToDevice, s.stream));
+        // h_tables is reused by the next frame of the group
+        if (f + 1 < s.n || true) CK(cudaStreamSynchronize(s.stream));
+    }
+    c->ns_host += now_ns() - t0;
+    return ELAS_B200_OK;
+}
+
+// ---- one launch chain: s.n frames (s.io) from images to maps, everything enqueued on the group's streams -----------
+int32_t submit_group(elas_b200_ctx* c, Group& s)
+{
+    const FrameGeom& g = c->g;
+    const elas_b200_params& p = c->p;
+    const GroupStrides& gs = c->st;
+    const int n = s.n;
+    const size_t N = (size_t)g.W * g.H, ND = (size_t)g.Dw * g.Dh;
     cudaStream_t st = s.stream;
+    const long long t0 = now_ns();
     if (s.capture) s.stages.clear();
     s.tables_valid = false;
     if (c->timing) {
         if (!s.timer.begin) cudaEventCreate(&s.timer.begin);
         cudaEventRecord(s.timer.begin, st);
     }
-    const long long t0 = now_ns();
-    if (int32_t rc = copy_image_in(g, s.d_img[0], io.I1, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[0])) return rc;
-    if (int32_t rc = copy_image_in(g, s.d_img[1], io.I2, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[1])) return rc;
+    // ---- images in, descriptors, support search ----------------------------------------------------------------------
+    for (int f = 0; f < n; f++) {
+        const FrameIO& io = s.io[f];
+        if (int32_t rc = copy_image_in(c, s.d_img[0] + (size_t)f * gs.img, io.I1, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[0] + (size_t)f * gs.img)) return rc;
+        if (int32_t rc = copy_image_in(c, s.d_img[1] + (size_t)f * gs.img, io.I2, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[1] + (size_t)f * gs.img)) return rc;
+    }
     mark(c, s, "copy_in");
-    launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], st);
+    launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], gs, n, st);
     mark(c, s, "descriptor");
-    launch_support(g, p, s.d_desc[0], s.d_desc[1], s.h_dcan, st);
+    launch_support(g, p, s.d_desc[0], s.d_desc[1], s.d_dcan_raw, gs, n, st);
     mark(c, s, "support");
-    CK(cudaGetLastError());                      // launch-configuration errors are not sticky: report them with THIS frame
-    c->ns_submit_a += now_ns() - t0;
-    return ELAS_B200_OK;
-}
-
-// ---- wait for phase A, then the host stage.  Returns the number of support points in *n_out. ------
-int32_t phase_a_finish_and_host(elas_b200_ctx* c, Slot& s, int* n_out)
-{
-    const FrameGeom& g = c->g;
-    const elas_b200_params& p = c->p;
-    const size_t N = (size_t)g.W * g.H;
-    const long long t1 = now_ns();
-    if (int32_t rc = wait_stream(c, s)) return rc;
-    const long long t2 = now_ns();
+    CK(cudaGetLastError());                      // launch-configuration errors are not sticky: report them with THIS group
     if (s.capture) {
         if (int32_t rc = grab(s, "desc1", s.d_desc[0], N * 16)) return rc;
         if (int32_t rc = grab(s, "desc2", s.d_desc[1], N * 16)) return rc;
-        grab_host(s, "dcan_raw", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
+        if (int32_t rc = grab(s, "dcan_raw", s.d_dcan_raw, (size_t)g.Wc * g.Hc * 2)) return rc;
         int32_t lat[2] = {g.Wc, g.Hc};
         grab_host(s, "lattice_dims", lat, sizeof lat);
     }
-    const int n = s.host.run(g, p, s.h_dcan, s.capture, false);
-    *n_out = n;
+    // ---- mesh stage: lattice filters, support list, Delaunay x2, raster units ---------------------------------------------
+    if (c->mesh_device) {
+        if (s.capture && !s.d_dcan_incon) CK(cudaMalloc(&s.d_dcan_incon, (size_t)s.cap * gs.dcan * 2));
+        launch_lattice(g, p, s.d_dcan_raw, s.d_dcan, s.capture ? s.d_dcan_incon : nullptr, s.d_support, s.d_hdr, gs, n, st);
+        mark(c, s, "lattice");
+        launch_delaunay(g, s.d_support, s.d_tri[0], s.d_tri[1], s.d_units[0], s.d_units[1], c->unit_cap, s.d_hdr,
+                        s.d_mesh_scratch, gs, n, st);
+        mark(c, s, "delaunay");
+        CK(cudaGetLastError());
+        if (s.capture) if (int32_t rc = grab(s, "dcan_incon", s.d_dcan_incon, (size_t)g.Wc * g.Hc * 2)) return rc;
+    } else {
+        if (int32_t rc = mesh_on_host(c, s)) return rc;
+        mark(c, s, "host_stage");
+    }
     if (s.capture) {
-        grab_host(s, "dcan_incon", s.host.dcan_incon.data(), s.host.dcan_incon.size() * 2);
-        grab_host(s, "dcan", s.h_dcan, (size_t)g.Wc * g.Hc * 2);
-        grab_host(s, "support", s.host.support.data(), s.host.support.size() * 4);
+        FrameHeader h{};
+        CK(cudaMemcpyAsync(&h, s.d_hdr, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (int32_t rc = grab(s, "dcan", s.d_dcan, (size_t)g.Wc * g.Hc * 2)) return rc;
+        if (int32_t rc = grab(s, "support", s.d_support, (size_t)std::min(h.n_support, c->support_cap) * 12)) return rc;
+        if (int32_t rc = grab(s, "tri1", s.d_tri[0], (size_t)h.n_tri[0] * 12)) return rc;
+        if (int32_t rc = grab(s, "tri2", s.d_tri[1], (size_t)h.n_tri[1] * 12)) return rc;
+        int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
+        grab_host(s, "grid_dims", gd, sizeof gd);
+        grab_host(s, "header", &h, sizeof h);
     }
-    if (n >= 3) {
-        const int nt1 = (int)s.host.tri[0].size() / 3, nt2 = (int)s.host.tri[1].size() / 3;
-        const int n_units = (int)s.host.units.size() / 2;
-        if (n > c->support_cap || nt1 > c->tri_cap || nt2 > c->tri_cap || n_units > c->unit_cap) return ELAS_B200_E_BAD_ARG;
-        s.n_tri[0] = nt1; s.n_tri[1] = nt2;
-        std::memcpy(s.h_tables, s.host.support.data(), (size_t)n * 12);
-        std::memcpy(s.h_tables + 3 * n, s.host.tri[0].data(), (size_t)nt1 * 12);
-        std::memcpy(s.h_tables + 3 * (n + nt1), s.host.tri[1].data(), (size_t)nt2 * 12);
-        const size_t units_at = 3 * (size_t)(n + nt1 + nt2) + ((n + nt1 + nt2) & 1);      // 8-byte aligned
-        std::memcpy(s.h_tables + units_at, s.host.units.data(), (size_t)n_units * 8);
-        s.n_units = n_units; s.units_at = units_at;
-        if (s.capture) {
-            grab_host(s, "tri1", s.host.tri[0].data(), s.host.tri[0].size() * 4);
-            grab_host(s, "tri2", s.host.tri[1].data(), s.host.tri[1].size() * 4);
-            int32_t gd[3] = {p.disp_max + 2, g.gw, g.gh};
-            grab_host(s, "grid_dims", gd, sizeof gd);
-        }
-    }
-    c->ns_wait_a += t2 - t1; c->ns_host += now_ns() - t2;
-    return ELAS_B200_OK;
-}
-
-MatchBuffers match_buffers(const elas_b200_ctx* c, const Slot& s)
-{
-    MatchBuffers b{};
-    for (int k = 0; k < 2; k++) {
-        b.desc[k] = s.d_desc[k]; b.tri[k] = s.d_tri[k]; b.map[k] = s.d_map[k]; b.grid[k] = s.d_grid[k];
-        b.lists[k] = s.d_lists[k]; b.D[k] = s.d_raw[k];
-    }
-    b.prior = c->d_prior;
-    return b;
-}
-
-// ---- phase B: tables in, grid, triangle-id maps, matching, post-processing, maps out ---------------
-int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
-{
-    const FrameGeom& g = c->g;
-    const elas_b200_params& p = c->p;
-    const size_t ND = (size_t)g.Dw * g.Dh;
-    cudaStream_t st = s.stream;
-    const int n = s.host.n_support, nt1 = s.n_tri[0], nt2 = s.n_tri[1], n_units = s.n_units;
-    const size_t units_at = s.units_at;
-    const int32_t* d_support = s.d_tables;
-    const int32_t* d_tri1 = s.d_tables + 3 * n;
-    const int32_t* d_tri2 = s.d_tables + 3 * (n + nt1);
-    const long long t3 = now_ns();
-    if (c->timing) mark(c, s, "host_stage");     // recorded when phase B is enqueued: includes the host time
-    CK(cudaMemcpyAsync(s.d_tables, s.h_tables, (units_at + 2 * (size_t)n_units) * 4, cudaMemcpyHostToDevice, st));
-    mark(c, s, "tables_in");
+    // ---- planes, candidate grid, triangle-id maps, dense matching ------------------------------------------------------------
     const size_t scratch_words = 2 * (size_t)g.gw * g.gh * g.gwords;
     uint32_t* scratch_cur = s.d_grid_scratch + (size_t)s.scratch_phase * scratch_words;
     uint32_t* scratch_next = s.d_grid_scratch + (size_t)(1 - s.scratch_phase) * scratch_words;
     s.scratch_phase ^= 1;
     if (++s.map_tag > c->map_tag_max) {
         // tag space used up: start over from cleared maps
-        for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s.d_map[k], 0xFF, (size_t)map_pitch(g) * g.H * 4, st));
+        for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s.d_map[k], 0xFF, (size_t)s.cap * gs.map * 4, st));
         s.map_tag = 1;
     }
     const int tag_bits = s.map_tag << c->map_tag_shift;
-    launch_planes_scatter(g, p, d_support, n, d_tri1, nt1, d_tri2, nt2, s.d_tri[0], s.d_tri[1], s.d_planes[0],
-                          s.d_planes[1], scratch_cur, st);                                 // elas.cpp:87-88, :697-727
+    launch_planes_scatter(g, p, s.d_hdr, s.d_support, s.d_tri[0], s.d_tri[1], s.d_traster[0], s.d_traster[1], s.d_planes[0],
+                          s.d_planes[1], scratch_cur, gs, n, st);                          // elas.cpp:87-88, :697-727
     mark(c, s, "planes+scatter");
     if (s.capture) {
-        if (int32_t rc = grab(s, "planes1", s.d_planes[0], (size_t)nt1 * 24)) return rc;
-        if (int32_t rc = grab(s, "planes2", s.d_planes[1], (size_t)nt2 * 24)) return rc;
+        const FrameHeader& h = *reinterpret_cast<const FrameHeader*>(s.stages["header"].data());
+        if (int32_t rc = grab(s, "planes1", s.d_planes[0], (size_t)h.n_tri[0] * 24)) return rc;
+        if (int32_t rc = grab(s, "planes2", s.d_planes[1], (size_t)h.n_tri[1] * 24)) return rc;
     }
-    launch_diffuse_raster(g, p.subsampling, scratch_cur, scratch_next, s.d_grid[0], s.d_grid[1], s.d_lists[0],
-                          s.d_lists[1], s.d_tri[0], s.d_tri[1], s.d_tables + units_at, n_units, s.d_map[0],
-                          s.d_map[1], tag_bits, st);                                        // :732-775, :1074-1114
+    launch_diffuse_raster(g, p.subsampling, s.d_hdr, scratch_cur, scratch_next, s.d_grid[0], s.d_grid[1], s.d_lists[0],
+                          s.d_lists[1], s.d_traster[0], s.d_traster[1], s.d_units[0], s.d_units[1], s.d_map[0],
+                          s.d_map[1], tag_bits, gs, n, st);                                 // :732-775, :1074-1114
     mark(c, s, "diffuse+raster");
-    launch_matching(g, p, match_buffers(c, s), 1, tag_bits, c->map_tag_shift, st);
+    launch_matching(g, p, match_buffers(c, s), n, tag_bits, c->map_tag_shift, st);
     mark(c, s, "matching");
     CK(cudaGetLastError());
     s.tables_valid = true;
@@ -493,131 +520,142 @@ int32_t phase_b_submit(elas_b200_ctx* c, Slot& s, const FrameIO& io)
         if (int32_t rc = grab(s, "D1_raw", s.d_raw[0], ND * 4)) return rc;
         if (int32_t rc = grab(s, "D2_raw", s.d_raw[1], ND * 4)) return rc;
     }
+    // ---- L/R check and post-processing ------------------------------------------------------------------------------------------
     const int n_post = p.postprocess_only_left ? 1 : 2;                                  // elas.cpp:121-159
-    const bool fused_post = post_fusable(p);
-    // With device-resident output buffers the last kernel that touches a map writes it straight into the
-    // caller's buffer.  D2 without post-processing is final after the L/R check.
-    // Where the kernels can store a finished map directly: device buffers and, optionally (direct_out),
-    // PINNED host buffers through their device alias.  A copy kernel reaches 52 GB/s that way
-    // (tools/micro/zerocopy_d2h.cu) but letting k_post_fused / k_lr_rows store across PCIe costs the pipeline
-    // more than the copy engine does, so the default for host buffers is the copy path.
-    float* user[2] = {io.D1, io.D2};
-    float* direct[2] = {nullptr, nullptr};
-    for (int k = 0; k < 2; k++) {
-        if (io.device_io) { direct[k] = user[k]; continue; }
-        cudaPointerAttributes attr{};
-        if (cudaPointerGetAttributes(&attr, user[k]) != cudaSuccess) { cudaGetLastError(); continue; }
-        // a device pointer handed to the host-buffer entry points is written in place like any device buffer
-        // (and must never reach the CPU-side widening below)
-        if (attr.type == cudaMemoryTypeDevice) direct[k] = user[k];
-        else if (attr.type == cudaMemoryTypeHost && attr.devicePointer && c->direct_out && !p.filter_median)
-            direct[k] = static_cast<float*>(attr.devicePointer);
-    }
-    float* lr_out[2] = {s.d_D[0], s.d_D[1]};
-    if (direct[1] && n_post == 1) lr_out[1] = direct[1];
+    const bool fused_post = post_fusable(p) && !p.filter_median;
     const bool rows_fused = lr_rows_fusable(g);
-    // Copy path, D2 final after the L/R check: its values are raw integer disparities or -10, so it
-    // crosses PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
-    const bool d2_i16 = !direct[1] && !io.device_io && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
-    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], s.d_parent, s.d_size,
-                                   d2_i16 ? s.d_D2_i16 : nullptr, st);
-    else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], lr_out[0], lr_out[1], st);          // elas.cpp:116
+    // Where a finished map goes: a caller's buffer in THIS device's memory is written by the last kernel that
+    // touches the map (D2 without post-processing is final after the L/R check); host buffers are reached by
+    // copies from the group's buffers.
+    bool direct[2][kMaxGroupFrames] = {};
+    bool any_direct_d2 = false, all_host = true;
+    for (int f = 0; f < n; f++)
+        for (int k = 0; k < 2; k++) {
+            float* user = k ? s.io[f].D2 : s.io[f].D1;
+            direct[k][f] = fused_post && (s.io[f].device_io || classify(user, c->device).device);
+            if (k == 1 && direct[k][f]) any_direct_d2 = true;
+            if (direct[k][f]) all_host = false;
+        }
+    // Copy path, D2 final after the L/R check: its values are raw integer disparities or -10, so it crosses
+    // PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
+    const bool d2_i16 = all_host && !any_direct_d2 && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
+    OutTable lr_d2 = out_table(s.d_D[1], gs.D, n);
+    if (n_post == 1) for (int f = 0; f < n; f++) if (direct[1][f]) lr_d2.p[f] = s.io[f].D2;
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, s.d_parent, s.d_size,
+                                   d2_i16 ? s.d_D2_i16 : nullptr, gs.D, n, st);
+    else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, gs.D, n, st);       // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
-        if (int32_t rc = grab(s, "D1_lr", lr_out[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_lr", lr_out[1], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D1_lr", s.d_D[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2_lr", lr_d2.p[0], ND * 4)) return rc;
     }
-    float* final_map[2] = {lr_out[0], lr_out[1]};
+    // final_map[k] = where frame f's finished map k lives
+    OutTable final_map[2] = {out_table(s.d_D[0], gs.D, n), lr_d2};
     if (fused_post) {
         // speckle sizes (K9 rows/merge/count), then ONE kernel for speckle apply + gap interpolation +
         // adaptive mean; it reads d_D and writes the final map (d_raw is dead after the L/R check)
         for (int k = 0; k < n_post; k++) {
-            launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, false, rows_fused && k == 0);
+            launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, gs.D, n, st, false, rows_fused && k == 0);
             mark(c, s, k ? "segments2" : "segments");
-            final_map[k] = direct[k] ? direct[k] : s.d_raw[k];
+            final_map[k] = out_table(s.d_raw[k], gs.D, n);
+            for (int f = 0; f < n; f++) if (direct[k][f]) final_map[k].p[f] = k ? s.io[f].D2 : s.io[f].D1;
             launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, final_map[k],
-                              s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, st);
+                              s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, gs.D, n, st);
             if (s.capture) {
                 if (int32_t rc = grab(s, k ? "D2_seg" : "D1_seg", s.d_tmp, ND * 4)) return rc;
-                if (int32_t rc = grab(s, k ? "D2_gap" : "D1_gap", p.filter_adaptive_mean ? s.d_tmp + ND : final_map[k], ND * 4)) return rc;
+                if (int32_t rc = grab(s, k ? "D2_gap" : "D1_gap", p.filter_adaptive_mean ? s.d_tmp + ND : final_map[k].p[0], ND * 4)) return rc;
             }
         }
         mark(c, s, "apply+gap+mean");
         if (s.capture && n_post == 1) {
-            if (int32_t rc = grab(s, "D2_seg", lr_out[1], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_gap", lr_out[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_seg", lr_d2.p[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", lr_d2.p[0], ND * 4)) return rc;
         }
     } else {
-        for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, st, true, rows_fused && k == 0);
+        // the unfused chain works in place on the group's buffers (settings outside the ROBOTICS family)
+        for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, gs.D, n, st, true, rows_fused && k == 0);
         mark(c, s, "segments");
         if (s.capture) {
-            if (int32_t rc = grab(s, "D1_seg", lr_out[0], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_seg", lr_out[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_seg", s.d_D[1], ND * 4)) return rc;
         }
-        for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, st);
+        for (int k = 0; k < n_post; k++) launch_gap(g, p, s.d_D[k], s.d_tmp, gs.D, 2 * gs.D, n, st);
         mark(c, s, "gap");
         if (s.capture) {
-            if (int32_t rc = grab(s, "D1_gap", lr_out[0], ND * 4)) return rc;
-            if (int32_t rc = grab(s, "D2_gap", lr_out[1], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D1_gap", s.d_D[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_gap", s.d_D[1], ND * 4)) return rc;
         }
         if (p.filter_adaptive_mean) {
-            for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, st);
+            for (int k = 0; k < n_post; k++) launch_adaptive_mean(g, p, s.d_D[k], s.d_tmp, gs.D, 2 * gs.D, n, st);
             mark(c, s, "adaptive_mean");
+        }
+        if (s.capture) {
+            if (int32_t rc = grab(s, "D1_mean", s.d_D[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_mean", s.d_D[1], ND * 4)) return rc;
+        }
+        if (p.filter_median) {
+            for (int k = 0; k < n_post; k++) launch_median(g, s.d_D[k], s.d_tmp, gs.D, 2 * gs.D, n, st);
+            mark(c, s, "median");
         }
     }
     if (s.capture) {
-        if (int32_t rc = grab(s, "D1_mean", final_map[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2_mean", final_map[1], ND * 4)) return rc;
-    }
-    if (p.filter_median) {
-        for (int k = 0; k < n_post; k++) launch_median(g, final_map[k], s.d_tmp, st);
-        mark(c, s, "median");
-    }
-    if (s.capture) {
-        if (int32_t rc = grab(s, "D1", final_map[0], ND * 4)) return rc;
-        if (int32_t rc = grab(s, "D2", final_map[1], ND * 4)) return rc;
+        if (fused_post) {
+            if (int32_t rc = grab(s, "D1_mean", final_map[0].p[0], ND * 4)) return rc;
+            if (int32_t rc = grab(s, "D2_mean", final_map[1].p[0], ND * 4)) return rc;
+        }
+        if (int32_t rc = grab(s, "D1", final_map[0].p[0], ND * 4)) return rc;
+        if (int32_t rc = grab(s, "D2", final_map[1].p[0], ND * 4)) return rc;
     }
     CK(cudaGetLastError());
-    s.last_D1 = final_map[0];
-    // maps out: nothing to do for maps the kernels stored in place; the others are copied on the slot's copy
-    // stream so that the compute stream is free for the next frame (stage timing keeps them in line)
-    auto in_place = [&](int k) { return direct[k] && final_map[k] == direct[k]; };
+    // a group-owned copy of frame 0's final left map serves elas_b200_colormap / _reproject with D1 == NULL
+    s.last_D1 = direct[0][0] ? nullptr : final_map[0].p[0];
+    // ---- maps and headers out: nothing to do for maps the kernels stored in place; the others are copied on the
+    // group's copy stream (stage timing keeps them in line) ---------------------------------------------------------------------
     cudaStream_t out_stream = st;
-    const bool copies = !in_place(0) || !in_place(1);
-    if (copies && !c->timing) {
+    if (!c->timing) {
         CK(cudaEventRecord(s.ev_done, st));
         CK(cudaStreamWaitEvent(s.copy_stream, s.ev_done, 0));
         out_stream = s.copy_stream;
     }
-    s.expand_D2 = nullptr;
-    for (int k = 0; k < 2; k++) {
-        if (in_place(k)) continue;
-        if (k == 1 && d2_i16) {
-            CK(cudaMemcpyAsync(s.h_D2_i16, s.d_D2_i16, ND * 2, cudaMemcpyDeviceToHost, out_stream));
-            s.expand_D2 = user[1];
-        } else {
-            CK(cudaMemcpyAsync(user[k], final_map[k], ND * 4, cudaMemcpyDefault, out_stream));
+    for (int f = 0; f < n; f++) {
+        s.expand_D2[f] = nullptr;
+        for (int k = 0; k < 2; k++) {
+            if (direct[k][f]) continue;
+            float* user = k ? s.io[f].D2 : s.io[f].D1;
+            if (k == 1 && d2_i16) {
+                CK(cudaMemcpyAsync(s.h_D2_i16 + (size_t)f * gs.D, s.d_D2_i16 + (size_t)f * gs.D, ND * 2, cudaMemcpyDeviceToHost, out_stream));
+                s.expand_D2[f] = user;
+            } else {
+                CK(cudaMemcpyAsync(user, final_map[k].p[f], ND * 4, cudaMemcpyDefault, out_stream));
+            }
         }
     }
+    CK(cudaMemcpyAsync(s.h_hdr, s.d_hdr, (size_t)n * sizeof(FrameHeader), cudaMemcpyDeviceToHost, out_stream));
     mark(c, s, "copy_out");
     CK(cudaEventRecord(s.ev_out, out_stream));
-    c->ns_submit_b += now_ns() - t3;
+    c->ns_submit += now_ns() - t0;
     return ELAS_B200_OK;
 }
 
-// ---- the frame's maps are in the caller's buffers ----------------------------------------------------
-int32_t frame_finish(elas_b200_ctx* c, Slot& s)
+// ---- the group's maps are in the caller's buffers: per-frame status into status_out[0..n) ------------------------------
+int32_t finish_group(elas_b200_ctx* c, Group& s, int32_t* status_out)
 {
-    const long long t4 = now_ns();
+    const long long t0 = now_ns();
     CK(cudaEventSynchronize(s.ev_out));
     CK(cudaGetLastError());
-    c->ns_wait_b += now_ns() - t4; c->frames += 1;
-    if (s.expand_D2) {
-        const long long t5 = now_ns();
-        widen_i16_to_f32(s.h_D2_i16, s.expand_D2, (size_t)c->g.Dw * c->g.Dh);
-        s.expand_D2 = nullptr;
-        c->ns_host += now_ns() - t5;             // counted with the host stage: CPU work of the frame
+    const long long t1 = now_ns();
+    c->ns_wait += t1 - t0; c->frames += s.n;
+    const size_t ND = (size_t)c->g.Dw * c->g.Dh;
+    for (int f = 0; f < s.n; f++) {
+        const FrameHeader& h = s.h_hdr[f];
+        status_out[f] = h.status < 0 ? h.status : h.n_support < 3 ? ELAS_B200_E_FEW_SUPPORT : ELAS_B200_OK;
+        if (s.expand_D2[f]) {
+            widen_i16_to_f32(s.h_D2_i16 + (size_t)f * c->st.D, s.expand_D2[f], ND);
+            s.expand_D2[f] = nullptr;
+        }
     }
+    s.last_n = s.n;
+    c->ns_finish += now_ns() - t1;
     if (c->timing) {
         CK(cudaStreamSynchronize(s.stream));
         s.timer.last.clear();
@@ -633,80 +671,28 @@ int32_t frame_finish(elas_b200_ctx* c, Slot& s)
 }
 
 // one frame, start to finish (the drop-in call and elas_b200_process_ctx)
-int32_t run_frame(elas_b200_ctx* c, Slot& s, const uint8_t* I1, const uint8_t* I2, float* D1,
+int32_t run_frame(elas_b200_ctx* c, Group& s, const uint8_t* I1, const uint8_t* I2, float* D1,
                   float* D2, int bytes_per_line, bool device_io)
 {
-    const FrameIO io{I1, I2, D1, D2, bytes_per_line, device_io};
-    if (int32_t rc = phase_a_submit(c, s, io)) return rc;
-    int n = 0;
-    if (int32_t rc = phase_a_finish_and_host(c, s, &n)) return rc;
-    if (n < 3) {
-        if (int32_t rc = fill_invalid(c, s, D1, D2, device_io)) return rc;
-        return ELAS_B200_E_FEW_SUPPORT;
-    }
-    if (int32_t rc = phase_b_submit(c, s, io)) return rc;
-    return frame_finish(c, s);
+    s.n = 1;
+    s.io[0] = FrameIO{I1, I2, D1, D2, bytes_per_line, device_io};
+    int32_t rc = submit_group(c, s);
+    if (rc) { cudaStreamSynchronize(s.stream); cudaStreamSynchronize(s.copy_stream); return rc; }
+    int32_t status = 0;
+    rc = finish_group(c, s, &status);
+    return rc ? rc : status;
 }
 
-// Batch scheduler.  Workers are not tied to slots: every worker walks over all slots and advances
-// whichever one can move -- an idle slot takes the next frame of the batch and gets its phase A
-// enqueued; a slot whose phase A has finished (event query, no blocking) gets its host stage run and its
-// phase B enqueued; a slot whose maps have landed is widened/reported and becomes idle again.  With more
-// slots than workers the GPU always has phases queued while every core does host stages, and no core
-// ever sits in a blocking wait on one particular frame.
-bool advance_slot(elas_b200_ctx* c, Slot& s, elas_b200_ctx::Job* job)
-{
-    auto report = [&](int i, int32_t rc) {
-        if (job->status) job->status[i] = rc;
-        if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
-        job->done.fetch_add(1);
-    };
-    switch (s.state) {
-    case 0: {
-        if (job->next.load(std::memory_order_relaxed) >= job->n) return false;
-        const int i = job->next.fetch_add(1);
-        if (i >= job->n) return false;
-        s.frame = i;
-        const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
-        int32_t rc = phase_a_submit(c, s, io);
-        if (!rc && cudaEventRecord(s.ev_a, s.stream) != cudaSuccess) rc = ELAS_B200_E_CUDA;
-        if (rc) { report(i, rc); return true; }
-        s.state = 1;
-        return true;
-    }
-    case 1: {
-        const cudaError_t q = cudaEventQuery(s.ev_a);
-        if (q == cudaErrorNotReady) return false;
-        const int i = s.frame;
-        const FrameIO io{job->I1[i], job->I2[i], job->D1[i], job->D2[i], job->bpl, job->device_io};
-        int n = 0;
-        int32_t rc = q == cudaSuccess ? phase_a_finish_and_host(c, s, &n) : ELAS_B200_E_CUDA;
-        if (!rc && n < 3) {
-            rc = fill_invalid(c, s, io.D1, io.D2, io.device_io);
-            if (!rc) rc = ELAS_B200_E_FEW_SUPPORT;
-        } else if (!rc && !(rc = phase_b_submit(c, s, io))) {
-            s.state = 2;
-            return true;
-        }
-        s.state = 0;
-        report(i, rc);
-        return true;
-    }
-    default: {
-        const cudaError_t q = cudaEventQuery(s.ev_out);
-        if (q == cudaErrorNotReady) return false;
-        s.state = 0;
-        report(s.frame, q == cudaSuccess ? frame_finish(c, s) : ELAS_B200_E_CUDA);
-        return true;
-    }
-    }
-}
-
-void worker_main(elas_b200_ctx* c, int worker)
+// Batch scheduler.  Nothing of a frame runs on the CPU (device mesh stage), so a worker only enqueues launch
+// chains and collects results: worker w drives the groups w, w + W, ...; for each of them in turn it waits
+// (blocking, no spinning) for the chain in flight, reports its frames, claims the next `cap` frames of the
+// batch and enqueues their chain.  With two or more groups per worker the GPU always has chains queued.
+void worker_main(elas_b200_ctx* c, int worker, int n_workers)
 {
     cudaSetDevice(c->device);
     uint64_t seen = 0;
-    const int n_slots = (int)c->slots.size();
+    const int n_groups = (int)c->groups.size();
+    std::vector<int32_t> status(kMaxGroupFrames);
     for (;;) {
         elas_b200_ctx::Job* job = nullptr;
         {
@@ -717,19 +703,37 @@ void worker_main(elas_b200_ctx* c, int worker)
             seen = c->job_seq;
             job->active++;
         }
-        int idle_scans = 0;
-        while (job->done.load(std::memory_order_acquire) < job->n) {
-            bool progressed = false;
-            for (int k = 0; k < n_slots; k++) {
-                Slot& s = *c->slots[(worker + k) % n_slots];
-                if (s.busy.load(std::memory_order_relaxed) || s.busy.exchange(1, std::memory_order_acquire)) continue;
-                progressed |= advance_slot(c, s, job);
-                s.busy.store(0, std::memory_order_release);
+        auto report = [&](int i, int32_t rc) {
+            if (job->status) job->status[i] = rc;
+            if (rc < 0) { int w = job->worst.load(); while (rc < w && !job->worst.compare_exchange_weak(w, rc)) {} }
+            job->done.fetch_add(1);
+        };
+        bool in_flight_any = true, frames_left = true;
+        while (in_flight_any || frames_left) {
+            in_flight_any = false;
+            for (int gi = worker; gi < n_groups; gi += n_workers) {
+                Group& s = *c->groups[gi];
+                if (s.first_frame >= 0) {
+                    // collect the chain in flight
+                    const int32_t rc = finish_group(c, s, status.data());
+                    for (int f = 0; f < s.n; f++) report(s.first_frame + f, rc ? rc : status[f]);
+                    s.first_frame = -1;
+                }
+                if (!frames_left) continue;
+                const int i0 = job->next.fetch_add(s.cap);
+                if (i0 >= job->n) { frames_left = false; continue; }
+                s.n = std::min(s.cap, job->n - i0);
+                for (int f = 0; f < s.n; f++)
+                    s.io[f] = FrameIO{job->I1[i0 + f], job->I2[i0 + f], job->D1[i0 + f], job->D2[i0 + f], job->bpl, job->device_io};
+                const int32_t rc = submit_group(c, s);
+                if (rc) {
+                    cudaStreamSynchronize(s.stream); cudaStreamSynchronize(s.copy_stream);
+                    for (int f = 0; f < s.n; f++) report(i0 + f, rc);
+                } else {
+                    s.first_frame = i0;
+                    in_flight_any = true;
+                }
             }
-            if (progressed) { idle_scans = 0; continue; }
-            // nothing could move: back off briefly (the GPU is working), longer if it keeps happening
-            const int spins = ++idle_scans < 16 ? 64 : 512;
-            for (int k = 0; k < spins; k++) _mm_pause();
         }
         {
             std::lock_guard<std::mutex> lk(c->mu);
@@ -820,7 +824,16 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
 int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
                             int32_t width, int32_t height, int32_t n_slots, int32_t n_workers)
 {
-    if (!out || !p || width < 16 || n_slots < 1 || n_slots > 64) return ELAS_B200_E_BAD_ARG;
+    int frames = 1;
+    if (const char* e = std::getenv("ELAS_B200_FRAMES_PER_GROUP")) frames = std::atoi(e);
+    return elas_b200_create_grouped(out, device, p, width, height, n_slots, frames, n_workers);
+}
+
+int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
+                                 int32_t width, int32_t height, int32_t n_groups, int32_t frames_per_group,
+                                 int32_t n_workers)
+{
+    if (!out || !p || width < 16 || n_groups < 1 || n_groups > 64 || frames_per_group < 0) return ELAS_B200_E_BAD_ARG;
     *out = nullptr;
     if (p->disp_max < 0 || p->disp_max > 4095 || p->disp_min > p->disp_max || p->candidate_stepsize < 1) return ELAS_B200_E_BAD_ARG;
     // the matching kernel divides by grid_size with a 32-bit reciprocal (exact for u, grid_size < 65536)
@@ -832,52 +845,71 @@ int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200
     std::unique_ptr<elas_b200_ctx> c(new elas_b200_ctx);
     c->device = device; c->p = *p;
     c->g = make_geom(*p, width, height);
-    c->support_cap = c->g.Wc * c->g.Hc + 6;
+    const FrameGeom& g = c->g;
+    // frames per launch chain: small frames are batched so that every kernel spans several waves of CTAs
+    if (frames_per_group == 0) frames_per_group = (int)std::max<long long>(1, std::min<long long>(kMaxGroupFrames, 4000000ll / ((long long)width * height)));
+    frames_per_group = std::min(frames_per_group, (int)kMaxGroupFrames);
+    c->support_cap = g.Wc * g.Hc + 6;
     c->tri_cap = 2 * c->support_cap + 8;
-    // raster work units: every triangle is at least one unit; large ones split into 32-column x 32-row
-    // pieces of their bounding boxes (bounded by a few times the image area)
     while ((1 << c->map_tag_shift) < c->tri_cap) c->map_tag_shift++;
     c->map_tag_max = (1 << (30 - c->map_tag_shift)) - 1;
     if (c->map_tag_max < 1) return ELAS_B200_E_UNSUPPORTED;
-    c->unit_cap = 2 * c->tri_cap + 8 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
+    // scan-conversion work units per image: every triangle is at least one unit, large ones split into 32-column x
+    // 32-row pieces of their bounding boxes.  Triangles that do not fit the list are scan-converted whole by one
+    // warp each (FrameHeader::ovf_from), so this is a performance knob, not a limit.
+    c->unit_cap = c->tri_cap + 4 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
+    c->mesh_device = mesh_on_device(g, *p);
+    if (const char* e = std::getenv("ELAS_B200_HOST_STAGE")) if (std::atoi(e)) c->mesh_device = false;
     // both SAD kernels stage their descriptor strips (segment + disparity range) in shared memory: at most
     // 200 KB per CTA, i.e. disp_max up to ~700 for the support search
-    if (matching_smem_bytes(c->g, *p) > 200 * 1024 || support_smem_bytes(c->g, *p) > 200 * 1024 ||
-        c->g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
-    std::vector<int32_t> prior = make_prior(*p, c->g.dn);
-    // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15
+    if (matching_smem_bytes(g, *p) > 200 * 1024 || support_smem_bytes(g, *p) > 200 * 1024 ||
+        g.plane_radius >= 16) return ELAS_B200_E_UNSUPPORTED;
+    std::vector<int32_t> prior = make_prior(*p, g.dn);
+    // the matching kernel packs (cost, evaluation order) into one 32-bit key: costs must stay below 2^15,
     // and relies on the prior never being positive (-log(1 + e/gamma)/beta <= 0 for gamma, beta > 0; k_matching.cu)
-    for (int k = 0; k <= c->g.plane_radius && k < c->g.dn; k++)
+    for (int k = 0; k <= g.plane_radius && k < g.dn; k++)
         if (prior[k] > 0 || prior[k] < -5000) return ELAS_B200_E_UNSUPPORTED;
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
     c->launches_at_create = launches_issued();
+    if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
     {
-        // spinning waits are the fastest while every slot's worker has a core of its own
-        const unsigned cores = std::thread::hardware_concurrency();
-        c->blocking_sync = cores > 0 && (unsigned)n_slots > cores;
-        if (const char* e = std::getenv("ELAS_B200_BLOCKING_SYNC")) c->blocking_sync = std::atoi(e) != 0;
-        if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
-        if (const char* e = std::getenv("ELAS_B200_DIRECT_OUT")) c->direct_out = std::atoi(e) != 0;
+        GroupStrides& st = c->st;
+        const size_t cells = (size_t)g.gw * g.gh;
+        st.img = (size_t)g.bpl * g.H;                 // bytes
+        st.desc = (size_t)g.W * g.H;                  // uint4
+        st.dcan = ((size_t)g.Wc * g.Hc + 7) & ~(size_t)7;   // int16
+        st.support = 3 * (size_t)c->support_cap;      // int32
+        st.tri = 3 * (size_t)c->tri_cap;
+        st.units = 2 * (size_t)c->unit_cap;
+        st.traster = (size_t)c->tri_cap;              // TriRaster
+        st.planes = 6 * (size_t)c->tri_cap;           // float
+        st.scratch = 4 * cells * g.gwords;            // uint32: two buffers of [2][cells][gwords]
+        st.grid = cells * g.gwords;
+        st.lists = cells * kGridListStride;           // uint16
+        st.map = (size_t)map_pitch(g) * g.H;          // int32
+        st.D = (size_t)g.Dw * g.Dh;                   // float
+        st.mesh_scratch = 17 * (size_t)c->support_cap + 8;
     }
-    for (int i = 0; i < n_slots; i++) {
-        c->slots.emplace_back(new Slot);
-        if (int32_t rc = alloc_slot(c.get(), *c->slots.back())) {
-            for (auto& s : c->slots) free_slot(*s);
+    for (int i = 0; i < n_groups; i++) {
+        c->groups.emplace_back(new Group);
+        if (int32_t rc = alloc_group(c.get(), *c->groups.back(), frames_per_group)) {
+            for (auto& s : c->groups) free_group(*s);
             cudaFree(c->d_prior);
             return rc;
         }
     }
     {
-        // workers: as many as there are cores to run host stages on, never more than slots
+        // workers only enqueue launch chains and collect results (device mesh stage): a few are enough; with the
+        // host stage every worker also runs lattice filters and triangulations, one per core pays off
         int cores = (int)std::thread::hardware_concurrency();
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
-        if (n_workers <= 0) n_workers = cores > 0 ? cores : 1;
+        if (n_workers <= 0) n_workers = c->mesh_device ? std::max(1, std::min(cores, (n_groups + 1) / 2)) : std::max(1, cores);
         if (const char* e = std::getenv("ELAS_B200_WORKERS")) n_workers = std::atoi(e);
-        n_workers = std::max(1, std::min(n_workers, n_slots));
+        n_workers = std::max(1, std::min(n_workers, n_groups));
     }
-    for (int i = 0; i < n_workers; i++) c->workers.emplace_back(worker_main, c.get(), i * n_slots / n_workers);
+    for (int i = 0; i < n_workers; i++) c->workers.emplace_back(worker_main, c.get(), i, n_workers);
     *out = c.release();
     return ELAS_B200_OK;
 }
@@ -892,20 +924,23 @@ void elas_b200_destroy(elas_b200_ctx* c)
     c->cv_work.notify_all();
     for (auto& t : c->workers) t.join();
     cudaSetDevice(c->device);
-    for (auto& s : c->slots) { cudaStreamSynchronize(s->stream); free_slot(*s); }
+    for (auto& s : c->groups) { cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->copy_stream); free_group(*s); }
     cudaFree(c->d_prior);
     cudaFree(c->d_flush);
     delete c;
 }
 
+int32_t elas_b200_frames_per_group(elas_b200_ctx* c) { return c && !c->groups.empty() ? c->groups[0]->cap : 0; }
+int32_t elas_b200_mesh_on_device(elas_b200_ctx* c) { return c && c->mesh_device ? 1 : 0; }
+
 int32_t elas_b200_process_ctx(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, const uint8_t* I2,
                               float* D1, float* D2, int32_t bytes_per_line)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size() || !I1 || !I2 || !D1 || !D2 || bytes_per_line < c->g.W)
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || !I1 || !I2 || !D1 || !D2 || bytes_per_line < c->g.W)
         return ELAS_B200_E_BAD_ARG;
     std::lock_guard<std::mutex> batch(c->batch_mu);
     CK(cudaSetDevice(c->device));
-    return run_frame(c, *c->slots[slot], I1, I2, D1, D2, bytes_per_line, false);
+    return run_frame(c, *c->groups[slot], I1, I2, D1, D2, bytes_per_line, false);
 }
 
 int32_t elas_b200_process_batch(elas_b200_ctx* c, int32_t n, const uint8_t* const* I1, const uint8_t* const* I2,
@@ -942,7 +977,7 @@ int32_t elas_b200_process(const elas_b200_params* p, const uint8_t* I1, const ui
 }
 
 // ---- D1's consumers in StereoThread::run ---------------------------------------
-static int32_t view_buffers(elas_b200_ctx* c, Slot& s)
+static int32_t view_buffers(elas_b200_ctx* c, Group& s)
 {
     if (!s.d_view) CK(cudaMalloc(&s.d_view, 5 * (size_t)c->g.W * c->g.H * sizeof(float)));
     return ELAS_B200_OK;
@@ -950,10 +985,10 @@ static int32_t view_buffers(elas_b200_ctx* c, Slot& s)
 
 int32_t elas_b200_colormap(elas_b200_ctx* c, int32_t slot, const float* D1, float* color)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size() || !color) return ELAS_B200_E_BAD_ARG;
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || !color) return ELAS_B200_E_BAD_ARG;
     std::lock_guard<std::mutex> batch(c->batch_mu);
     CK(cudaSetDevice(c->device));
-    Slot& s = *c->slots[slot];
+    Group& s = *c->groups[slot];
     if (int32_t rc = view_buffers(c, s)) return rc;
     const size_t nd = (size_t)c->g.Dw * c->g.Dh;
     const float* src = s.last_D1;
@@ -974,12 +1009,12 @@ int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, i
                             const float* D1, const elas_b200_view* view,
                             float* I, float* D, float* X, float* Y, float* Z)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size() || !view || !I || !D || !X || !Y || !Z) return ELAS_B200_E_BAD_ARG;
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || !view || !I || !D || !X || !Y || !Z) return ELAS_B200_E_BAD_ARG;
     if (c->p.subsampling) return ELAS_B200_E_UNSUPPORTED;            // createCurrentMap reads D1 at full resolution
     if (I1 && bytes_per_line < c->g.W) return ELAS_B200_E_BAD_ARG;
     std::lock_guard<std::mutex> batch(c->batch_mu);
     CK(cudaSetDevice(c->device));
-    Slot& s = *c->slots[slot];
+    Group& s = *c->groups[slot];
     if (int32_t rc = view_buffers(c, s)) return rc;
     const FrameGeom& g = c->g;
     const size_t n = (size_t)g.W * g.H;
@@ -990,7 +1025,7 @@ int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, i
         src = s.d_tmp;
     }
     if (!src) return ELAS_B200_E_BAD_ARG;
-    if (I1) { if (int32_t rc = copy_image_in(g, s.d_img[0], I1, bytes_per_line, s.stream)) return rc; }
+    if (I1) { if (int32_t rc = copy_image_in(c, s.d_img[0], I1, bytes_per_line, s.stream, nullptr)) return rc; }
     float* out[5] = {s.d_view, s.d_view + n, s.d_view + 2 * n, s.d_view + 3 * n, s.d_view + 4 * n};
     launch_reproject(g.W, g.H, s.d_img[0], g.bpl, src, *view, out[0], out[1], out[2], out[3], out[4], s.stream);
     float* user[5] = {I, D, X, Y, Z};
@@ -1002,10 +1037,10 @@ int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, i
 
 int32_t elas_b200_time_view(elas_b200_ctx* c, int32_t slot, int32_t iters, float ms_out[2])
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size() || iters < 1 || !ms_out || c->p.subsampling) return ELAS_B200_E_BAD_ARG;
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || iters < 1 || !ms_out || c->p.subsampling) return ELAS_B200_E_BAD_ARG;
     std::lock_guard<std::mutex> batch(c->batch_mu);
     CK(cudaSetDevice(c->device));
-    Slot& s = *c->slots[slot];
+    Group& s = *c->groups[slot];
     if (!s.last_D1) return ELAS_B200_E_BAD_ARG;
     if (int32_t rc = view_buffers(c, s)) return rc;
     const FrameGeom& g = c->g;
@@ -1032,16 +1067,16 @@ int32_t elas_b200_time_view(elas_b200_ctx* c, int32_t slot, int32_t iters, float
 
 int32_t elas_b200_stage_capture(elas_b200_ctx* c, int32_t slot, int32_t enable)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size()) return ELAS_B200_E_BAD_ARG;
-    c->slots[slot]->capture = enable != 0;
-    if (!enable) c->slots[slot]->stages.clear();
+    if (!c || slot < 0 || slot >= (int)c->groups.size()) return ELAS_B200_E_BAD_ARG;
+    c->groups[slot]->capture = enable != 0;
+    if (!enable) c->groups[slot]->stages.clear();
     return ELAS_B200_OK;
 }
 
 static const std::vector<uint8_t>* find_stage(elas_b200_ctx* c, int32_t slot, const char* name, std::vector<uint8_t>& scratch)
 {
-    if (!c || !name || slot < 0 || slot >= (int)c->slots.size()) return nullptr;
-    Slot& s = *c->slots[slot];
+    if (!c || !name || slot < 0 || slot >= (int)c->groups.size()) return nullptr;
+    Group& s = *c->groups[slot];
     const std::string n(name);
     if (n == "grid1" || n == "grid2") {
         auto it = s.stages.find(n + "_bits");
@@ -1097,10 +1132,10 @@ int64_t elas_b200_launch_count(elas_b200_ctx* c)
 int32_t elas_b200_host_times(elas_b200_ctx* c, double ms_out[5], int64_t* frames, int32_t reset)
 {
     if (!c || !ms_out) return ELAS_B200_E_BAD_ARG;
-    ms_out[0] = c->ns_submit_a * 1e-6; ms_out[1] = c->ns_wait_a * 1e-6; ms_out[2] = c->ns_host * 1e-6;
-    ms_out[3] = c->ns_submit_b * 1e-6; ms_out[4] = c->ns_wait_b * 1e-6;
+    ms_out[0] = c->ns_submit * 1e-6; ms_out[1] = c->ns_wait * 1e-6; ms_out[2] = c->ns_host * 1e-6;
+    ms_out[3] = c->ns_finish * 1e-6; ms_out[4] = 0.0;
     if (frames) *frames = c->frames;
-    if (reset) { c->ns_submit_a = 0; c->ns_wait_a = 0; c->ns_host = 0; c->ns_submit_b = 0; c->ns_wait_b = 0; c->frames = 0; }
+    if (reset) { c->ns_submit = 0; c->ns_wait = 0; c->ns_host = 0; c->ns_finish = 0; c->frames = 0; }
     return ELAS_B200_OK;
 }
 
@@ -1113,8 +1148,8 @@ int32_t elas_b200_stage_timing(elas_b200_ctx* c, int32_t enable)
 
 int32_t elas_b200_stage_times(elas_b200_ctx* c, int32_t slot, const char** names_out, float* ms_out, int32_t cap)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size()) return ELAS_B200_E_BAD_ARG;
-    Slot& s = *c->slots[slot];
+    if (!c || slot < 0 || slot >= (int)c->groups.size()) return ELAS_B200_E_BAD_ARG;
+    Group& s = *c->groups[slot];
     int n = 0;
     for (auto& e : s.timer.last) {
         if (n >= cap) break;
@@ -1128,22 +1163,31 @@ int32_t elas_b200_stage_times(elas_b200_ctx* c, int32_t slot, const char** names
 
 float elas_b200_time_matching(elas_b200_ctx* c, int32_t slot, int32_t iters, int32_t flush_l2)
 {
-    if (!c || slot < 0 || slot >= (int)c->slots.size() || iters < 1) return -1.f;
-    Slot& s = *c->slots[slot];
-    if (!s.tables_valid) return -1.f;
+    return elas_b200_time_matching_ex(c, slot, iters, flush_l2, nullptr);
+}
+
+float elas_b200_time_matching_ex(elas_b200_ctx* c, int32_t slot, int32_t iters, int32_t flush_l2, int32_t* frames_per_launch)
+{
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || iters < 1) return -1.f;
+    Group& s = *c->groups[slot];
+    if (!s.tables_valid || s.last_n < 1) return -1.f;
     std::lock_guard<std::mutex> batch(c->batch_mu);
     if (cudaSetDevice(c->device) != cudaSuccess) return -1.f;
     if (flush_l2 && !c->d_flush) {
         c->flush_bytes = (size_t)512 << 20;       // 4x the 126 MB L2
         if (cudaMalloc(&c->d_flush, c->flush_bytes) != cudaSuccess) return -1.f;
     }
+    if (frames_per_launch) *frames_per_launch = s.last_n;
+    // K7 writes the raw maps; plane 0 doubles as the finished left map of the group's last chain, which
+    // elas_b200_colormap / _reproject may no longer use afterwards
+    s.last_D1 = nullptr;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     double total = 0;
     for (int i = 0; i < iters; i++) {
         if (flush_l2) cudaMemsetAsync(c->d_flush, i & 0xff, c->flush_bytes, s.stream);
         cudaEventRecord(e0, s.stream);
-        launch_matching(c->g, c->p, match_buffers(c, s), 1, s.map_tag << c->map_tag_shift, c->map_tag_shift, s.stream);
+        launch_matching(c->g, c->p, match_buffers(c, s), s.last_n, s.map_tag << c->map_tag_shift, c->map_tag_shift, s.stream);
         cudaEventRecord(e1, s.stream);
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { total = -1; break; }
         float ms = 0;

@@ -45,15 +45,16 @@ __device__ __forceinline__ Win load_win(const uint8_t* row, int idx)      // idx
 
 __global__ void __launch_bounds__(256)
 k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint8_t* __restrict__ img2,
-             uint4* __restrict__ desc1, uint4* __restrict__ desc2)
+             uint4* __restrict__ desc1, uint4* __restrict__ desc2, size_t img_stride, size_t desc_stride)
 {
     __shared__ __align__(16) uint8_t sI[IH][IW];
     __shared__ __align__(16) uint8_t sU[UH][UP];
     __shared__ __align__(16) uint8_t sV[UH][UP];
     __shared__ uint4 sO[TH][TW];               // finished descriptors, 16-byte chunks XOR-swizzled within 128-byte lines
 
-    const uint8_t* __restrict__ img = blockIdx.z ? img2 : img1;
-    uint4* __restrict__ desc = blockIdx.z ? desc2 : desc1;
+    // blockIdx.z = 2 * frame + image
+    const uint8_t* __restrict__ img = ((blockIdx.z & 1) ? img2 : img1) + (size_t)(blockIdx.z >> 1) * img_stride;
+    uint4* __restrict__ desc = ((blockIdx.z & 1) ? desc2 : desc1) + (size_t)(blockIdx.z >> 1) * desc_stride;
     const int u0 = blockIdx.x * TW, v0 = blockIdx.y * TH;
     const int tid = threadIdx.x;
 
@@ -145,10 +146,10 @@ k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint
 }  // namespace
 
 void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const uint8_t* img2,
-                       uint4* desc1, uint4* desc2, cudaStream_t s)
+                       uint4* desc1, uint4* desc2, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
-    dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2);
-    k_descriptor<<<grid, 256, 0, s>>>(g, half, img1, img2, desc1, desc2);
+    dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2 * n_frames);
+    k_descriptor<<<grid, 256, 0, s>>>(g, half, img1, img2, desc1, desc2, st.img, st.desc);
     count_launch();
 }
 

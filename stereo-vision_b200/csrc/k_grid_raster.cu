@@ -6,6 +6,8 @@
 // kept here as a bitmask of disp_max+1 bits per cell (32 B): bit d set <=> d is in the list.  The
 // ascending list order the matching kernel needs is the order of the set bits.  The expansion back to
 // the reference layout (for parity checks) is done on the host by the stage-dump hook.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace elasb {
@@ -179,7 +181,8 @@ __device__ __forceinline__ void planes_body(int gid, const int32_t* __restrict__
     r.uA = (int)Au; r.uB = (int)Bu; r.uC = (int)Cu;
     r.valid = (double)fabsf(r.pa) < 0.7 && (double)fabsf(pd) < 0.7;     // :1072
     r.pad0 = min(sv[0], min(sv[1], sv[2]));     // smallest corner row: anchor of k_raster's row bands
-    r.pad1 = r.pad2 = 0;
+    r.pad1 = max(sv[0], max(sv[1], sv[2]));     // largest corner row (overflow triangles walk all their bands)
+    r.pad2 = 0;
     (right_image ? out2 : out1)[i] = r;
 }
 
@@ -197,16 +200,12 @@ __device__ __forceinline__ void planes_body(int gid, const int32_t* __restrict__
 // Map entries are (frame tag << tag_shift) | triangle index: a new frame's entries compare greater than
 // anything an earlier frame left behind, so the maps are never cleared between frames (the matching
 // kernel ignores entries whose tag is not the current one).
-__device__ __forceinline__ void raster_body(int unit, const FrameGeom& g, int subsampling,
+__device__ __forceinline__ void raster_unit(int t, int img, int chunk, int band, const FrameGeom& g, int subsampling,
                                             const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
-                                            const int2* __restrict__ units, int n_units,
                                             int32_t* __restrict__ map1, int32_t* __restrict__ map2, int tag_bits)
 {
     const int lane = threadIdx.x & 31;
     const int pitch = map_pitch(g);
-    if (unit >= n_units) return;
-    const int2 w = __ldg(units + unit);
-    const int t = w.x & 0x3FFFFFFF, img = (w.x >> 30) & 1, chunk = w.y & 0xFFFF, band = w.y >> 16;
     const TriRaster* tri = (img ? tri2 : tri1) + t;
     int32_t* map = img ? map2 : map1;
     const float4 e0 = __ldg(reinterpret_cast<const float4*>(tri));          // ACa, ACb, ABa, ABb
@@ -231,7 +230,7 @@ __device__ __forceinline__ void raster_body(int unit, const FrameGeom& g, int su
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
         vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
     }
-    const int v_anchor = max(__ldg(&tri->pad0) - 1, 0);                      // min corner row - 1 (host_stage.cc units)
+    const int v_anchor = max(__ldg(&tri->pad0) - 1, 0);                      // min corner row - 1 (mesh_core.h raster_box)
     const int b_lo = v_anchor + band * kRasterBandRows, b_hi = b_lo + kRasterBandRows;
     const int vlo = max(vmin, b_lo), vhi = min(vmax, b_hi);
     int32_t* col = map + u;
@@ -240,63 +239,114 @@ __device__ __forceinline__ void raster_body(int unit, const FrameGeom& g, int su
     }
 }
 
-// K5 + the scatter half of K6 in one launch: blocks [0, plane_blocks) fit planes, the rest scatter
-// support points into the candidate-grid bitmasks.  Both read only the uploaded tables.
+// one warp: work item w of a frame = a listed unit of the left image, of the right image, or a whole overflow triangle
+__device__ __forceinline__ void raster_item(int w, const FrameHeader& h, const FrameGeom& g, int subsampling,
+                                            const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
+                                            const int2* __restrict__ units1, const int2* __restrict__ units2,
+                                            int32_t* __restrict__ map1, int32_t* __restrict__ map2, int tag_bits)
+{
+    if (w < h.n_units[0] + h.n_units[1]) {
+        const int2 u = w < h.n_units[0] ? __ldg(units1 + w) : __ldg(units2 + (w - h.n_units[0]));
+        raster_unit(u.x & 0x3FFFFFFF, (u.x >> 30) & 1, u.y & 0xFFFF, u.y >> 16, g, subsampling, tri1, tri2, map1, map2, tag_bits);
+        return;
+    }
+    w -= h.n_units[0] + h.n_units[1];
+    const int ovf0 = h.n_tri[0] - h.ovf_from[0];
+    const int img = w >= ovf0;
+    const int t = img ? h.ovf_from[1] + (w - ovf0) : h.ovf_from[0] + w;
+    const TriRaster* tri = (img ? tri2 : tri1) + t;
+    const int uA = __ldg(&tri->uA), uC = __ldg(&tri->uC), v0 = __ldg(&tri->pad0), v1 = __ldg(&tri->pad1);
+    const int chunks = (min(uC, g.W) - max(uA, 0) + 31) / 32;
+    const int bands = (min(v1 + 1, g.H) - max(v0 - 1, 0) + kRasterBandRows - 1) / kRasterBandRows;
+    for (int ch = 0; ch < chunks; ch++)
+        for (int bd = 0; bd < bands; bd++)
+            raster_unit(t, img, ch, bd, g, subsampling, tri1, tri2, map1, map2, tag_bits);
+}
+
+// K5 + the scatter half of K6 in one launch, frames of a group in blockIdx.y.  The numbers of support points and
+// triangles come from the frame's header in device memory (the mesh stage runs on the GPU), so the grid is a fixed
+// size and every block strides over the work: items [0, P) fit planes (two threads per triangle, whole warps),
+// items [P, P + n) scatter support points into the candidate-grid bitmasks.  Both read only the frame's tables.
 constexpr int kSetupThreads = 128;
 __global__ void __launch_bounds__(kSetupThreads)
-k_planes_scatter(FrameGeom g, elas_b200_params p, int plane_blocks, const int32_t* __restrict__ support, int n,
-                 const int32_t* __restrict__ tri1, int nt1, const int32_t* __restrict__ tri2, int nt2,
+k_planes_scatter(FrameGeom g, elas_b200_params p, const FrameHeader* __restrict__ hdr, const int32_t* __restrict__ support,
+                 const int32_t* __restrict__ tri1, const int32_t* __restrict__ tri2,
                  TriRaster* __restrict__ out1, TriRaster* __restrict__ out2, float* __restrict__ planes1,
-                 float* __restrict__ planes2, uint32_t* __restrict__ scratch)
+                 float* __restrict__ planes2, uint32_t* __restrict__ scratch, GroupStrides st)
 {
-    if ((int)blockIdx.x < plane_blocks)
-        planes_body(blockIdx.x * kSetupThreads + threadIdx.x, support, tri1, nt1, tri2, nt2, out1, out2, planes1, planes2);
-    else
-        grid_scatter_body((blockIdx.x - plane_blocks) * kSetupThreads + threadIdx.x, g, p, support, n, scratch);
+    const int f = blockIdx.y;
+    const FrameHeader h = hdr[f];
+    if (h.n_support < 3) return;                                           // elas.cpp:69-75
+    support += (size_t)f * st.support;
+    tri1 += (size_t)f * st.tri; tri2 += (size_t)f * st.tri;
+    out1 += (size_t)f * st.traster; out2 += (size_t)f * st.traster;
+    planes1 += (size_t)f * st.planes; planes2 += (size_t)f * st.planes;
+    scratch += (size_t)f * st.scratch;
+    const int plane_items = (2 * (h.n_tri[0] + h.n_tri[1]) + 31) & ~31;
+    const int total = (plane_items + h.n_support + 31) & ~31;
+    for (int w = blockIdx.x * kSetupThreads + threadIdx.x; w < total; w += gridDim.x * kSetupThreads) {
+        if (w < plane_items) planes_body(w, support, tri1, h.n_tri[0], tri2, h.n_tri[1], out1, out2, planes1, planes2);
+        else grid_scatter_body(w - plane_items, g, p, support, h.n_support, scratch);
+    }
 }
 
 // The diffusion half of K6 + scan conversion in one launch: blocks [0, diffuse_blocks) turn the scatter
-// planes into per-cell bitmasks and lists, the rest rasterise triangle work units (8 per block).
+// planes into per-cell bitmasks and lists, the rest scan-convert triangle work items (one per warp, strided).
 constexpr int kRasterThreads = 256;
 __global__ void __launch_bounds__(kRasterThreads)
-k_diffuse_raster(FrameGeom g, int subsampling, int diffuse_blocks, const uint32_t* __restrict__ scratch,
-                 uint32_t* __restrict__ scratch_next, uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
+k_diffuse_raster(FrameGeom g, int subsampling, int diffuse_blocks, const FrameHeader* __restrict__ hdr,
+                 const uint32_t* __restrict__ scratch, uint32_t* __restrict__ scratch_next,
+                 uint32_t* __restrict__ grid1, uint32_t* __restrict__ grid2,
                  uint16_t* __restrict__ lists1, uint16_t* __restrict__ lists2,
                  const TriRaster* __restrict__ tri1, const TriRaster* __restrict__ tri2,
-                 const int2* __restrict__ units, int n_units, int32_t* __restrict__ map1, int32_t* __restrict__ map2,
-                 int tag_bits)
+                 const int2* __restrict__ units1, const int2* __restrict__ units2,
+                 int32_t* __restrict__ map1, int32_t* __restrict__ map2, int tag_bits, GroupStrides st)
 {
-    if ((int)blockIdx.x < diffuse_blocks)
-        grid_diffuse_body(blockIdx.x * kRasterThreads + threadIdx.x, g, scratch, scratch_next, grid1, grid2, lists1, lists2);
-    else
-        raster_body((blockIdx.x - diffuse_blocks) * (kRasterThreads >> 5) + (threadIdx.x >> 5), g, subsampling,
-                    tri1, tri2, units, n_units, map1, map2, tag_bits);
+    const int f = blockIdx.y;
+    if ((int)blockIdx.x < diffuse_blocks) {
+        grid_diffuse_body(blockIdx.x * kRasterThreads + threadIdx.x, g, scratch + (size_t)f * st.scratch,
+                          scratch_next + (size_t)f * st.scratch, grid1 + (size_t)f * st.grid, grid2 + (size_t)f * st.grid,
+                          lists1 + (size_t)f * st.lists, lists2 + (size_t)f * st.lists);
+        return;
+    }
+    const FrameHeader h = hdr[f];
+    if (h.n_support < 3) return;
+    const int items = h.n_units[0] + h.n_units[1] + (h.n_tri[0] - h.ovf_from[0]) + (h.n_tri[1] - h.ovf_from[1]);
+    const int warps = (gridDim.x - diffuse_blocks) * (kRasterThreads >> 5);
+    for (int w = (blockIdx.x - diffuse_blocks) * (kRasterThreads >> 5) + (threadIdx.x >> 5); w < items; w += warps)
+        raster_item(w, h, g, subsampling, tri1 + (size_t)f * st.traster, tri2 + (size_t)f * st.traster,
+                    units1 + (size_t)f * (st.units / 2), units2 + (size_t)f * (st.units / 2),
+                    map1 + (size_t)f * st.map, map2 + (size_t)f * st.map, tag_bits);
 }
 
 }  // namespace
 
-void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const int32_t* support, int n_support,
-                           const int32_t* tri1, int nt1, const int32_t* tri2, int nt2, TriRaster* out1,
-                           TriRaster* out2, float* planes1, float* planes2, uint32_t* scratch, cudaStream_t s)
+void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const FrameHeader* hdr, const int32_t* support,
+                           const int32_t* tri1, const int32_t* tri2, TriRaster* out1, TriRaster* out2,
+                           float* planes1, float* planes2, uint32_t* scratch, const GroupStrides& st, int n_frames,
+                           cudaStream_t s)
 {
-    const int plane_blocks = (2 * (nt1 + nt2) + kSetupThreads - 1) / kSetupThreads;
-    const int scatter_blocks = (n_support + kSetupThreads - 1) / kSetupThreads;
-    if (plane_blocks + scatter_blocks == 0) return;
-    k_planes_scatter<<<plane_blocks + scatter_blocks, kSetupThreads, 0, s>>>(g, p, plane_blocks, support, n_support, tri1, nt1,
-                                                                             tri2, nt2, out1, out2, planes1, planes2, scratch);
+    // enough threads for a densely textured frame (a third of the lattice survives the filters at most:
+    // ~2 triangles per point per image, 2 threads per triangle), strided beyond that
+    const int expect = 3 * g.Wc * g.Hc;
+    const int blocks = std::max(8, std::min(1024, (expect + kSetupThreads - 1) / kSetupThreads));
+    k_planes_scatter<<<dim3(blocks, n_frames), kSetupThreads, 0, s>>>(g, p, hdr, support, tri1, tri2, out1, out2, planes1,
+                                                                      planes2, scratch, st);
     count_launch();
 }
 
-void launch_diffuse_raster(const FrameGeom& g, int subsampling, const uint32_t* scratch, uint32_t* scratch_next,
-                           uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
-                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units, int n_units,
-                           int32_t* map1, int32_t* map2, int tag_bits, cudaStream_t s)
+void launch_diffuse_raster(const FrameGeom& g, int subsampling, const FrameHeader* hdr, const uint32_t* scratch,
+                           uint32_t* scratch_next, uint32_t* grid1, uint32_t* grid2, uint16_t* lists1, uint16_t* lists2,
+                           const TriRaster* tri1, const TriRaster* tri2, const int32_t* units1, const int32_t* units2,
+                           int32_t* map1, int32_t* map2, int tag_bits, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     const int diffuse_blocks = (2 * g.gw * g.gh + kRasterThreads - 1) / kRasterThreads;
-    const int raster_blocks = (n_units + (kRasterThreads >> 5) - 1) / (kRasterThreads >> 5);
-    k_diffuse_raster<<<diffuse_blocks + raster_blocks, kRasterThreads, 0, s>>>(
-        g, subsampling, diffuse_blocks, scratch, scratch_next, grid1, grid2, lists1, lists2, tri1, tri2,
-        reinterpret_cast<const int2*>(units), n_units, map1, map2, tag_bits);
+    // one warp per ~32x32 piece of the image and image side is plenty of parallelism; more work is strided
+    const int pieces = 2 * ((g.W + 31) / 32) * ((g.H + kRasterBandRows - 1) / kRasterBandRows);
+    const int raster_blocks = std::max(16, std::min(2048, (2 * pieces + (kRasterThreads >> 5) - 1) / (kRasterThreads >> 5)));
+    k_diffuse_raster<<<dim3(diffuse_blocks + raster_blocks, n_frames), kRasterThreads, 0, s>>>(
+        g, subsampling, diffuse_blocks, hdr, scratch, scratch_next, grid1, grid2, lists1, lists2, tri1, tri2,
+        reinterpret_cast<const int2*>(units1), reinterpret_cast<const int2*>(units2), map1, map2, tag_bits, st);
     count_launch();
 }
 

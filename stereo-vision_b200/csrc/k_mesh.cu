@@ -1,0 +1,252 @@
+// Mesh stage on the device: lattice filters + support list (k_lattice, one CTA per frame) and the
+// Triangle-compatible Delaunay triangulation + scan-conversion work units (k_delaunay, one CTA per frame and
+// image).  The algorithms are the phases of mesh_core.h; this file adds what a CTA needs around them:
+// barriers, prefix sums, a bitonic sort, and the choice between shared memory and a global scratch area.
+//
+// Both kernels are latency-bound single-CTA programs (tens of microseconds on < 200 KB): they exist so that a
+// frame never leaves the GPU between the support search and the dense matching -- no host round trip, no CPU
+// work per frame -- and they overlap with the bandwidth-heavy kernels of other frame groups.
+//
+// Reference: elas.cpp:174-279, :496-517 (k_lattice); :534-600 with triangle.cpp:5446-6217, :7800-7853 (k_delaunay).
+#include "common.cuh"
+#include "mesh_core.h"
+
+namespace elasb {
+namespace {
+
+constexpr int kMeshThreads = 1024;
+
+// in-place inclusive prefix sum of data[0..m) by the whole CTA; warp_sums = 32 ints of shared memory
+__device__ void block_scan_inclusive(int32_t* data, int m, int32_t* warp_sums)
+{
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    const int chunk = (m + T - 1) / T;
+    const int lo = min(tid * chunk, m), hi = min(lo + chunk, m);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += data[i];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < (T >> 5) ? warp_sums[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off) wi += v;
+        }
+        warp_sums[lane] = wi - w;                    // exclusive
+    }
+    __syncthreads();
+    int run = warp_sums[warp] + incl - sum;
+    for (int i = lo; i < hi; i++) { run += data[i]; data[i] = run; }
+    __syncthreads();
+}
+
+// ascending bitonic sort of npad (a power of two) 64-bit keys by the whole CTA
+__device__ void block_bitonic_sort(unsigned long long* k, int npad)
+{
+    for (int size = 2; size <= npad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (npad >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+        }
+    __syncthreads();
+}
+
+struct LatticeArgs {
+    int Wc, Hc, step, win, thr, need;
+    const int16_t* dcan_raw;     // K2's lattice, [frames][Hc][Wc]
+    int16_t* dcan;               // after all three filters
+    int16_t* dcan_incon;         // after the inconsistency filter only (stage dump; may be null)
+    int32_t* support;            // [frames][support_cap][3]
+    FrameHeader* hdr;
+    size_t dcan_stride, support_stride;
+};
+
+__global__ void __launch_bounds__(kMeshThreads)
+k_lattice(const LatticeArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int32_t warp_sums[32];
+    const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    mesh::Lattice L{a.Wc, a.Hc, a.Wc + 2 * mesh::kPadC, a.step, reinterpret_cast<int16_t*>(smem_raw)};
+    int32_t* col = reinterpret_cast<int32_t*>(smem_raw + (((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15));   // [Wc + 1]
+    const int16_t* raw = a.dcan_raw + (size_t)f * a.dcan_stride;
+    int16_t* out = a.dcan + (size_t)f * a.dcan_stride;
+    int32_t* support = a.support + (size_t)f * a.support_stride;
+
+    mesh::lattice_load(L, raw, tid, T);
+    __syncthreads();
+    while (__syncthreads_or(mesh::incon_round(L, a.win, a.thr, a.need, tid, T))) {}
+    mesh::incon_finish(L, a.dcan_incon ? a.dcan_incon + (size_t)f * a.dcan_stride : nullptr, tid, T);
+    __syncthreads();
+    mesh::redundant_pass(L, true, tid, T);          // elas.cpp:501
+    __syncthreads();
+    mesh::redundant_pass(L, false, tid, T);         // elas.cpp:502
+    __syncthreads();
+    mesh::support_count(L, col + 1, tid, T);
+    if (tid == 0) col[0] = 0;
+    block_scan_inclusive(col + 1, a.Wc, warp_sums);  // col[uc] = survivors in columns < uc
+    mesh::support_write(L, col, support, tid, T);
+    mesh::lattice_store(L, out, tid, T);
+    if (tid == 0) {
+        FrameHeader h{};
+        h.n_support = col[a.Wc];
+        a.hdr[f] = h;
+    }
+}
+
+struct DelaunayArgs {
+    int W, H, unit_cap, smem_ints;
+    const int32_t* support;
+    int32_t* tri[2];             // [frames][tri_cap][3]
+    int32_t* units[2];           // [frames][unit_cap][2]
+    FrameHeader* hdr;
+    int32_t* scratch;            // [frames][2][mesh_scratch]: used when a triangulation does not fit shared memory
+    size_t support_stride, tri_stride, units_stride, scratch_stride;
+};
+
+__global__ void __launch_bounds__(kMeshThreads)
+k_delaunay(const DelaunayArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int32_t warp_sums[32];
+    const int img = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+    FrameHeader* hdr = a.hdr + f;
+    const int n = hdr->n_support;
+    if (n < 3) {                                                           // elas.cpp:69-75
+        if (tid == 0) { hdr->n_tri[img] = 0; hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; }
+        return;
+    }
+    // working memory, 17 n ints: shared memory when it fits, else this (frame, image)'s global scratch
+    int32_t* mem = 17 * n + 2 <= a.smem_ints ? reinterpret_cast<int32_t*>(smem_raw)
+                                             : a.scratch + ((size_t)f * 2 + img) * a.scratch_stride;
+    int32_t* x = mem; int32_t* y = mem + n; int32_t* s = mem + 2 * n; int32_t* hull = mem + 3 * n;
+    int32_t* nbr = mem + 5 * n; int32_t* vtx = mem + 11 * n;
+    const int32_t* support = a.support + (size_t)f * a.support_stride;
+    for (int i = tid; i < n; i += T) {                                     // elas.cpp:543-559
+        x[i] = img ? support[3 * i] - support[3 * i + 2] : support[3 * i];
+        y[i] = support[3 * i + 1];
+    }
+    // ---- the two sorted id lists: (x,y) and (y,x), keys are unique (no duplicate points on this path) -----
+    int32_t* R = nbr;                                                      // 12 n ints free until the triangulation starts
+    mesh::Order o{n, s, R, R + n, R + 2 * n, R + 3 * n, R + 4 * n, R + 5 * n, R + 6 * n, R + 7 * n};
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(mem + ((5 * n + 8 * n + 1) & ~1));
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    __syncthreads();
+    int dup = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = tid; i < npad; i += T)
+            keys[i] = i < n ? ((unsigned long long)(pass ? ((uint32_t)y[i] << 16) | (uint32_t)x[i] : ((uint32_t)x[i] << 16) | (uint32_t)y[i]) << 32) | (uint32_t)i
+                            : ~0ull;
+        block_bitonic_sort(keys, npad);
+        for (int i = tid; i < n; i += T) {
+            (pass ? o.ys : o.xs)[i] = (int32_t)(uint32_t)keys[i];
+            if (pass == 0 && i > 0 && (keys[i] >> 32) == (keys[i - 1] >> 32)) dup = 1;
+        }
+        __syncthreads();
+    }
+    if (__syncthreads_or(dup)) {
+        // two support points on one pixel of this image: Triangle keeps whichever its randomised sort meets first
+        // (triangle.cpp:6180-6195); contexts whose parameters allow that use the host stage instead
+        if (tid == 0) { hdr->n_tri[img] = 0; hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; hdr->status = ELAS_B200_E_UNSUPPORTED; }
+        return;
+    }
+    // ---- alternating-cut vertex order (triangle.cpp:6197-6206) ---------------------------------------------
+    mesh::order_init(o, tid, T);
+    __syncthreads();
+    for (int axis = 0;; axis ^= 1) {
+        if (!__syncthreads_or(mesh::order_flags(o, axis, tid, T))) break;
+        for (int i = tid; i < n; i += T) o.scan[i] = o.side[i];
+        block_scan_inclusive(o.scan, n, warp_sums);
+        mesh::order_scatter(o, axis, tid, T);
+        __syncthreads();
+        mesh::order_commit(o, axis, tid, T);
+        __syncthreads();
+    }
+    // ---- divide and conquer, deepest level first ---------------------------------------------------------------
+    mesh::Mesh m{n, x, y, s, nbr, vtx, hull};
+    for (int depth = mesh::tree_depth(n); depth >= 0; depth--) {
+        __syncthreads();
+        mesh::triangulate_depth(m, depth, tid, T);
+    }
+    __syncthreads();
+    // ---- elements in pool order without the ghosts (triangle.cpp:7834-7853) ----------------------------------------
+    const int pool = 2 * n - 2;
+    int32_t* flag = nbr; int32_t* fscan = nbr + 2 * n; int32_t* count = nbr + 4 * n;     // the links are dead now
+    mesh::real_flags(m, flag, tid, T);
+    __syncthreads();
+    for (int i = tid; i < pool; i += T) fscan[i] = flag[i];
+    block_scan_inclusive(fscan, pool, warp_sums);
+    const int nt = fscan[pool - 1];
+    int32_t* tri = a.tri[img] + (size_t)f * a.tri_stride;
+    mesh::write_triangles(m, flag, fscan, tri, tid, T);
+    __syncthreads();
+    // ---- scan-conversion work units ----------------------------------------------------------------------------------
+    mesh::unit_counts(x, y, tri, nt, a.W, a.H, kRasterBandRows, count, tid, T);
+    __syncthreads();
+    int32_t* cscan = flag;
+    for (int i = tid; i < nt; i += T) cscan[i] = count[i];
+    block_scan_inclusive(cscan, nt, warp_sums);
+    mesh::write_units(x, y, tri, nt, a.W, a.H, kRasterBandRows, img, count, cscan, a.unit_cap,
+                      a.units[img] + (size_t)f * a.units_stride, tid, T);
+    // the prefix sums are monotone: the triangles that do not fit are a suffix [ovf_from, nt)
+    if (tid == 0) { hdr->n_tri[img] = nt; if (nt == 0 || cscan[0] > a.unit_cap) { hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; } }
+    for (int t = tid; t < nt; t += T)
+        if (cscan[t] <= a.unit_cap && (t == nt - 1 || cscan[t + 1] > a.unit_cap)) { hdr->n_units[img] = cscan[t]; hdr->ovf_from[img] = t + 1; }
+}
+
+}  // namespace
+
+size_t lattice_smem_bytes(const FrameGeom& g)
+{
+    return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + ((size_t)g.Wc + 1) * 4;
+}
+
+// parameters / sizes the device mesh stage handles; everything else takes the host stage (host_stage.cc)
+bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p)
+{
+    return !p.add_corners &&                                  // elas.cpp:283-318 appends points outside the lattice
+           2 * p.lr_threshold < g.step &&                     // no two support points on one right-image pixel
+           p.incon_window_size <= mesh::kPadC && p.incon_window_size >= 0 &&
+           p.disp_max < mesh::kRemoved && g.W < 16384 && g.H < 16384 &&
+           lattice_smem_bytes(g) <= 220 * 1024;
+}
+
+void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
+                    int32_t* support, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s)
+{
+    static unsigned long long optin = 0;
+    if (ensure_dynamic_smem(k_lattice, 224 * 1024, &optin) != cudaSuccess) return;
+    LatticeArgs a{g.Wc, g.Hc, g.step, p.incon_window_size, p.incon_threshold, p.incon_min_support,
+                  dcan_raw, dcan, dcan_incon, support, hdr, st.dcan, st.support};
+    k_lattice<<<n_frames, kMeshThreads, lattice_smem_bytes(g), s>>>(a);
+    count_launch();
+}
+
+void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, int32_t* tri2, int32_t* units1, int32_t* units2,
+                     int unit_cap, FrameHeader* hdr, int32_t* scratch, const GroupStrides& st, int n_frames, cudaStream_t s)
+{
+    static unsigned long long optin = 0;
+    constexpr int kSmem = 200 * 1024;
+    if (ensure_dynamic_smem(k_delaunay, kSmem, &optin) != cudaSuccess) return;
+    DelaunayArgs a{g.W, g.H, unit_cap, kSmem / 4, support, {tri1, tri2}, {units1, units2}, hdr, scratch,
+                   st.support, st.tri, st.units, st.mesh_scratch};
+    k_delaunay<<<dim3(2, n_frames), kMeshThreads, kSmem, s>>>(a);
+    count_launch();
+}
+
+}  // namespace elasb

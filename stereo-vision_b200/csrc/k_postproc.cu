@@ -18,10 +18,12 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 __global__ void k_lr_check(int Dw, int Dh, int subsampling, float lr_threshold,
                            const float* __restrict__ D1, const float* __restrict__ D2,
-                           float* __restrict__ O1, float* __restrict__ O2)
+                           float* __restrict__ O1, OutTable O2_tab, size_t D_stride)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= Dw || v >= Dh) return;
+    D1 += blockIdx.z * D_stride; D2 += blockIdx.z * D_stride; O1 += blockIdx.z * D_stride;
+    float* __restrict__ O2 = O2_tab.p[blockIdx.z];
     const size_t row = (size_t)v * Dw, a = row + u;
     const float d1 = D1[a], d2 = D2[a];
     const float w1 = subsampling ? __fsub_rn((float)u, __fmul_rn(d1, 0.5f)) : __fsub_rn((float)u, d1);  // :1152-1161
@@ -121,11 +123,12 @@ __device__ __forceinline__ void label_row_runs(const float* row, int Dw, int bas
 }
 
 __global__ void __launch_bounds__(256)
-k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size)
+k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size, size_t D_stride)
 {
     __shared__ int warp_last[8];
     __shared__ int carry_s;
     const int v = blockIdx.x;
+    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
     label_row_runs(D + (size_t)v * Dw, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
 }
 
@@ -136,14 +139,20 @@ k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__
 __global__ void __launch_bounds__(256)
 k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
           const float* __restrict__ D1, const float* __restrict__ D2,
-          float* __restrict__ O1, float* __restrict__ O2, int32_t* __restrict__ parent, int32_t* __restrict__ size,
-          int16_t* __restrict__ O2_i16)      // optional: O2 narrowed (exact: raw integer disparities or -10)
+          float* __restrict__ O1, OutTable O2_tab, int32_t* __restrict__ parent, int32_t* __restrict__ size,
+          int16_t* __restrict__ O2_i16,      // optional: O2 narrowed (exact: raw integer disparities or -10)
+          size_t D_stride)
 {
     extern __shared__ float s_rows[];          // [3][Dw]: raw D1 row, raw D2 row, checked D1 row
     __shared__ int warp_last[8];
     __shared__ int carry_s;
     float* r1 = s_rows; float* r2 = s_rows + Dw; float* c1 = s_rows + 2 * Dw;
     const int v = blockIdx.x;
+    // blockIdx.y = frame of the group
+    D1 += blockIdx.y * D_stride; D2 += blockIdx.y * D_stride; O1 += blockIdx.y * D_stride;
+    parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
+    if (O2_i16) O2_i16 += blockIdx.y * D_stride;
+    float* __restrict__ O2 = O2_tab.p[blockIdx.y];
     const size_t row = (size_t)v * Dw;
     for (int u = threadIdx.x; u < Dw; u += 256) { r1[u] = D1[row + u]; r2[u] = D2[row + u]; }
     __syncthreads();
@@ -171,9 +180,10 @@ k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
 constexpr int kSegCtasPerSm = 2;
 
 __global__ void __launch_bounds__(256)
-k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent)
+k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent, size_t D_stride)
 {
     const int n = Dw * (Dh - 1);
+    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride;
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
         const int u = a % Dw, b = a + Dw;
         const float da = D[a], db = D[b];
@@ -191,9 +201,10 @@ k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* par
 
 __global__ void __launch_bounds__(256)
 k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
-            int32_t* parent, int32_t* size)
+            int32_t* parent, int32_t* size, size_t D_stride)
 {
     const int n = Dw * Dh;
+    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
         const int u = a % Dw;
         const float d = D[a];
@@ -208,10 +219,11 @@ k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
 }
 
 __global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int32_t* __restrict__ parent,
-                            const int32_t* __restrict__ size)
+                            const int32_t* __restrict__ size, size_t D_stride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
     const float d = D[i];
     if (d >= 0.f) {
         int root = parent[i];                      // pixel -> run start -> (usually one hop) -> root
@@ -229,10 +241,11 @@ __global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int
 // of the line outwards by up to ipol_gap_width pixels (:1401-1436, :1493-1528).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_gap_pass(int Dw, int Dh, int gap, int add_corners, int vertical,
-                           const float* __restrict__ in, float* __restrict__ out)
+                           const float* __restrict__ in, float* __restrict__ out, size_t in_stride, size_t out_stride)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= Dw || v >= Dh) return;
+    in += blockIdx.z * in_stride; out += blockIdx.z * out_stride;
     const int len = vertical ? Dh : Dw, pos = vertical ? v : u;
     const ptrdiff_t stride = vertical ? Dw : 1;
     const float* line = in + (vertical ? (size_t)u : (size_t)v * Dw);
@@ -320,11 +333,13 @@ __device__ __forceinline__ bool mean_window(const float* __restrict__ line, ptrd
 // vertical:   in = D_tmp, out = D (keeps its value where the window gives nothing)
 template <int TAPS>
 __global__ void k_mean_pass(int Dw, int Dh, int vertical, const float* __restrict__ in,
-                            const float* keep, float* out)      // keep may alias out (vertical pass)
+                            const float* keep, float* out,      // keep may alias out (vertical pass)
+                            size_t in_stride, size_t keep_stride, size_t out_stride)
 {
     constexpr int BACK = TAPS == 8 ? 4 : 2, FWD = TAPS - BACK - 1;
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= Dw || v >= Dh) return;
+    in += blockIdx.z * in_stride; keep += blockIdx.z * keep_stride; out += blockIdx.z * out_stride;
     const size_t a = (size_t)v * Dw + u;
     float o = keep[a];
     if (!vertical) {
@@ -360,10 +375,12 @@ __device__ __forceinline__ float median7(const float* __restrict__ p, ptrdiff_t 
 }
 
 __global__ void k_median_pass(int Dw, int Dh, int vertical, const float* D,
-                              const float* in, float* out)        // D aliases in (horizontal) or out (vertical)
+                              const float* in, float* out,        // D aliases in (horizontal) or out (vertical)
+                              size_t D_stride, size_t in_stride, size_t out_stride)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
     if (u >= Dw || v >= Dh) return;
+    D += blockIdx.z * D_stride; in += blockIdx.z * in_stride; out += blockIdx.z * out_stride;
     const size_t a = (size_t)v * Dw + u;
     const bool inner = u >= 3 && u < Dw - 3 && v >= 3 && v < Dh - 3;
     if (!vertical) {
@@ -398,12 +415,13 @@ constexpr int kFuseTW = 64, kFuseTH = 32, kFuseThreads = 512;
 
 struct FuseArgs {
     int Dw, Dh, gap, speckle, apply;     // apply: fold k_seg_apply in (parent/size valid)
-    const float* in;                     // D after the L/R check (apply) or after speckle removal
+    const float* in;                     // D after the L/R check (apply) or after speckle removal; frames D_stride apart
     const int32_t* parent;
     const int32_t* size;
-    float* out;                          // final map (must not alias in)
-    float* dump_seg;                     // optional stage dumps (tests): D after speckle removal, after gap interpolation
+    OutTable out;                        // final map of every frame of the group (must not alias in)
+    float* dump_seg;                     // optional stage dumps (tests, single frame): D after speckle removal, after gap interpolation
     float* dump_gap;
+    size_t D_stride;
 };
 
 __device__ __forceinline__ float gap_fill(const float* __restrict__ line, int stride, int gap)
@@ -426,8 +444,13 @@ __device__ __forceinline__ float gap_fill(const float* __restrict__ line, int st
 
 template <int TAPS, bool MEAN>
 __global__ void __launch_bounds__(kFuseThreads)
-k_post_fused(const FuseArgs a)
+k_post_fused(const FuseArgs a_)
 {
+    // blockIdx.z = frame of the group
+    FuseArgs a = a_;
+    a.in += blockIdx.z * a.D_stride;
+    if (a.apply) { a.parent += blockIdx.z * a.D_stride; a.size += blockIdx.z * a.D_stride; }
+    float* __restrict__ out = a.out.p[blockIdx.z];
     constexpr int BACK = MEAN ? (TAPS == 8 ? 4 : 2) : 0, FWD = MEAN ? TAPS - BACK - 1 : 0, G = kFuseGap;
     constexpr int AW = kFuseTW + BACK + FWD + 2 * G, AH = kFuseTH + BACK + FWD + 2 * G;
     constexpr int BW = kFuseTW + BACK + FWD, BH = AH;
@@ -497,7 +520,7 @@ k_post_fused(const FuseArgs a)
         if (a.dump_gap || !MEAN) {
             const int v = r0 - BACK + y, u = c0 - BACK + x;
             if (v >= r0 && v < min(r0 + kFuseTH, Dh) && u >= c0 && u < min(c0 + kFuseTW, Dw))
-                (MEAN ? a.dump_gap : a.out)[v * Dw + u] = d;
+                (MEAN ? a.dump_gap : out)[v * Dw + u] = d;
         }
     }
     if (!MEAN) return;
@@ -530,18 +553,30 @@ k_post_fused(const FuseArgs a)
             float r;
             if (mean_window<TAPS>(sM + (y + BACK) * MW + x - (ptrdiff_t)v * MW, MW, v, &r)) o = r;
         }
-        a.out[v * Dw + u] = o;
+        out[v * Dw + u] = o;
     }
 }
 
-inline dim3 grid2d(int Dw, int Dh, int bx) { return dim3((Dw + bx - 1) / bx, Dh, 1); }
+inline dim3 grid2d(int Dw, int Dh, int bx, int frames) { return dim3((Dw + bx - 1) / bx, Dh, frames); }
+
+int speckle_size_of(const elas_b200_params& p)
+{
+    return p.subsampling ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;   // elas.cpp:1218
+}
 
 }  // namespace
 
-void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                     float* O1, float* O2, cudaStream_t s)
+OutTable out_table(float* base, size_t stride, int n_frames)
 {
-    k_lr_check<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, p.subsampling, (float)p.lr_threshold, D1, D2, O1, O2);
+    OutTable t{};
+    for (int i = 0; i < n_frames && i < kMaxGroupFrames; i++) t.p[i] = base + (size_t)i * stride;
+    return t;
+}
+
+void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
+                     float* O1, const OutTable& O2, size_t D_stride, int n_frames, cudaStream_t s)
+{
+    k_lr_check<<<grid2d(g.Dw, g.Dh, 256, n_frames), 256, 0, s>>>(g.Dw, g.Dh, p.subsampling, (float)p.lr_threshold, D1, D2, O1, O2, D_stride);
     count_launch();
 }
 
@@ -549,36 +584,34 @@ bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 12 <= 160 * 102
 
 // K8 for both maps + the run labelling of D1 (launch_segments(..., rows_done = true) continues from there)
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, float* O2, int32_t* parent, int32_t* size, int16_t* O2_i16, cudaStream_t s)
+                    float* O1, const OutTable& O2, int32_t* parent, int32_t* size, int16_t* O2_i16, size_t D_stride,
+                    int n_frames, cudaStream_t s)
 {
     const size_t smem = (size_t)g.Dw * 12;
     static unsigned long long optin = 0;
     if (ensure_dynamic_smem(k_lr_rows, 160 * 1024, &optin) != cudaSuccess) return;
-    k_lr_rows<<<g.Dh, 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
-                                      D1, D2, O1, O2, parent, size, O2_i16);
+    k_lr_rows<<<dim3(g.Dh, n_frames), 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
+                                                      D1, D2, O1, O2, parent, size, O2_i16, D_stride);
     count_launch();
 }
 
 void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, cudaStream_t s, bool apply, bool rows_done)
+                     int32_t* size, size_t D_stride, int n_frames, cudaStream_t s, bool apply, bool rows_done)
 {
     const int n = g.Dw * g.Dh;
-    int speckle = p.speckle_size;
-    if (p.subsampling) speckle = (int)(sqrtf((float)p.speckle_size) * 2);            // :1218
+    const int speckle = speckle_size_of(p);
     const float thr = p.speckle_sim_threshold;
-    if (!rows_done) { k_seg_rows<<<g.Dh, 256, 0, s>>>(g.Dw, thr, D, parent, size); count_launch(); }
-    static const int seg_ctas = [] {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const char* e = std::getenv("ELAS_B200_SEG_CTAS_PER_SM");
-        return sms * (e ? std::atoi(e) : kSegCtasPerSm);
-    }();
-    const int seg_grid = std::min(seg_ctas, (n + 255) / 256);
-    k_seg_merge<<<seg_grid, 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent);
-    k_seg_count<<<seg_grid, 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size);
+    if (!rows_done) { k_seg_rows<<<dim3(g.Dh, n_frames), 256, 0, s>>>(g.Dw, thr, D, parent, size, D_stride); count_launch(); }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static int sms_of[64] = {0};
+    if (!sms_of[dev & 63]) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_of[dev & 63] = sms; }
+    static const int per_sm = [] { const char* e = std::getenv("ELAS_B200_SEG_CTAS_PER_SM"); return e ? std::atoi(e) : kSegCtasPerSm; }();
+    const int seg_grid = std::min(std::max(1, sms_of[dev & 63] * per_sm / std::max(1, std::min(n_frames, 4))), (n + 255) / 256);
+    k_seg_merge<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent, D_stride);
+    k_seg_count<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size, D_stride);
     if (!apply) { count_launch(2); return; }
-    k_seg_apply<<<(n + 255) / 256, 256, 0, s>>>(n, speckle, D, parent, size);
+    k_seg_apply<<<dim3((n + 255) / 256, n_frames), 256, 0, s>>>(n, speckle, D, parent, size, D_stride);
     count_launch(3);
 }
 
@@ -590,50 +623,56 @@ bool post_fusable(const elas_b200_params& p)
 
 // speckle apply (when parent != nullptr) + gap interpolation + adaptive mean (when filter_adaptive_mean)
 void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
-                       const int32_t* size, float* out, float* dump_seg, float* dump_gap, cudaStream_t s)
+                       const int32_t* size, const OutTable& out, float* dump_seg, float* dump_gap, size_t D_stride,
+                       int n_frames, cudaStream_t s)
 {
     FuseArgs a;
     a.Dw = g.Dw; a.Dh = g.Dh;
     a.gap = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;               // :1335-1341
-    a.speckle = p.subsampling ? (int)(sqrtf((float)p.speckle_size) * 2) : p.speckle_size;   // :1218
+    a.speckle = speckle_size_of(p);
     a.apply = parent != nullptr;
     a.in = in; a.parent = parent; a.size = size; a.out = out; a.dump_seg = dump_seg; a.dump_gap = dump_gap;
-    const dim3 grid((g.Dw + kFuseTW - 1) / kFuseTW, (g.Dh + kFuseTH - 1) / kFuseTH, 1);
+    a.D_stride = D_stride;
+    const dim3 grid((g.Dw + kFuseTW - 1) / kFuseTW, (g.Dh + kFuseTH - 1) / kFuseTH, n_frames);
     if (!p.filter_adaptive_mean) k_post_fused<8, false><<<grid, kFuseThreads, 0, s>>>(a);
     else if (p.subsampling)      k_post_fused<4, true><<<grid, kFuseThreads, 0, s>>>(a);
     else                         k_post_fused<8, true><<<grid, kFuseThreads, 0, s>>>(a);
     count_launch();
 }
 
-void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, cudaStream_t s)
+// the unfused chain works in place on D (frames D_stride apart) with one scratch plane per frame (tmp, tmp_stride apart)
+void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, size_t D_stride, size_t tmp_stride,
+                int n_frames, cudaStream_t s)
 {
     const int gap = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;     // :1335-1341
-    k_gap_pass<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, gap, p.add_corners, 0, D, tmp);
-    k_gap_pass<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, gap, p.add_corners, 1, tmp, D);
+    k_gap_pass<<<grid2d(g.Dw, g.Dh, 256, n_frames), 256, 0, s>>>(g.Dw, g.Dh, gap, p.add_corners, 0, D, tmp, D_stride, tmp_stride);
+    k_gap_pass<<<grid2d(g.Dw, g.Dh, 256, n_frames), 256, 0, s>>>(g.Dw, g.Dh, gap, p.add_corners, 1, tmp, D, tmp_stride, D_stride);
     count_launch(2);
 }
 
-void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp,
-                          cudaStream_t s)
+void launch_adaptive_mean(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, size_t D_stride,
+                          size_t tmp_stride, int n_frames, cudaStream_t s)
 {
     // The reference filters a copy of D in which invalid pixels are set to -10 (elas.cpp:1553-1559).
     // Here every invalid pixel already IS -10: the L/R check writes -10 for everything it rejects
     // (elas.cpp:1172-1196) and speckle removal / gap interpolation only write -10 or valid values,
     // so the copy is D itself.  tmp = the reference's D_tmp (one plane).
+    const dim3 grid = grid2d(g.Dw, g.Dh, 256, n_frames);
     if (p.subsampling) {
-        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp);
-        k_mean_pass<4><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D);
+        k_mean_pass<4><<<grid, 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp, D_stride, D_stride, tmp_stride);
+        k_mean_pass<4><<<grid, 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D, tmp_stride, D_stride, D_stride);
     } else {
-        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp);
-        k_mean_pass<8><<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D);
+        k_mean_pass<8><<<grid, 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp, D_stride, D_stride, tmp_stride);
+        k_mean_pass<8><<<grid, 256, 0, s>>>(g.Dw, g.Dh, 1, tmp, D, D, tmp_stride, D_stride, D_stride);
     }
     count_launch(2);
 }
 
-void launch_median(const FrameGeom& g, float* D, float* tmp, cudaStream_t s)
+void launch_median(const FrameGeom& g, float* D, float* tmp, size_t D_stride, size_t tmp_stride, int n_frames, cudaStream_t s)
 {
-    k_median_pass<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp);
-    k_median_pass<<<grid2d(g.Dw, g.Dh, 256), 256, 0, s>>>(g.Dw, g.Dh, 1, D, tmp, D);
+    const dim3 grid = grid2d(g.Dw, g.Dh, 256, n_frames);
+    k_median_pass<<<grid, 256, 0, s>>>(g.Dw, g.Dh, 0, D, D, tmp, D_stride, D_stride, tmp_stride);
+    k_median_pass<<<grid, 256, 0, s>>>(g.Dw, g.Dh, 1, D, tmp, D, D_stride, tmp_stride, D_stride);
     count_launch(2);
 }
 

@@ -129,9 +129,13 @@ constexpr int kPointsPerCta = 32;     // lattice points of one row handled by a 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(256)
-k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
-          const uint4* __restrict__ desc2, int16_t* __restrict__ dcan)
+k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1_g,
+          const uint4* __restrict__ desc2_g, int16_t* __restrict__ dcan_g, size_t desc_stride, size_t dcan_stride)
 {
+    // blockIdx.z = frame of the group
+    const uint4* __restrict__ desc1 = desc1_g + (size_t)blockIdx.z * desc_stride;
+    const uint4* __restrict__ desc2 = desc2_g + (size_t)blockIdx.z * desc_stride;
+    int16_t* __restrict__ dcan = dcan_g + (size_t)blockIdx.z * dcan_stride;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31;
@@ -209,8 +213,6 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1,
         }
         if (lane == 0) s_result[i] = (int16_t)result;
     }
-    // dcan is pinned HOST memory (the host stage consumes the lattice): one coalesced store per CTA
-    // crosses PCIe instead of a device->host copy queued behind other slots' disparity-map copies
     __syncthreads();
     if (threadIdx.x < npts) dcan[vc * g.Wc + uc0 + threadIdx.x] = s_result[threadIdx.x];
 }
@@ -225,13 +227,13 @@ size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p)
 }
 
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,
-                    const uint4* desc2, int16_t* dcan, cudaStream_t s)
+                    const uint4* desc2, int16_t* dcan, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     static unsigned long long optin = 0;
     if (ensure_dynamic_smem(k_support, 200 * 1024, &optin) != cudaSuccess) return;
     const size_t smem = support_smem_bytes(g, p);
-    dim3 grid((g.Wc + kPointsPerCta - 1) / kPointsPerCta, g.Hc);
-    k_support<<<grid, 256, smem, s>>>(g, p, desc1, desc2, dcan);
+    dim3 grid((g.Wc + kPointsPerCta - 1) / kPointsPerCta, g.Hc, n_frames);
+    k_support<<<grid, 256, smem, s>>>(g, p, desc1, desc2, dcan, st.desc, st.dcan);
     count_launch();
 }
 

@@ -53,7 +53,8 @@ _lib = None
 
 EXPORTS = [
     "elas_b200_default_params", "elas_b200_stereomapper_params", "elas_b200_process",
-    "elas_b200_create", "elas_b200_create_ex", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
+    "elas_b200_create", "elas_b200_create_ex", "elas_b200_create_grouped", "elas_b200_frames_per_group",
+    "elas_b200_mesh_on_device", "elas_b200_time_matching_ex", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
@@ -81,6 +82,11 @@ def load_library():
     lib.elas_b200_process.argtypes = [P, u8p, u8p, f32p, f32p, i32p]
     lib.elas_b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, P, C.c_int32, C.c_int32, C.c_int32]
     lib.elas_b200_create_ex.argtypes = [C.POINTER(C.c_void_p), C.c_int32, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.elas_b200_create_grouped.argtypes = [C.POINTER(C.c_void_p), C.c_int32, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.elas_b200_frames_per_group.argtypes = [C.c_void_p]
+    lib.elas_b200_mesh_on_device.argtypes = [C.c_void_p]
+    lib.elas_b200_time_matching_ex.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, i32p]
+    lib.elas_b200_time_matching_ex.restype = C.c_float
     lib.elas_b200_destroy.argtypes = [C.c_void_p]
     lib.elas_b200_destroy.restype = None
     lib.elas_b200_process_ctx.argtypes = [C.c_void_p, C.c_int32, u8p, u8p, f32p, f32p, C.c_int32]
@@ -179,18 +185,22 @@ def host_stage(params, width, height, dcan):
 
 
 class ElasB200:
-    """A persistent context (elas_b200_create): n_slots frames in flight on one device."""
+    """A persistent context: n_slots frame groups of frames_per_group frames each in flight on one device
+    (frames_per_group=1: elas_b200_create_ex, the "slot" model; 0 = chosen from the frame size)."""
 
-    def __init__(self, params, width, height, n_slots=1, device=0, n_workers=0):
+    def __init__(self, params, width, height, n_slots=1, device=0, n_workers=0, frames_per_group=1):
         self.lib = load_library()
         if self.lib.elas_b200_device_count() < 1:
             raise RuntimeError("elas_b200: no CUDA device; this library has no CPU fallback")
         self.params, self.W, self.H, self.n_slots, self.device = params, width, height, n_slots, device
         self.shape = (height // 2, width // 2) if params.subsampling else (height, width)
         self.ctx = C.c_void_p()
-        rc = self.lib.elas_b200_create_ex(C.byref(self.ctx), device, C.byref(params), width, height, n_slots, n_workers)
+        rc = self.lib.elas_b200_create_grouped(C.byref(self.ctx), device, C.byref(params), width, height, n_slots,
+                                               frames_per_group, n_workers)
         if rc != 0:
-            raise RuntimeError(f"elas_b200_create_ex failed with {rc}")
+            raise RuntimeError(f"elas_b200_create_grouped failed with {rc}")
+        self.frames_per_group = int(self.lib.elas_b200_frames_per_group(self.ctx))
+        self.mesh_on_device = bool(self.lib.elas_b200_mesh_on_device(self.ctx))
 
     def close(self):
         if self.ctx:
@@ -306,11 +316,14 @@ class ElasB200:
         frames = C.c_int64(0)
         self.lib.elas_b200_host_times(self.ctx, ms, C.byref(frames), 1 if reset else 0)
         n = max(frames.value, 1)
-        names = ["submit_a", "wait_a", "host_stage", "submit_b", "wait_b"]
+        names = ["submit", "wait", "host_stage", "finish", "unused"]
         return {k: ms[i] / n for i, k in enumerate(names)}, frames.value
 
-    def time_matching(self, iters=20, flush_l2=True, slot=0):
-        ms = float(self.lib.elas_b200_time_matching(self.ctx, slot, iters, 1 if flush_l2 else 0))
+    def time_matching(self, iters=20, flush_l2=True, slot=0, per_frame=True):
+        """Mean ms of the matching kernel on the tables of the slot's last launch chain: per frame (default) or
+        per launch with the number of frames it processes."""
+        frames = C.c_int32(0)
+        ms = float(self.lib.elas_b200_time_matching_ex(self.ctx, slot, iters, 1 if flush_l2 else 0, C.byref(frames)))
         if ms < 0:
             raise RuntimeError("elas_b200_time_matching failed (run a frame through the slot first)")
-        return ms
+        return ms / frames.value if per_frame else (ms, frames.value)

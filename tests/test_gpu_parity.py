@@ -302,3 +302,76 @@ def test_device_pointers_through_the_host_buffer_entry_point():
     assert rc == 0 and st == [0, 0]
     assert bits_equal(dD[0, 0].cpu().numpy(), D1) and bits_equal(dD[0, 1].cpu().numpy(), D2)
     assert bits_equal(hD[0].numpy(), D1) and bits_equal(hD[1].numpy(), D2)
+
+
+def test_frame_groups_equal_single_frames(oracle):
+    """Frames batched per launch chain (every kernel takes the frame as a grid dimension): 19 frames over 3 groups
+    of 4 frames driven by 2 workers, one frame without texture; results are the per-frame oracle results, in order."""
+    p = checkers.stereomapper(95)
+    pairs = [synth.synthetic_pair(416, 200, 95, s)[:2] for s in (41, 42, 43, 44, 45)]
+    blank = (np.full((200, 416), 90, np.uint8), np.full((200, 416), 90, np.uint8))
+    order = [0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 1, 0, 5, 2, 3, 4, 0, 1]
+    frames = [pairs[i] if i < 5 else blank for i in order]
+    e = elas_b200.ElasB200(as_product_params(p), 416, 200, n_slots=3, n_workers=2, frames_per_group=4)
+    try:
+        assert e.frames_per_group == 4 and e.mesh_on_device
+        status, D1, D2 = e.process_batch([a for a, _ in frames], [b for _, b in frames])
+        status2, E1, E2 = e.process_batch([a for a, _ in frames[:5]], [b for _, b in frames[:5]])   # a partial last group
+    finally:
+        e.close()
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    for i, k in enumerate(order):
+        if k == 5:
+            assert status[i] == elas_b200.E_FEW_SUPPORT and (D1[i] == -10).all() and (D2[i] == -10).all()
+        else:
+            assert status[i] == 0 and bits_equal(D1[i], want[k][1]) and bits_equal(D2[i], want[k][2]), f"frame {i}"
+    for i in range(5):
+        assert status2[i] == 0 and bits_equal(E1[i], want[i][1]) and bits_equal(E2[i], want[i][2])
+
+
+def test_frame_groups_at_the_metric_size_device_buffers(oracle):
+    """1242x375 d_max 255, groups of 8 frames, device-resident inputs and outputs (the bench's `value` path)."""
+    torch = pytest.importorskip("torch")
+    W, H, dmax = 1242, 375, 255
+    p = checkers.stereomapper(dmax)
+    pairs = [synth.synthetic_pair(W, H, dmax, s)[:2] for s in (50, 51, 52)]
+    n = 20
+    dI = torch.stack([torch.stack([torch.from_numpy(pairs[i % 3][0]), torch.from_numpy(pairs[i % 3][1])]) for i in range(n)]).cuda()
+    dD = torch.full((n, 2, H, W), -77.0, dtype=torch.float32, device="cuda")
+    e = elas_b200.ElasB200(as_product_params(p), W, H, n_slots=2, n_workers=1, frames_per_group=0)
+    try:
+        assert e.frames_per_group == 8
+        st = e.process_batch_ptrs([dI[i, 0].data_ptr() for i in range(n)], [dI[i, 1].data_ptr() for i in range(n)],
+                                  [dD[i, 0].data_ptr() for i in range(n)], [dD[i, 1].data_ptr() for i in range(n)], W, device=True)
+        torch.cuda.synchronize()
+    finally:
+        e.close()
+    assert st == [0] * n
+    out = dD.cpu().numpy()
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    for i in range(n):
+        assert bits_equal(out[i, 0], want[i % 3][1]) and bits_equal(out[i, 1], want[i % 3][2]), f"frame {i}"
+
+
+def test_host_stage_path_equals_device_mesh_stage(oracle, monkeypatch):
+    """Contexts whose parameters the device mesh stage does not take run lattice filters and Delaunay on the host
+    (host_stage.cc); forcing that path for a ROBOTICS-family set gives the same bits."""
+    L, R, _ = synth.synthetic_pair(640, 240, 127, 33)
+    p = checkers.stereomapper(127)
+    _, O1, O2 = oracle.process(L, R, p)
+    monkeypatch.setenv("ELAS_B200_HOST_STAGE", "1")
+    e = elas_b200.ElasB200(as_product_params(p), 640, 240, n_slots=2, n_workers=2, frames_per_group=2)
+    try:
+        assert not e.mesh_on_device
+        status, D1, D2 = e.process_batch([L] * 5, [R] * 5)
+    finally:
+        e.close()
+    assert status == [0] * 5
+    for i in range(5):
+        assert bits_equal(D1[i], O1) and bits_equal(D2[i], O2)
+    # MIDDLEBURY adds corner support points (elas.cpp:283-318): host stage by construction
+    e = elas_b200.ElasB200(elas_b200.middlebury().copy(disp_max=63), 320, 160, n_slots=1)
+    try:
+        assert not e.mesh_on_device
+    finally:
+        e.close()
