@@ -35,9 +35,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-W, H, DMAX = 1242, 375, 255           # BASELINE.json configs[1]
+# BASELINE.json configs: K = configs[1] (the metric's configuration, default), HD = configs[2], 4K = configs[4] geometry
+CONFIGS = {"K": (1242, 375, 255, 512, 8), "HD": (1920, 1080, 128, 128, 2), "4K": (4096, 2160, 256, 32, 1)}
+W, H, DMAX = CONFIGS["K"][:3]
 WORKLOAD = f"synthetic {W}x{H} random-texture stereo pairs, d_max={DMAX}, stereomapper parameter set"
 METRIC = "stereo pairs/sec @1242x375 d_max=255"
+
+
+def select_config(name):
+    global W, H, DMAX, WORKLOAD, METRIC
+    W, H, DMAX = CONFIGS[name][:3]
+    WORKLOAD = f"synthetic {W}x{H} random-texture stereo pairs, d_max={DMAX}, stereomapper parameter set"
+    METRIC = f"stereo pairs/sec @{W}x{H} d_max={DMAX}"
 
 
 def algorithmic_bytes_matching(w, h, dmax, grid_size=20):
@@ -116,8 +125,9 @@ class ClockSampler:
 _cpu_state = {}
 
 
-def _cpu_init(kind):
+def _cpu_init(kind, config):
     import checkers
+    select_config(config)
     _cpu_state["impl"] = checkers.RefElas() if kind == "reference" else checkers.OracleElas()
     _cpu_state["params"] = checkers.stereomapper(DMAX)
 
@@ -141,10 +151,10 @@ def cpu_kind():
 class CpuArm:
     """A pool of one worker process per host core, each with the checker library loaded."""
 
-    def __init__(self):
+    def __init__(self, config="K"):
         self.kind = cpu_kind()
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind, config))
         self.pool.map(_cpu_work, [(0, 1)] * self.cores)      # load libraries, touch memory
 
     def run(self, pairs_per_core):
@@ -161,8 +171,8 @@ class CpuArm:
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    arm = CpuArm()
-    per_core = args.cpu_pairs_per_core
+    arm = CpuArm(args.config)
+    per_core = args.cpu_pairs_per_core or CONFIGS[args.config][4]
     for _ in range(args.warmup):
         arm.run(1)
     t_total, pairs = 0.0, 0
@@ -172,7 +182,8 @@ def run_reference_arm(args, rank):
         pairs += arm.cores * per_core
     arm.close()
     value = pairs / t_total
-    sample = f"{arm.cores} processes x {per_core} pairs per step, {args.steps} steps, Elas::process only"
+    sample = (f"{arm.cores} processes x {per_core} pairs per step, {args.steps} steps, Elas::process only "
+              "(its _mm_malloc buffers come zero-filled from the harness, a few % of extra memset, oracle/ref_harness.cpp)")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3),
@@ -194,14 +205,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="stereo pairs per GPU per step")
+    ap.add_argument("--config", default="K", choices=sorted(CONFIGS), help="K = 1242x375 d255 (the metric), HD = 1920x1080 d128, 4K = 4096x2160 d256")
+    ap.add_argument("--batch", type=int, default=0, help="stereo pairs per GPU per step (0 = the configuration's default)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled through the batch")
-    ap.add_argument("--slots", type=int, default=0, help="frames in flight per GPU (0 = twice the workers)")
-    ap.add_argument("--workers", type=int, default=0, help="host worker threads per GPU (0 = cores / ranks)")
-    ap.add_argument("--cpu-pairs-per-core", type=int, default=8)
+    ap.add_argument("--slots", type=int, default=0, help="frame groups in flight per GPU (0 = three per worker)")
+    ap.add_argument("--group", type=int, default=0, help="frames per launch chain (0 = chosen from the frame size)")
+    ap.add_argument("--workers", type=int, default=0, help="host worker threads per GPU (0 = from the cores per rank)")
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-4k", action="store_true", help="skip the 4096x2160 roofline point of the matching kernel")
+    ap.add_argument("--no-4k", action="store_true", help="skip the extra roofline points of the matching kernel (HD, 4096x2160)")
     args = ap.parse_args()
+    select_config(args.config)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,10 +245,12 @@ def main():
     # host workers: this rank's share of the cores; slots: twice that, so the GPU has phases queued while
     # every worker runs a host stage (workers are not tied to slots, elas_b200.cu)
     share = cores // max(world, 1)
-    # a few cores stay free for the main thread, the driver's threads and (end-to-end path) the copies' completion work
-    workers = args.workers or max(1, min(32, share - (4 if share >= 16 else 2 if share >= 12 else 1)))
-    slots = args.slots or max(2, min(48, 2 * workers))
-    B = args.batch
+    # The whole frame runs on the GPU, so a worker only enqueues launch chains and collects results (the end-to-end
+    # path also widens D2 from int16 on the host): a few per GPU, one core per rank stays free for the main thread
+    workers = args.workers or max(1, min(6, share - 1))
+    slots = args.slots or max(2, min(24, 3 * workers))
+    B = args.batch or CONFIGS[args.config][3]
+    args.distinct = min(args.distinct, B)
     bpl = W + 15 - (W - 1) % 16
 
     # synthetic inputs: `distinct` seeded pairs per rank, cycled to fill the batch
@@ -267,7 +283,14 @@ def main():
     def ptrs(t, k):
         return [t[i, k].data_ptr() for i in range(B)]
 
-    engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank, n_workers=workers)
+    engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank, n_workers=workers, frames_per_group=args.group)
+    if not engine.mesh_on_device:
+        # lattice filters + Delaunay on the host for this geometry (the lattice does not fit one CTA's shared memory):
+        # one worker per core pays off again
+        engine.close()
+        workers = args.workers or max(1, share - 1)
+        slots = args.slots or max(2, min(32, 2 * workers))
+        engine = elas_b200.ElasB200(params, W, H, n_slots=slots, device=local_rank, n_workers=workers, frames_per_group=args.group)
 
     # pointer tables of the batch, built once: the timed call is the C ABI call and nothing else
     dev_ptrs = (ptrs(d_I, 0), ptrs(d_I, 1), ptrs(d_D, 0), ptrs(d_D, 1))
@@ -317,22 +340,34 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # parity guard inside the bench: device-resident and host paths must give identical maps
+    # parity guards inside the bench: device-resident and host paths must give identical maps, and every rank
+    # checks frames of its own against the CPU oracle (bit for bit)
     same = bool(torch.equal(d_D.cpu(), h_D))
+    import checkers
+    oracle = checkers.OracleElas()
+    oracle_mismatch, oracle_checked = 0, 0
+    for i in sorted({0, B // 2, B - 1} if W * H < 4000000 else {0}):
+        L, R = pairs[i % args.distinct]
+        _, O1, O2 = oracle.process(L, R, checkers.Params.from_buffer_copy(bytes(params)))
+        got = h_D[i].numpy()
+        oracle_checked += 1
+        if not (np.array_equal(got[0].view(np.uint32), O1.view(np.uint32)) and np.array_equal(got[1].view(np.uint32), O2.view(np.uint32))):
+            oracle_mismatch += 1
+    oracle_mismatch, oracle_checked = (int(x) for x in sharding.sum_over_ranks([oracle_mismatch, oracle_checked], dev))
 
     ms_dev_max, ms_host_max = sharding.max_over_ranks([ms_dev, ms_host], dev)
 
     # roofline of the matching kernel: isolated launches cycling over all slots' tables (their
     # combined descriptors exceed L2), CUDA events on the launching stream, L2 flushed first
-    k7_ms = engine.time_matching(iters=max(20, 2 * slots), flush_l2=True)
+    k7_ms, k7_frames = engine.time_matching(iters=30, flush_l2=True, per_frame=False)
     peak, peak_src = measured_hbm_peak()
-    b_match = algorithmic_bytes_matching(W, H, DMAX)
+    b_match = algorithmic_bytes_matching(W, H, DMAX) * k7_frames          # one launch processes a frame group
     achieved = b_match / (k7_ms * 1e-3) / 1e9
 
     # the consumers of D1 (colour map, back-projection) on a frame left in HBM:
     # algorithmic bytes 16 N (4 in, 12 out) and 25 N (1 + 4 in, 20 out)
     view = None
-    if rank == 0:
+    if rank == 0 and args.config == "K":
         L0, R0 = pairs[0]
         engine.process(L0, R0)                      # single-frame path: leaves D1 in the slot's own buffers
         ms_c, ms_r = engine.time_view(iters=50)
@@ -343,7 +378,7 @@ def main():
     # the synchronous drop-in call itself (what Elas::process forwards to, one frame at a time, pageable host
     # buffers, nothing pipelined): the latency-bound number a caller like StereoThread::run sees
     drop_in = None
-    if rank == 0:
+    if rank == 0 and args.config == "K":
         import ctypes as C
         lib = elas_b200.load_library()
         o1 = np.empty((H, W), np.float32); o2 = np.empty((H, W), np.float32)
@@ -357,23 +392,25 @@ def main():
         dt = time.perf_counter() - t0
         drop_in = {"value": round(n_calls / dt, 1), "unit": "pairs/s", "ms_per_call": round(1e3 * dt / n_calls, 3),
                    "note": "elas_b200_process, synchronous, one frame in flight, pageable numpy buffers"}
+    engine_frames, engine_mesh = engine.frames_per_group, engine.mesh_on_device
     engine.close()
 
     # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
     # (683 MB algorithmic) does not fit L2, so this is the honest HBM-roofline point of the same kernel
     roof_4k = roof_hd = None
-    if rank == 0 and world == 1 and not args.no_4k:
+    if rank == 0 and world == 1 and not args.no_4k and args.config == "K":
         def roof_point(Wx, Hx, Dx):
             Lx, Rx, _ = synth.synthetic_pair(Wx, Hx, Dx, seed=0)
-            ex = elas_b200.ElasB200(elas_b200.stereomapper(Dx), Wx, Hx, n_slots=1, device=local_rank)
-            ex.process(Lx, Rx)
-            msx = ex.time_matching(iters=20, flush_l2=True)
+            ex = elas_b200.ElasB200(elas_b200.stereomapper(Dx), Wx, Hx, n_slots=1, device=local_rank, frames_per_group=0)
+            nfx = ex.frames_per_group
+            ex.process_batch([Lx] * nfx, [Rx] * nfx)
+            msx, nf = ex.time_matching(iters=20, flush_l2=True, per_frame=False)
             ex.close()
-            bx = algorithmic_bytes_matching(Wx, Hx, Dx)
+            bx = algorithmic_bytes_matching(Wx, Hx, Dx) * nf
             ax = bx / (msx * 1e-3) / 1e9
             return {"workload": f"synthetic {Wx}x{Hx}, d_max={Dx}", "bound": "hbm", "achieved": round(ax, 1), "peak": peak,
                     "unit": "GB/s", "frac": round(ax / peak, 4), "algorithmic_bytes_per_launch": bx,
-                    "ms_per_launch": round(msx, 5)}
+                    "frames_per_launch": nf, "ms_per_launch": round(msx, 5)}
         roof_hd = roof_point(1920, 1080, 128)       # BASELINE.json configs[2] geometry
         roof_4k = roof_point(4096, 2160, 256)       # BASELINE.json configs[4] geometry
         roof_4k["traffic"] = ncu_traffic_k7("bandwidth_config")
@@ -382,11 +419,12 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            arm = CpuArm()
-            rate, dt = arm.run(args.cpu_pairs_per_core)
+        if not args.no_cpu_baseline:
+            arm = CpuArm(args.config)
+            per_core = args.cpu_pairs_per_core or CONFIGS[args.config][4]
+            rate, dt = arm.run(per_core)
             cpu = {"value": round(rate, 3), "unit": "pairs/s", "cores": arm.cores, "kind": arm.kind,
-                   "sample": f"{arm.cores} processes x {args.cpu_pairs_per_core} pairs, Elas::process only, {dt:.1f} s wall"}
+                   "sample": f"{arm.cores} processes x {per_core} pairs, Elas::process only, {dt:.1f} s wall"}
             arm.close()
         total_pairs = world * B * args.steps
         line = {
@@ -394,18 +432,21 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_dev_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "slots_per_gpu": slots, "host_workers_per_gpu": workers,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "frame_groups_per_gpu": slots,
+                       "frames_per_launch_chain": engine_frames, "host_workers_per_gpu": workers,
+                       "mesh_stage": "device" if engine_mesh else "host",
                        "distinct_pairs": args.distinct, "l2": "512 MiB buffer rewritten between timed steps",
                        "parallelism": f"frame-sharded x{world}, one NCCL broadcast of the parameter block",
                        "host_cores": cores},
             "e2e": {"value": round(total_pairs / (ms_host_max * 1e-3), 2), "unit": "pairs/s",
-                    "h2d_bytes_per_step": B * 2 * W * H,
+                    # whole job, like `value`
+                    "h2d_bytes_per_step": world * B * 2 * W * H,
                     # D1 as float32; D2 (final after the L/R check: integers or -10) crosses as int16
                     # and is widened into the caller's float map by the library (elas_b200.cu)
-                    "d2h_bytes_per_step": B * W * H * (4 + 2),
+                    "d2h_bytes_per_step": world * B * W * H * (4 + 2),
                     "ms_per_step": round(ms_host_max / args.steps, 4)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right in one launch)",
+            "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right, one launch per frame group)", "frames_per_launch": k7_frames,
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic_k7(),
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
@@ -416,7 +457,8 @@ def main():
             "drop_in_call": drop_in,
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same},
+            "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same,
+                       "oracle_frames_checked": oracle_checked, "oracle_mismatch": oracle_mismatch},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

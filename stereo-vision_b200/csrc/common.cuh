@@ -189,10 +189,19 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long l
     if (err != cudaSuccess) return err;
     const unsigned long long bit = 1ull << (dev & 63);
     if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
-    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    err = bytes > 0 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) : cudaSuccess;
+    // Every kernel of the path asks for the same L1 / shared-memory split (all shared): chains of different frame
+    // groups run concurrently on different streams, and CTAs of kernels that want different splits cannot share an SM
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err == cudaSuccess) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
     return err;
 }
+// kernels without dynamic shared memory: the carve-out preference only
+#define ELASB_PREPARE_KERNEL(kernel)                                                        \
+    do {                                                                                    \
+        static unsigned long long prepared__ = 0;                                           \
+        if (::elasb::ensure_dynamic_smem(kernel, 0, &prepared__) != cudaSuccess) return;    \
+    } while (0)
 
 // number of kernel launches issued through the launchers above (process-wide, relaxed)
 long long launches_issued();

@@ -889,7 +889,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
         st.lists = cells * kGridListStride;           // uint16
         st.map = (size_t)map_pitch(g) * g.H;          // int32
         st.D = (size_t)g.Dw * g.Dh;                   // float
-        st.mesh_scratch = 17 * (size_t)c->support_cap + 8;
+        st.mesh_scratch = 18 * (size_t)c->support_cap + 8;
     }
     for (int i = 0; i < n_groups; i++) {
         c->groups.emplace_back(new Group);

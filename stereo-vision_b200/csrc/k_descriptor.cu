@@ -149,6 +149,7 @@ void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const 
                        uint4* desc1, uint4* desc2, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2 * n_frames);
+    ELASB_PREPARE_KERNEL(k_descriptor);
     k_descriptor<<<grid, 256, 0, s>>>(g, half, img1, img2, desc1, desc2, st.img, st.desc);
     count_launch();
 }

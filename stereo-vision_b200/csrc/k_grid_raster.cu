@@ -330,6 +330,7 @@ void launch_planes_scatter(const FrameGeom& g, const elas_b200_params& p, const 
     // ~2 triangles per point per image, 2 threads per triangle), strided beyond that
     const int expect = 3 * g.Wc * g.Hc;
     const int blocks = std::max(8, std::min(1024, (expect + kSetupThreads - 1) / kSetupThreads));
+    ELASB_PREPARE_KERNEL(k_planes_scatter);
     k_planes_scatter<<<dim3(blocks, n_frames), kSetupThreads, 0, s>>>(g, p, hdr, support, tri1, tri2, out1, out2, planes1,
                                                                       planes2, scratch, st);
     count_launch();
@@ -344,6 +345,7 @@ void launch_diffuse_raster(const FrameGeom& g, int subsampling, const FrameHeade
     // one warp per ~32x32 piece of the image and image side is plenty of parallelism; more work is strided
     const int pieces = 2 * ((g.W + 31) / 32) * ((g.H + kRasterBandRows - 1) / kRasterBandRows);
     const int raster_blocks = std::max(16, std::min(2048, (2 * pieces + (kRasterThreads >> 5) - 1) / (kRasterThreads >> 5)));
+    ELASB_PREPARE_KERNEL(k_diffuse_raster);
     k_diffuse_raster<<<dim3(diffuse_blocks + raster_blocks, n_frames), kRasterThreads, 0, s>>>(
         g, subsampling, diffuse_blocks, hdr, scratch, scratch_next, grid1, grid2, lists1, lists2, tri1, tri2,
         reinterpret_cast<const int2*>(units1), reinterpret_cast<const int2*>(units2), map1, map2, tag_bits, st);

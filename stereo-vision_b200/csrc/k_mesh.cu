@@ -8,13 +8,16 @@
 // work per frame -- and they overlap with the bandwidth-heavy kernels of other frame groups.
 //
 // Reference: elas.cpp:174-279, :496-517 (k_lattice); :534-600 with triangle.cpp:5446-6217, :7800-7853 (k_delaunay).
+#include <algorithm>
+
 #include "common.cuh"
 #include "mesh_core.h"
 
 namespace elasb {
 namespace {
 
-constexpr int kMeshThreads = 1024;
+constexpr int kMeshThreads = 1024;      // k_lattice
+constexpr int kDelaunayThreads = 512;   // k_delaunay: the parallel parts are small, the merges are single threads
 
 // in-place inclusive prefix sum of data[0..m) by the whole CTA; warp_sums = 32 ints of shared memory
 __device__ void block_scan_inclusive(int32_t* data, int m, int32_t* warp_sums)
@@ -65,6 +68,87 @@ __device__ void block_bitonic_sort(unsigned long long* k, int npad)
     __syncthreads();
 }
 
+// atomic bit operations on one 16-bit lattice element of shared memory, through its 32-bit word
+__device__ __forceinline__ void atomic_or16(int16_t* p, int bits)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    atomicOr(reinterpret_cast<unsigned*>(a & ~(uintptr_t)3), ((unsigned)bits & 0xFFFFu) << ((a & 2) * 8));
+}
+__device__ __forceinline__ void atomic_and16(int16_t* p, int mask)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    atomicAnd(reinterpret_cast<unsigned*>(a & ~(uintptr_t)3), ~((~(unsigned)mask & 0xFFFFu) << ((a & 2) * 8)));
+}
+
+// One round of the inconsistency filter (mesh::incon_round) on the device.  The cells marked for this round are
+// first compacted into a work list (per segment of kListSegment cells, 16-bit offsets), then evaluated one cell
+// per THREAD: 32 different cells per warp instruction, every lane busy, rows nearest the centre first and the count
+// stops at incon_min_support.  A cell that is invalidated marks its dependents for the next round.
+constexpr int kListSegment = 16384;
+
+__device__ __forceinline__ bool incon_fails_early(const mesh::Lattice& L, const int16_t* c, int x, int win, int thr, int need)
+{
+    using namespace mesh;
+    int support = 0;
+    for (int k = 0; k <= 2 * win && support < need; k++) {
+        const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);                  // v, v+1, v-1, v+2, v-2, ...
+        const int16_t* row = c + dv * L.pitch;
+        for (int du = -win; du <= win; du++) {
+            const int y = row[du];
+            const bool gone = y < 0 || ((y & kRemoved) && (du < 0 || (du == 0 && dv < 0)));
+            support += !gone && iabs((x & kValueMask) - (y & kValueMask)) <= thr;
+        }
+    }
+    return support < need;
+}
+
+__device__ bool incon_round_list(const mesh::Lattice& L, int win, int thr, int need, int round, uint16_t* list, int* list_n)
+{
+    using namespace mesh;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+    const int now = (round & 1) ? kDirty1 : kDirty0, next = (round & 1) ? kDirty0 : kDirty1;
+    const int cells = L.Wc * L.Hc;
+    bool changed = false;
+    for (int seg = 0; seg < cells; seg += kListSegment) {
+        if (tid == 0) *list_n = 0;
+        __syncthreads();
+        const int seg_end = min(seg + kListSegment, cells);
+        for (int i0 = seg + (tid & ~31); i0 < seg_end; i0 += T) {          // whole warps stay together for the ballot
+            const int i = i0 + lane;
+            bool todo = false;
+            if (i < seg_end) {
+                const int vc = i / L.Wc, uc = i - vc * L.Wc;
+                const int x = L.P[lat_index(L, uc, vc)];
+                todo = x >= 0 && !(x & kRemoved) && (x & now);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, todo);
+            int at = 0;
+            if (lane == 0 && m) at = atomicAdd(list_n, __popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (todo) list[at + __popc(m & ((1u << lane) - 1))] = (uint16_t)(i - seg);
+        }
+        __syncthreads();
+        const int n = *list_n;
+        for (int k = tid; k < n; k += T) {
+            const int i = seg + list[k];
+            const int vc = i / L.Wc, uc = i - vc * L.Wc;
+            int16_t* c = L.P + lat_index(L, uc, vc);
+            const int x = *c;
+            atomic_and16(c, ~now);
+            if (!incon_fails_early(L, c, x, win, thr, need)) continue;
+            atomic_or16(c, kRemoved);
+            changed = true;
+            for (int dv = -win; dv <= win; dv++)
+                for (int du = (dv > 0 ? 0 : 1); du <= win; du++) {          // later in scan order only
+                    int16_t* d = c + dv * L.pitch + du;
+                    if (incon_depends(x, *d, du, dv, thr)) atomic_or16(d, next);
+                }
+        }
+        __syncthreads();
+    }
+    return changed;
+}
+
 struct LatticeArgs {
     int Wc, Hc, step, win, thr, need;
     const int16_t* dcan_raw;     // K2's lattice, [frames][Hc][Wc]
@@ -82,14 +166,17 @@ k_lattice(const LatticeArgs a)
     __shared__ int32_t warp_sums[32];
     const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     mesh::Lattice L{a.Wc, a.Hc, a.Wc + 2 * mesh::kPadC, a.step, reinterpret_cast<int16_t*>(smem_raw)};
-    int32_t* col = reinterpret_cast<int32_t*>(smem_raw + (((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15));   // [Wc + 1]
+    const size_t lat_bytes = ((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15;
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + lat_bytes);      // [kListSegment] work list of the inconsistency rounds
+    int32_t* col = reinterpret_cast<int32_t*>(smem_raw + lat_bytes);         // [Wc + 1], after the rounds
+    __shared__ int list_n;
     const int16_t* raw = a.dcan_raw + (size_t)f * a.dcan_stride;
     int16_t* out = a.dcan + (size_t)f * a.dcan_stride;
     int32_t* support = a.support + (size_t)f * a.support_stride;
 
     mesh::lattice_load(L, raw, tid, T);
     __syncthreads();
-    while (__syncthreads_or(mesh::incon_round(L, a.win, a.thr, a.need, tid, T))) {}
+    for (int round = 0; __syncthreads_or(incon_round_list(L, a.win, a.thr, a.need, round, list, &list_n)); round++) {}
     mesh::incon_finish(L, a.dcan_incon ? a.dcan_incon + (size_t)f * a.dcan_stride : nullptr, tid, T);
     __syncthreads();
     mesh::redundant_pass(L, true, tid, T);          // elas.cpp:501
@@ -118,27 +205,21 @@ struct DelaunayArgs {
     size_t support_stride, tri_stride, units_stride, scratch_stride;
 };
 
-__global__ void __launch_bounds__(kMeshThreads)
-k_delaunay(const DelaunayArgs a)
+// mem = 18 n ints of working memory.  Inlined twice by the kernel, once with shared memory (the compiler then
+// addresses it with LDS/STS: the merges are chains of dependent loads, their latency is the kernel's run time)
+// and once with the global scratch area.
+__device__ __forceinline__ void delaunay_body(const DelaunayArgs& a, int32_t* mem, FrameHeader* hdr, int n, int img, int f,
+                                              int32_t* warp_sums)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ int32_t warp_sums[32];
-    const int img = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
-    FrameHeader* hdr = a.hdr + f;
-    const int n = hdr->n_support;
-    if (n < 3) {                                                           // elas.cpp:69-75
-        if (tid == 0) { hdr->n_tri[img] = 0; hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; }
-        return;
-    }
-    // working memory, 17 n ints: shared memory when it fits, else this (frame, image)'s global scratch
-    int32_t* mem = 17 * n + 2 <= a.smem_ints ? reinterpret_cast<int32_t*>(smem_raw)
-                                             : a.scratch + ((size_t)f * 2 + img) * a.scratch_stride;
+    const int tid = threadIdx.x, T = blockDim.x;
     int32_t* x = mem; int32_t* y = mem + n; int32_t* s = mem + 2 * n; int32_t* hull = mem + 3 * n;
     int32_t* nbr = mem + 5 * n; int32_t* vtx = mem + 11 * n;
+    uint32_t* xy = reinterpret_cast<uint32_t*>(mem + 17 * n);
     const int32_t* support = a.support + (size_t)f * a.support_stride;
     for (int i = tid; i < n; i += T) {                                     // elas.cpp:543-559
         x[i] = img ? support[3 * i] - support[3 * i + 2] : support[3 * i];
         y[i] = support[3 * i + 1];
+        xy[i] = ((uint32_t)x[i] << 16) | (uint32_t)y[i];
     }
     // ---- the two sorted id lists: (x,y) and (y,x), keys are unique (no duplicate points on this path) -----
     int32_t* R = nbr;                                                      // 12 n ints free until the triangulation starts
@@ -149,6 +230,11 @@ k_delaunay(const DelaunayArgs a)
     __syncthreads();
     int dup = 0;
     for (int pass = 0; pass < 2; pass++) {
+        if (pass == 0 && img == 0) {
+            // the support list is in u-outer / v-inner order (elas.cpp:505-517): the left image's points are sorted by (x,y)
+            for (int i = tid; i < n; i += T) o.xs[i] = i;
+            continue;
+        }
         for (int i = tid; i < npad; i += T)
             keys[i] = i < n ? ((unsigned long long)(pass ? ((uint32_t)y[i] << 16) | (uint32_t)x[i] : ((uint32_t)x[i] << 16) | (uint32_t)y[i]) << 32) | (uint32_t)i
                             : ~0ull;
@@ -178,7 +264,7 @@ k_delaunay(const DelaunayArgs a)
         __syncthreads();
     }
     // ---- divide and conquer, deepest level first ---------------------------------------------------------------
-    mesh::Mesh m{n, x, y, s, nbr, vtx, hull};
+    mesh::Mesh m{n, xy, s, nbr, vtx, hull};
     for (int depth = mesh::tree_depth(n); depth >= 0; depth--) {
         __syncthreads();
         mesh::triangulate_depth(m, depth, tid, T);
@@ -209,11 +295,28 @@ k_delaunay(const DelaunayArgs a)
         if (cscan[t] <= a.unit_cap && (t == nt - 1 || cscan[t + 1] > a.unit_cap)) { hdr->n_units[img] = cscan[t]; hdr->ovf_from[img] = t + 1; }
 }
 
+
+__global__ void __launch_bounds__(kDelaunayThreads)
+k_delaunay(const DelaunayArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int32_t warp_sums[32];
+    const int img = blockIdx.x, f = blockIdx.y;
+    FrameHeader* hdr = a.hdr + f;
+    const int n = hdr->n_support;
+    if (n < 3) {                                                           // elas.cpp:69-75
+        if (threadIdx.x == 0) { hdr->n_tri[img] = 0; hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; }
+        return;
+    }
+    if (18 * n + 2 <= a.smem_ints) delaunay_body(a, reinterpret_cast<int32_t*>(smem_raw), hdr, n, img, f, warp_sums);
+    else delaunay_body(a, a.scratch + ((size_t)f * 2 + img) * a.scratch_stride, hdr, n, img, f, warp_sums);
+}
+
 }  // namespace
 
 size_t lattice_smem_bytes(const FrameGeom& g)
 {
-    return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + ((size_t)g.Wc + 1) * 4;
+    return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + std::max<size_t>(((size_t)g.Wc + 1) * 4, (size_t)kListSegment * 2);
 }
 
 // parameters / sizes the device mesh stage handles; everything else takes the host stage (host_stage.cc)
@@ -223,7 +326,7 @@ bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p)
            2 * p.lr_threshold < g.step &&                     // no two support points on one right-image pixel
            p.incon_window_size <= mesh::kPadC && p.incon_window_size >= 0 &&
            p.disp_max < mesh::kRemoved && g.W < 16384 && g.H < 16384 &&
-           lattice_smem_bytes(g) <= 220 * 1024;
+           lattice_smem_bytes(g) <= 224 * 1024;
 }
 
 void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
@@ -245,7 +348,7 @@ void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, 
     if (ensure_dynamic_smem(k_delaunay, kSmem, &optin) != cudaSuccess) return;
     DelaunayArgs a{g.W, g.H, unit_cap, kSmem / 4, support, {tri1, tri2}, {units1, units2}, hdr, scratch,
                    st.support, st.tri, st.units, st.mesh_scratch};
-    k_delaunay<<<dim3(2, n_frames), kMeshThreads, kSmem, s>>>(a);
+    k_delaunay<<<dim3(2, n_frames), kDelaunayThreads, kSmem, s>>>(a);
     count_launch();
 }
 

@@ -608,6 +608,8 @@ void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, in
     if (!sms_of[dev & 63]) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_of[dev & 63] = sms; }
     static const int per_sm = [] { const char* e = std::getenv("ELAS_B200_SEG_CTAS_PER_SM"); return e ? std::atoi(e) : kSegCtasPerSm; }();
     const int seg_grid = std::min(std::max(1, sms_of[dev & 63] * per_sm / std::max(1, std::min(n_frames, 4))), (n + 255) / 256);
+    ELASB_PREPARE_KERNEL(k_seg_merge);
+    ELASB_PREPARE_KERNEL(k_seg_count);
     k_seg_merge<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent, D_stride);
     k_seg_count<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size, D_stride);
     if (!apply) { count_launch(2); return; }
@@ -634,6 +636,9 @@ void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const floa
     a.in = in; a.parent = parent; a.size = size; a.out = out; a.dump_seg = dump_seg; a.dump_gap = dump_gap;
     a.D_stride = D_stride;
     const dim3 grid((g.Dw + kFuseTW - 1) / kFuseTW, (g.Dh + kFuseTH - 1) / kFuseTH, n_frames);
+    ELASB_PREPARE_KERNEL((k_post_fused<8, false>));
+    ELASB_PREPARE_KERNEL((k_post_fused<4, true>));
+    ELASB_PREPARE_KERNEL((k_post_fused<8, true>));
     if (!p.filter_adaptive_mean) k_post_fused<8, false><<<grid, kFuseThreads, 0, s>>>(a);
     else if (p.subsampling)      k_post_fused<4, true><<<grid, kFuseThreads, 0, s>>>(a);
     else                         k_post_fused<8, true><<<grid, kFuseThreads, 0, s>>>(a);

@@ -36,7 +36,10 @@ namespace elasb {
 namespace mesh {
 
 constexpr int kPadC = 8, kPadR = 8;        // lattice padding: >= incon_window_size and >= the redundancy reach (5)
-constexpr int kRemoved = 0x4000;           // flag on a lattice value: invalidated by the inconsistency filter
+// bits of a valid lattice value (disparities stay below 4096): the inconsistency filter's working state
+constexpr int kValueMask = 0x0FFF;
+constexpr int kDirty0 = 0x1000, kDirty1 = 0x2000;   // to be (re-)evaluated in an even / odd round
+constexpr int kRemoved = 0x4000;           // invalidated by the inconsistency filter
 constexpr int kRedunDist = 5, kRedunThr = 1;   // elas.cpp:501-502
 
 struct Lattice {
@@ -48,53 +51,77 @@ MESH_FN int lat_index(const Lattice& L, int uc, int vc) { return (vc + kPadR) * 
 MESH_FN int lat_elems(int Wc, int Hc) { return (Wc + 2 * kPadC) * (Hc + 2 * kPadR); }
 MESH_FN int iabs(int x) { return x < 0 ? -x : x; }
 
-// ---- phase L0: padded copy of the candidate lattice (K2's output, [Hc][Wc]) ----------------------------
+// ---- phase L0: padded copy of the candidate lattice (K2's output, [Hc][Wc]); valid cells start out "dirty" ---
 MESH_FN void lattice_load(const Lattice& L, const int16_t* dcan, int tid, int nthr)
 {
     const int rows = L.Hc + 2 * kPadR, total = rows * L.pitch;
     for (int i = tid; i < total; i += nthr) {
         const int r = i / L.pitch, c = i - r * L.pitch;
         const int vc = r - kPadR, uc = c - kPadC;
-        L.P[i] = (vc >= 0 && vc < L.Hc && uc >= 0 && uc < L.Wc) ? dcan[vc * L.Wc + uc] : (int16_t)-1;
+        int x = -1;
+        if (vc >= 0 && vc < L.Hc && uc >= 0 && uc < L.Wc) { x = dcan[vc * L.Wc + uc]; if (x >= 0) x |= kDirty0; }
+        L.P[i] = (int16_t)x;
     }
 }
 
-// ---- phase L1 (repeated until no thread reports a change): one round of the inconsistency filter -------
-// elas.cpp:174-209.  Counting stops at incon_min_support (only '<' is observable); rows nearest the centre first.
-MESH_FN bool incon_round(const Lattice& L, int win, int thr, int need, int tid, int nthr)
+// removeInconsistentSupportPoints, elas.cpp:174-209: does cell (uc,vc) with value x keep fewer than `need`
+// supporters?  A window cell that precedes it in scan order (u outer, v inner) counts with its CURRENT state.
+MESH_FN bool incon_fails(const Lattice& L, const int16_t* c, int x, int win, int thr, int need)
+{
+    int support = 0;
+    for (int dv = -win; dv <= win; dv++) {
+        const int16_t* row = c + dv * L.pitch;
+        for (int du = -win; du <= win; du++) {
+            const int y = row[du];
+            if (y < 0) continue;
+            if ((y & kRemoved) && (du < 0 || (du == 0 && dv < 0))) continue;
+            support += iabs((x & kValueMask) - (y & kValueMask)) <= thr;
+        }
+    }
+    return support < need;
+}
+// the cells whose verdict may change when (uc,vc) is invalidated: valid, similar, LATER in scan order
+MESH_FN bool incon_depends(int x, int y, int du, int dv, int thr)
+{
+    return y >= 0 && !(y & kRemoved) && (du > 0 || (du == 0 && dv > 0)) && iabs((x & kValueMask) - (y & kValueMask)) <= thr;
+}
+
+// ---- phase L1 (round r = 0, 1, ...; repeated until no thread reports a change) ----------------------------
+// Evaluates the cells marked for this round; a cell that is invalidated marks its dependents for the next round.
+// or16 / and16: atomic bit operations on a lattice element (plain operations in the CPU emulation).
+template <class Or16, class And16>
+MESH_FN bool incon_round(const Lattice& L, int win, int thr, int need, int round, int tid, int nthr, Or16 or16, And16 and16)
 {
     bool changed = false;
+    const int now = (round & 1) ? kDirty1 : kDirty0, next = (round & 1) ? kDirty0 : kDirty1;
     const int cells = L.Wc * L.Hc;
     for (int i = tid; i < cells; i += nthr) {
         const int vc = i / L.Wc, uc = i - vc * L.Wc;
         int16_t* c = L.P + lat_index(L, uc, vc);
         const int x = *c;
-        if (x < 0 || (x & kRemoved)) continue;
-        int support = 0;
-        for (int k = 0; k <= 2 * win && support < need; k++) {
-            const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);              // v, v+1, v-1, v+2, v-2, ...
-            const int16_t* row = c + dv * L.pitch;
-            for (int du = -win; du <= win; du++) {
-                const int y = row[du];
-                if (y < 0) continue;
-                // a cell that precedes (uc,vc) in scan order (u outer, v inner) counts with its CURRENT state
-                if ((y & kRemoved) && (du < 0 || (du == 0 && dv < 0))) continue;
-                support += iabs(x - (y & (kRemoved - 1))) <= thr;
+        if (x < 0 || (x & kRemoved) || !(x & now)) continue;
+        and16(c, ~now);
+        if (!incon_fails(L, c, x, win, thr, need)) continue;
+        or16(c, kRemoved);
+        changed = true;
+        for (int dv = -win; dv <= win; dv++)
+            for (int du = (dv > 0 ? 0 : 1); du <= win; du++) {          // later in scan order only
+                int16_t* d = c + dv * L.pitch + du;
+                if (incon_depends(x, *d, du, dv, thr)) or16(d, next);
             }
-        }
-        if (support < need) { *c = (int16_t)(x | kRemoved); changed = true; }
     }
     return changed;
 }
 
-// ---- phase L2: invalidated cells become -1; optional dump of the lattice after this filter -------------
+// ---- phase L2: invalidated cells become -1, the others plain disparities; optional dump after this filter --
 MESH_FN void incon_finish(const Lattice& L, int16_t* dump, int tid, int nthr)
 {
     const int cells = L.Wc * L.Hc;
     for (int i = tid; i < cells; i += nthr) {
         const int vc = i / L.Wc, uc = i - vc * L.Wc;
         int16_t* c = L.P + lat_index(L, uc, vc);
-        if (*c >= 0 && (*c & kRemoved)) *c = -1;
+        const int x = *c;
+        if (x >= 0) *c = (int16_t)((x & kRemoved) ? -1 : (x & kValueMask));
         if (dump) dump[i] = *c;
     }
 }
@@ -160,7 +187,7 @@ struct OTri { int t, o; };                  // oriented triangle: edge org->dest
 
 struct Mesh {
     int n;                                  // vertices
-    const int32_t* x; const int32_t* y;     // coordinates by vertex id
+    const uint32_t* xy;                     // coordinates by vertex id, x << 16 | y (both below 2^14)
     int32_t* s;                             // vertex ids in the alternating-cut order (triangle.cpp:6197-6206)
     int32_t* nbr; int32_t* vtx;             // 3 links / 3 vertices per triangle, 2n-2 triangles; vertex -1 = ghost
     int32_t* hull;                          // [2n]: (farleft, farright) handles of the subtree that starts at s[lo]
@@ -186,22 +213,27 @@ MESH_FN OTri make(const Mesh& m, int t)
     return {t, 0};
 }
 
-// exact predicates: coordinates are integers below 2^14, every product below 2^58 (triangle.cpp:2706, :3334
-// return exact signs)
-MESH_FN int ccw(const Mesh& m, int a, int b, int c)
+// A vertex with its coordinates in registers: the merge loop keeps the four corners of the knitting edge and
+// the candidate apex this way, so a predicate costs one load (the new vertex) instead of eight.
+struct PV { int id, x, y; };
+MESH_FN PV pv(const Mesh& m, int id)
 {
-    const long long l = (long long)(m.x[a] - m.x[c]) * (m.y[b] - m.y[c]);
-    const long long r = (long long)(m.y[a] - m.y[c]) * (m.x[b] - m.x[c]);
+    const uint32_t c = m.xy[id];
+    return {id, (int)(c >> 16), (int)(c & 0xFFFFu)};
+}
+// exact predicates (triangle.cpp:2706, :3334 return exact signs): coordinates are integers below 2^14, so every
+// difference is below 2^14, every product of two below 2^28 (32-bit), the in-circle determinant below 2^60
+MESH_FN int ccw(const PV& a, const PV& b, const PV& c)
+{
+    const int l = (a.x - c.x) * (b.y - c.y), r = (a.y - c.y) * (b.x - c.x);
     return (l > r) - (l < r);
 }
-MESH_FN int incircle(const Mesh& m, int a, int b, int c, int d)
+MESH_FN int incircle(const PV& a, const PV& b, const PV& c, const PV& d)
 {
-    const long long adx = m.x[a] - m.x[d], ady = m.y[a] - m.y[d];
-    const long long bdx = m.x[b] - m.x[d], bdy = m.y[b] - m.y[d];
-    const long long cdx = m.x[c] - m.x[d], cdy = m.y[c] - m.y[d];
-    const long long det = (adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
-                          (bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
-                          (cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
+    const int adx = a.x - d.x, ady = a.y - d.y, bdx = b.x - d.x, bdy = b.y - d.y, cdx = c.x - d.x, cdy = c.y - d.y;
+    const long long det = (long long)(adx * adx + ady * ady) * (bdx * cdy - cdx * bdy) +
+                          (long long)(bdx * bdx + bdy * bdy) * (cdx * ady - adx * cdy) +
+                          (long long)(cdx * cdx + cdy * cdy) * (adx * bdy - bdx * ady);
     return (det > 0) - (det < 0);
 }
 
@@ -312,7 +344,7 @@ MESH_FN void build_leaf(const Mesh& m, const Node& nd, OTri& farleft, OTri& farr
         return;
     }
     OTri mid = make(m, t), t1 = make(m, t + 1), t2 = make(m, t + 2), t3 = make(m, t + 3);
-    const int area = ccw(m, s[0], s[1], s[2]);
+    const int area = ccw(pv(m, s[0]), pv(m, s[1]), pv(m, s[2]));
     if (area == 0) {
         set_org(m, mid, s[0]); set_dest(m, mid, s[1]);
         set_org(m, t1, s[1]);  set_dest(m, t1, s[0]);
@@ -352,56 +384,55 @@ MESH_FN void build_leaf(const Mesh& m, const Node& nd, OTri& farleft, OTri& farr
 MESH_FN void merge_hulls(const Mesh& m, OTri& farleft, OTri innerleft, OTri innerright, OTri& farright, int axis,
                          int base_t, int top_t)
 {
-    const int32_t* X = m.x; const int32_t* Y = m.y;
-    int ild = dest(m, innerleft), ila = apex(m, innerleft);
-    int iro = org(m, innerright), ira = apex(m, innerright);
+    PV ild = pv(m, dest(m, innerleft)), ila = pv(m, apex(m, innerleft));
+    PV iro = pv(m, org(m, innerright)), ira = pv(m, apex(m, innerright));
 
     if (axis == 1) {
         // horizontal cut: re-aim the four hull handles at the bottom-/top-most vertices (:5666-5704)
-        int flp = org(m, farleft), fla = apex(m, farleft);
-        int frp = dest(m, farright);
-        while (Y[fla] < Y[flp]) {
+        PV flp = pv(m, org(m, farleft)), fla = pv(m, apex(m, farleft));
+        PV frp = pv(m, dest(m, farright));
+        while (fla.y < flp.y) {
             farleft = sym(m, lnext(farleft));
             flp = fla;
-            fla = apex(m, farleft);
+            fla = pv(m, apex(m, farleft));
         }
         OTri check = sym(m, innerleft);
-        int cv = apex(m, check);
-        while (Y[cv] > Y[ild]) {
+        PV cv = pv(m, apex(m, check));
+        while (cv.y > ild.y) {
             innerleft = lnext(check);
             ila = ild;
             ild = cv;
             check = sym(m, innerleft);
-            cv = apex(m, check);
+            cv = pv(m, apex(m, check));
         }
-        while (Y[ira] < Y[iro]) {
+        while (ira.y < iro.y) {
             innerright = sym(m, lnext(innerright));
             iro = ira;
-            ira = apex(m, innerright);
+            ira = pv(m, apex(m, innerright));
         }
         check = sym(m, farright);
-        cv = apex(m, check);
-        while (Y[cv] > Y[frp]) {
+        cv = pv(m, apex(m, check));
+        while (cv.y > frp.y) {
             farright = lnext(check);
             frp = cv;
             check = sym(m, farright);
-            cv = apex(m, check);
+            cv = pv(m, apex(m, check));
         }
     }
 
     // lower common tangent (:5706-5726)
     for (bool changed = true; changed;) {
         changed = false;
-        if (ccw(m, ild, ila, iro) > 0) {
+        if (ccw(ild, ila, iro) > 0) {
             innerleft = sym(m, lprev(innerleft));
             ild = ila;
-            ila = apex(m, innerleft);
+            ila = pv(m, apex(m, innerleft));
             changed = true;
         }
-        if (ccw(m, ira, iro, ild) > 0) {
+        if (ccw(ira, iro, ild) > 0) {
             innerright = sym(m, lnext(innerright));
             iro = ira;
-            ira = apex(m, innerright);
+            ira = pv(m, apex(m, innerright));
             changed = true;
         }
     }
@@ -412,21 +443,21 @@ MESH_FN void merge_hulls(const Mesh& m, OTri& farleft, OTri innerleft, OTri inne
     base = lnext(base);
     bond(m, base, innerright);
     base = lnext(base);
-    set_org(m, base, iro);
-    set_dest(m, base, ild);
-    if (ild == org(m, farleft)) farleft = lnext(base);   // :5745-5752
-    if (iro == dest(m, farright)) farright = lprev(base);
+    set_org(m, base, iro.id);
+    set_dest(m, base, ild.id);
+    if (ild.id == org(m, farleft)) farleft = lnext(base);   // :5745-5752
+    if (iro.id == dest(m, farright)) farright = lprev(base);
 
-    int lowerleft = ild, lowerright = iro;
-    int upperleft = apex(m, leftcand), upperright = apex(m, rightcand);
+    PV lowerleft = ild, lowerright = iro;
+    PV upperleft = pv(m, apex(m, leftcand)), upperright = pv(m, apex(m, rightcand));
 
     for (;;) {
-        const bool leftdone = ccw(m, upperleft, lowerleft, lowerright) <= 0;     // :5765-5768
-        const bool rightdone = ccw(m, upperright, lowerleft, lowerright) <= 0;
+        const bool leftdone = ccw(upperleft, lowerleft, lowerright) <= 0;     // :5765-5768
+        const bool rightdone = ccw(upperright, lowerleft, lowerright) <= 0;
         if (leftdone && rightdone) {
             OTri top = make(m, top_t);                   // top bounding triangle (:5771-5780)
-            set_org(m, top, lowerleft);
-            set_dest(m, top, lowerright);
+            set_org(m, top, lowerleft.id);
+            set_dest(m, top, lowerright.id);
             bond(m, top, base);
             top = lnext(top);
             bond(m, top, rightcand);
@@ -434,20 +465,20 @@ MESH_FN void merge_hulls(const Mesh& m, OTri& farleft, OTri innerleft, OTri inne
             bond(m, top, leftcand);
             if (axis == 1) {
                 // restore the handles to the left-/right-most vertices (:5786-5809)
-                int flp = org(m, farleft);
-                int frp = dest(m, farright), fra = apex(m, farright);
+                PV flp = pv(m, org(m, farleft));
+                PV frp = pv(m, dest(m, farright)), fra = pv(m, apex(m, farright));
                 OTri check = sym(m, farleft);
-                int cv = apex(m, check);
-                while (X[cv] < X[flp]) {
+                PV cv = pv(m, apex(m, check));
+                while (cv.x < flp.x) {
                     farleft = lprev(check);
                     flp = cv;
                     check = sym(m, farleft);
-                    cv = apex(m, check);
+                    cv = pv(m, apex(m, check));
                 }
-                while (X[fra] > X[frp]) {
+                while (fra.x > frp.x) {
                     farright = sym(m, lprev(farright));
                     frp = fra;
-                    fra = apex(m, farright);
+                    fra = pv(m, apex(m, farright));
                 }
             }
             return;
@@ -456,77 +487,73 @@ MESH_FN void merge_hulls(const Mesh& m, OTri& farleft, OTri innerleft, OTri inne
             // flip away left-hull edges that are not Delaunay w.r.t. the knitting edge (:5813-5859)
             OTri next = sym(m, lprev(leftcand));
             int nextapex = apex(m, next);
-            if (nextapex >= 0) {
-                bool bad = incircle(m, lowerleft, lowerright, upperleft, nextapex) > 0;
-                while (bad) {
-                    next = lnext(next);
-                    const OTri topcasing = sym(m, next);
-                    next = lnext(next);
-                    const OTri sidecasing = sym(m, next);
-                    bond(m, next, topcasing);
-                    bond(m, leftcand, sidecasing);
-                    leftcand = lnext(leftcand);
-                    const OTri outercasing = sym(m, leftcand);
-                    next = lprev(next);
-                    bond(m, next, outercasing);
-                    set_org(m, leftcand, lowerleft);
-                    set_dest(m, leftcand, -1);
-                    set_apex(m, leftcand, nextapex);
-                    set_org(m, next, -1);
-                    set_dest(m, next, upperleft);
-                    set_apex(m, next, nextapex);
-                    upperleft = nextapex;
-                    next = sidecasing;
-                    nextapex = apex(m, next);
-                    bad = nextapex >= 0 && incircle(m, lowerleft, lowerright, upperleft, nextapex) > 0;
-                }
+            while (nextapex >= 0) {
+                const PV na = pv(m, nextapex);
+                if (!(incircle(lowerleft, lowerright, upperleft, na) > 0)) break;
+                next = lnext(next);
+                const OTri topcasing = sym(m, next);
+                next = lnext(next);
+                const OTri sidecasing = sym(m, next);
+                bond(m, next, topcasing);
+                bond(m, leftcand, sidecasing);
+                leftcand = lnext(leftcand);
+                const OTri outercasing = sym(m, leftcand);
+                next = lprev(next);
+                bond(m, next, outercasing);
+                set_org(m, leftcand, lowerleft.id);
+                set_dest(m, leftcand, -1);
+                set_apex(m, leftcand, nextapex);
+                set_org(m, next, -1);
+                set_dest(m, next, upperleft.id);
+                set_apex(m, next, nextapex);
+                upperleft = na;
+                next = sidecasing;
+                nextapex = apex(m, next);
             }
         }
         if (!rightdone) {
             // same on the right hull (:5861-5907)
             OTri next = sym(m, lnext(rightcand));
             int nextapex = apex(m, next);
-            if (nextapex >= 0) {
-                bool bad = incircle(m, lowerleft, lowerright, upperright, nextapex) > 0;
-                while (bad) {
-                    next = lprev(next);
-                    const OTri topcasing = sym(m, next);
-                    next = lprev(next);
-                    const OTri sidecasing = sym(m, next);
-                    bond(m, next, topcasing);
-                    bond(m, rightcand, sidecasing);
-                    rightcand = lprev(rightcand);
-                    const OTri outercasing = sym(m, rightcand);
-                    next = lnext(next);
-                    bond(m, next, outercasing);
-                    set_org(m, rightcand, -1);
-                    set_dest(m, rightcand, lowerright);
-                    set_apex(m, rightcand, nextapex);
-                    set_org(m, next, upperright);
-                    set_dest(m, next, -1);
-                    set_apex(m, next, nextapex);
-                    upperright = nextapex;
-                    next = sidecasing;
-                    nextapex = apex(m, next);
-                    bad = nextapex >= 0 && incircle(m, lowerleft, lowerright, upperright, nextapex) > 0;
-                }
+            while (nextapex >= 0) {
+                const PV na = pv(m, nextapex);
+                if (!(incircle(lowerleft, lowerright, upperright, na) > 0)) break;
+                next = lprev(next);
+                const OTri topcasing = sym(m, next);
+                next = lprev(next);
+                const OTri sidecasing = sym(m, next);
+                bond(m, next, topcasing);
+                bond(m, rightcand, sidecasing);
+                rightcand = lprev(rightcand);
+                const OTri outercasing = sym(m, rightcand);
+                next = lnext(next);
+                bond(m, next, outercasing);
+                set_org(m, rightcand, -1);
+                set_dest(m, rightcand, lowerright.id);
+                set_apex(m, rightcand, nextapex);
+                set_org(m, next, upperright.id);
+                set_dest(m, next, -1);
+                set_apex(m, next, nextapex);
+                upperright = na;
+                next = sidecasing;
+                nextapex = apex(m, next);
             }
         }
         // choose the next tooth; on co-circular quads the LEFT candidate wins (:5908-5910)
-        if (leftdone || (!rightdone && incircle(m, upperleft, lowerleft, lowerright, upperright) > 0)) {
+        if (leftdone || (!rightdone && incircle(upperleft, lowerleft, lowerright, upperright) > 0)) {
             bond(m, base, rightcand);
             base = lprev(rightcand);
-            set_dest(m, base, lowerleft);
+            set_dest(m, base, lowerleft.id);
             lowerright = upperright;
             rightcand = sym(m, base);
-            upperright = apex(m, rightcand);
+            upperright = pv(m, apex(m, rightcand));
         } else {
             bond(m, base, leftcand);
             base = lnext(leftcand);
-            set_org(m, base, lowerright);
+            set_org(m, base, lowerright.id);
             lowerleft = upperleft;
             leftcand = sym(m, base);
-            upperleft = apex(m, leftcand);
+            upperleft = pv(m, apex(m, leftcand));
         }
     }
 }

@@ -35,9 +35,11 @@ int mesh_emulate_lattice(int Wc, int Hc, int step, int win, int thr, int need, i
     Lattice L{Wc, Hc, Wc + 2 * kPadC, step, pad.data()};
     emu.phase([&](int t, int n) { lattice_load(L, dcan, t, n); });
     int rounds = 0;
+    auto or16 = [](int16_t* p, int bits) { *p = (int16_t)(*p | bits); };
+    auto and16 = [](int16_t* p, int bits) { *p = (int16_t)(*p & bits); };
     for (;;) {
         bool changed = false;
-        emu.phase([&](int t, int n) { changed |= incon_round(L, win, thr, need, t, n); });
+        emu.phase([&](int t, int n) { changed |= incon_round(L, win, thr, need, rounds, t, n, or16, and16); });
         rounds++;
         if (!changed) break;
     }
@@ -80,7 +82,9 @@ int mesh_emulate_delaunay(const int32_t* support, int n, int right_image, int W,
         emu.phase([&](int t, int k) { order_commit(o, axis, t, k); });
     }
     std::vector<int32_t> nbr(3 * (size_t)(2 * n)), vtx(3 * (size_t)(2 * n)), hull(2 * (size_t)n);
-    Mesh m{n, x.data(), y.data(), xs.data(), nbr.data(), vtx.data(), hull.data()};
+    std::vector<uint32_t> xy(n);
+    for (int i = 0; i < n; i++) xy[i] = ((uint32_t)x[i] << 16) | (uint32_t)y[i];
+    Mesh m{n, xy.data(), xs.data(), nbr.data(), vtx.data(), hull.data()};
     for (int depth = tree_depth(n); depth >= 0; depth--)
         emu.phase([&](int t, int k) { triangulate_depth(m, depth, t, k); });
     const int nt_pool = 2 * n - 2;

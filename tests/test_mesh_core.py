@@ -76,6 +76,7 @@ def test_random_lattices_match_the_sequential_host_stage(emu):
         base = rng.integers(0, 60, (Hc, Wc))
         smooth = (np.add.outer(np.arange(Hc), np.arange(Wc)) // 3) % 50
         d = np.where(rng.random((Hc, Wc)) < 0.5, smooth, base)
+        d = np.minimum(d, np.maximum(5 * np.arange(Wc) - 5, 0)[None, :])     # K2 only returns d <= u - 5 (elas.cpp:384-387)
         d = np.where(rng.random((Hc, Wc)) < rng.choice([0.1, 0.3, 0.6]), -1, d).astype(np.int16)
         d[0, :] = 0; d[:, 0] = 0                      # calloc'ed row/column
         W, H = Wc * 5 - 2, Hc * 5 - 1
