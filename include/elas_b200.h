@@ -134,6 +134,24 @@ int32_t elas_b200_process_batch_device(elas_b200_ctx* ctx, int32_t n,
                                        int32_t bytes_per_line, int32_t* status);
 
 /* ------------------------------------------------------------------------------------------
+ * 2a. Several GPUs from ONE process (a C++ host like stereomapper needs no launcher): one context per device,
+ *     every context gets the same parameter block (the path's only "broadcast"), frame i of a batch goes to
+ *     device i mod n (stereo pairs are independent: stereothread.cpp:113 builds a fresh Elas per frame), the
+ *     per-device batches run concurrently.  devices == NULL: devices 0..n_devices-1.  Host buffers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct elas_b200_multi elas_b200_multi;
+int32_t elas_b200_multi_create(elas_b200_multi** out, const int32_t* devices, int32_t n_devices,
+                               const elas_b200_params* p, int32_t width, int32_t height,
+                               int32_t n_groups, int32_t frames_per_group, int32_t n_workers);
+void    elas_b200_multi_destroy(elas_b200_multi* m);
+int32_t elas_b200_multi_device_count(elas_b200_multi* m);
+elas_b200_ctx* elas_b200_multi_context(elas_b200_multi* m, int32_t i);      /* for the introspection entries */
+int32_t elas_b200_multi_process_batch(elas_b200_multi* m, int32_t n,
+                                      const uint8_t* const* I1, const uint8_t* const* I2,
+                                      float* const* D1, float* const* D2,
+                                      int32_t bytes_per_line, int32_t* status);
+
+/* ------------------------------------------------------------------------------------------
  * 2b. The consumers of D1 inside StereoThread::run, computed where D1 already is (HBM):
  *     the HSV colour map shown by View2D (stereothread.cpp:116-147) and the back-projected
  *     map StereoThread::createCurrentMap builds for the 3-D reconstruction (:180-255).

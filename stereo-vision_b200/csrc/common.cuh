@@ -61,7 +61,7 @@ static_assert(sizeof(FrameHeader) == 32, "FrameHeader is 32 bytes");
 
 // Element strides between consecutive frames of a group (frames batched per launch, blockIdx.z / .y)
 struct GroupStrides {
-    size_t img, desc, dcan, support, tri, units, traster, planes, scratch, grid, lists, map, D, mesh_scratch;
+    size_t img, desc, dcan, support, tri, units, traster, planes, scratch, grid, lists, map, D, mesh_scratch, lat_work, seg_nodes;
 };
 
 #ifdef __CUDACC__
@@ -112,7 +112,7 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
 // K3  lattice filters + support list (elas.cpp:174-279, :496-517), one CTA per frame; fills hdr[f].n_support
 bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p);
 void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
-                    int32_t* support, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s);
+                    int32_t* support, int32_t* work, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K4  Delaunay triangulation of both images + scan-conversion work units (elas.cpp:534-600, triangle.cpp), one CTA
 //     per frame and image; fills hdr[f].n_tri / n_units / ovf_from
 void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, int32_t* tri2, int32_t* units1, int32_t* units2,
@@ -151,20 +151,21 @@ size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p);
 // K8  left/right consistency (elas.cpp:1122-1204); O2 = per-frame destination of the checked right map
 void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
                      float* O1, const OutTable& O2, size_t D_stride, int n_frames, cudaStream_t s);
-// K9  speckle removal (elas.cpp:1208-1326)
-// apply = false: stop after the component sizes are known; launch_post_fused then applies them
-void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, size_t D_stride, int n_frames, cudaStream_t s, bool apply = true, bool rows_done = false);
-// K8 + K9's row step for D1 in one kernel (rows staged in shared memory)
+// K9  speckle removal (elas.cpp:1208-1326): tile-local labelling in shared memory + a global union-find on the few
+// small components that touch tile borders (k_postproc.cu).  label = one int32 per pixel, nodes = segment_node_ints()
+// int32 per frame.  apply = false: stop when the sizes are known; launch_post_fused then applies them
+size_t segment_node_ints(const FrameGeom& g);
+void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* label, int32_t* nodes,
+                     size_t D_stride, size_t nodes_stride, int n_frames, cudaStream_t s, bool apply = true);
+// K8 with both rows staged in shared memory
 bool lr_rows_fusable(const FrameGeom& g);
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, const OutTable& O2, int32_t* parent, int32_t* size, int16_t* O2_i16, size_t D_stride,
-                    int n_frames, cudaStream_t s);
+                    float* O1, const OutTable& O2, int16_t* O2_i16, size_t D_stride, int n_frames, cudaStream_t s);
 // K9 apply + K10 + K11 in one tiled kernel (ipol_gap_width <= 3, no add_corners); out must not alias in
 bool post_fusable(const elas_b200_params& p);
-void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
-                       const int32_t* size, const OutTable& out, float* dump_seg, float* dump_gap, size_t D_stride,
-                       int n_frames, cudaStream_t s);
+void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* label,
+                       const int32_t* nodes, size_t nodes_stride, const OutTable& out, float* dump_seg, float* dump_gap,
+                       size_t D_stride, int n_frames, cudaStream_t s);
 // K10 gap interpolation (elas.cpp:1330-1530), K11 adaptive mean (elas.cpp:1535-1754), K12 median (elas.cpp:1758-1838):
 // in place on D with one scratch plane per frame
 void launch_gap(const FrameGeom& g, const elas_b200_params& p, float* D, float* tmp, size_t D_stride, size_t tmp_stride,

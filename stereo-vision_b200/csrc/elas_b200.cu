@@ -83,6 +83,7 @@ struct Group {
     int32_t* d_tri[2] = {nullptr, nullptr};    // (c1,c2,c3) triples
     int32_t* d_units[2] = {nullptr, nullptr};  // scan-conversion work units
     int32_t* d_mesh_scratch = nullptr;         // k_delaunay working memory beyond shared memory
+    int32_t* d_lat_work = nullptr;             // k_lattice: supporter counts + two work lists
     FrameHeader* d_hdr = nullptr;
     TriRaster* d_traster[2] = {nullptr, nullptr};
     float* d_planes[2] = {nullptr, nullptr};   // (t1a,t1b,t1c,t2a,t2b,t2c) per triangle
@@ -93,8 +94,8 @@ struct Group {
     float* d_raw[2] = {nullptr, nullptr};      // K7 output; plane 0 is reused for the final left map
     float* d_D[2] = {nullptr, nullptr};        // after the L/R check and post-processing
     float* d_tmp = nullptr;                    // two planes of scratch per frame
-    int32_t* d_parent = nullptr;
-    int32_t* d_size = nullptr;
+    int32_t* d_seg_label = nullptr;            // speckle removal: label per pixel
+    int32_t* d_seg_nodes = nullptr;            // ... and the open components on tile borders
     int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
     // pinned host
     uint8_t* h_img[2] = {nullptr, nullptr};    // staging for images that arrive in pageable host memory
@@ -202,9 +203,9 @@ void free_group(Group& s)
         cudaFree(s.d_traster[k]); cudaFree(s.d_grid[k]); cudaFree(s.d_lists[k]);
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]); cudaFree(s.d_planes[k]);
     }
-    cudaFree(s.d_dcan_raw); cudaFree(s.d_dcan); cudaFree(s.d_dcan_incon); cudaFree(s.d_support); cudaFree(s.d_mesh_scratch);
+    cudaFree(s.d_dcan_raw); cudaFree(s.d_dcan); cudaFree(s.d_dcan_incon); cudaFree(s.d_support); cudaFree(s.d_mesh_scratch); cudaFree(s.d_lat_work);
     cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16); cudaFreeHost(s.h_hdr);
-    cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp); cudaFree(s.d_parent); cudaFree(s.d_size);
+    cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp); cudaFree(s.d_seg_label); cudaFree(s.d_seg_nodes);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
@@ -252,7 +253,10 @@ int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
     CK(cudaMalloc(&s.d_hdr, n * sizeof(FrameHeader)));
     CK(cudaMemset(s.d_hdr, 0, n * sizeof(FrameHeader)));
     CK(cudaMallocHost(&s.h_hdr, n * sizeof(FrameHeader)));
-    if (c->mesh_device) CK(cudaMalloc(&s.d_mesh_scratch, n * 2 * st.mesh_scratch * 4));
+    if (c->mesh_device) {
+        CK(cudaMalloc(&s.d_mesh_scratch, n * 2 * st.mesh_scratch * 4));
+        CK(cudaMalloc(&s.d_lat_work, n * st.lat_work * 4));
+    }
     else {
         CK(cudaMallocHost(&s.h_dcan, n * st.dcan * 2));
         CK(cudaMallocHost(&s.h_tables, table_ints(c) * 4));
@@ -260,8 +264,8 @@ int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
     CK(cudaMalloc(&s.d_grid_scratch, n * st.scratch * 4));                  // per frame two buffers of [2][cells] words
     CK(cudaMemset(s.d_grid_scratch, 0, n * st.scratch * 4));
     CK(cudaMalloc(&s.d_tmp, n * 2 * st.D * 4));
-    CK(cudaMalloc(&s.d_parent, n * st.D * 4));
-    CK(cudaMalloc(&s.d_size, n * st.D * 4));
+    CK(cudaMalloc(&s.d_seg_label, n * st.D * 4));
+    CK(cudaMalloc(&s.d_seg_nodes, n * st.seg_nodes * 4));
     CK(cudaMalloc(&s.d_D2_i16, n * st.D * 2));
     CK(cudaMallocHost(&s.h_D2_i16, n * st.D * 2));
     return ELAS_B200_OK;
@@ -463,7 +467,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     // ---- mesh stage: lattice filters, support list, Delaunay x2, raster units ---------------------------------------------
     if (c->mesh_device) {
         if (s.capture && !s.d_dcan_incon) CK(cudaMalloc(&s.d_dcan_incon, (size_t)s.cap * gs.dcan * 2));
-        launch_lattice(g, p, s.d_dcan_raw, s.d_dcan, s.capture ? s.d_dcan_incon : nullptr, s.d_support, s.d_hdr, gs, n, st);
+        launch_lattice(g, p, s.d_dcan_raw, s.d_dcan, s.capture ? s.d_dcan_incon : nullptr, s.d_support, s.d_lat_work, s.d_hdr, gs, n, st);
         mark(c, s, "lattice");
         launch_delaunay(g, s.d_support, s.d_tri[0], s.d_tri[1], s.d_units[0], s.d_units[1], c->unit_cap, s.d_hdr,
                         s.d_mesh_scratch, gs, n, st);
@@ -541,8 +545,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     const bool d2_i16 = all_host && !any_direct_d2 && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
     OutTable lr_d2 = out_table(s.d_D[1], gs.D, n);
     if (n_post == 1) for (int f = 0; f < n; f++) if (direct[1][f]) lr_d2.p[f] = s.io[f].D2;
-    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, s.d_parent, s.d_size,
-                                   d2_i16 ? s.d_D2_i16 : nullptr, gs.D, n, st);
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, d2_i16 ? s.d_D2_i16 : nullptr, gs.D, n, st);
     else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, gs.D, n, st);       // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
@@ -555,11 +558,11 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         // speckle sizes (K9 rows/merge/count), then ONE kernel for speckle apply + gap interpolation +
         // adaptive mean; it reads d_D and writes the final map (d_raw is dead after the L/R check)
         for (int k = 0; k < n_post; k++) {
-            launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, gs.D, n, st, false, rows_fused && k == 0);
+            launch_segments(g, p, s.d_D[k], s.d_seg_label, s.d_seg_nodes, gs.D, gs.seg_nodes, n, st, false);
             mark(c, s, k ? "segments2" : "segments");
             final_map[k] = out_table(s.d_raw[k], gs.D, n);
             for (int f = 0; f < n; f++) if (direct[k][f]) final_map[k].p[f] = k ? s.io[f].D2 : s.io[f].D1;
-            launch_post_fused(g, p, s.d_D[k], s.d_parent, s.d_size, final_map[k],
+            launch_post_fused(g, p, s.d_D[k], s.d_seg_label, s.d_seg_nodes, gs.seg_nodes, final_map[k],
                               s.capture ? s.d_tmp : nullptr, s.capture ? s.d_tmp + ND : nullptr, gs.D, n, st);
             if (s.capture) {
                 if (int32_t rc = grab(s, k ? "D2_seg" : "D1_seg", s.d_tmp, ND * 4)) return rc;
@@ -573,7 +576,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         }
     } else {
         // the unfused chain works in place on the group's buffers (settings outside the ROBOTICS family)
-        for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_parent, s.d_size, gs.D, n, st, true, rows_fused && k == 0);
+        for (int k = 0; k < n_post; k++) launch_segments(g, p, s.d_D[k], s.d_seg_label, s.d_seg_nodes, gs.D, gs.seg_nodes, n, st, true);
         mark(c, s, "segments");
         if (s.capture) {
             if (int32_t rc = grab(s, "D1_seg", s.d_D[0], ND * 4)) return rc;
@@ -890,6 +893,8 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
         st.map = (size_t)map_pitch(g) * g.H;          // int32
         st.D = (size_t)g.Dw * g.Dh;                   // float
         st.mesh_scratch = 18 * (size_t)c->support_cap + 8;
+        st.lat_work = 3 * (size_t)g.Wc * g.Hc;
+        st.seg_nodes = segment_node_ints(g);
     }
     for (int i = 0; i < n_groups; i++) {
         c->groups.emplace_back(new Group);
@@ -954,6 +959,71 @@ int32_t elas_b200_process_batch_device(elas_b200_ctx* c, int32_t n, const uint8_
                                        int32_t bytes_per_line, int32_t* status)
 {
     return run_batch(c, n, dI1, dI2, dD1, dD2, bytes_per_line, status, true);
+}
+
+// ---- several GPUs from one process: frames are sharded round-robin over per-device contexts -----------
+struct elas_b200_multi {
+    std::vector<elas_b200_ctx*> ctx;
+};
+
+int32_t elas_b200_multi_create(elas_b200_multi** out, const int32_t* devices, int32_t n_devices, const elas_b200_params* p,
+                               int32_t width, int32_t height, int32_t n_groups, int32_t frames_per_group, int32_t n_workers)
+{
+    if (!out || n_devices < 1 || n_devices > 64) return ELAS_B200_E_BAD_ARG;
+    *out = nullptr;
+    std::unique_ptr<elas_b200_multi> m(new elas_b200_multi);
+    for (int i = 0; i < n_devices; i++) {
+        elas_b200_ctx* c = nullptr;
+        // every context receives the same parameter block: the path's one "broadcast"
+        const int32_t rc = elas_b200_create_grouped(&c, devices ? devices[i] : i, p, width, height, n_groups, frames_per_group, n_workers);
+        if (rc) {
+            for (elas_b200_ctx* x : m->ctx) elas_b200_destroy(x);
+            return rc;
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m.release();
+    return ELAS_B200_OK;
+}
+
+void elas_b200_multi_destroy(elas_b200_multi* m)
+{
+    if (!m) return;
+    for (elas_b200_ctx* c : m->ctx) elas_b200_destroy(c);
+    delete m;
+}
+
+int32_t elas_b200_multi_device_count(elas_b200_multi* m) { return m ? (int32_t)m->ctx.size() : 0; }
+elas_b200_ctx* elas_b200_multi_context(elas_b200_multi* m, int32_t i) { return m && i >= 0 && i < (int)m->ctx.size() ? m->ctx[i] : nullptr; }
+
+int32_t elas_b200_multi_process_batch(elas_b200_multi* m, int32_t n, const uint8_t* const* I1, const uint8_t* const* I2,
+                                      float* const* D1, float* const* D2, int32_t bytes_per_line, int32_t* status)
+{
+    if (!m || n < 0 || !I1 || !I2 || !D1 || !D2) return ELAS_B200_E_BAD_ARG;
+    const int nd = (int)m->ctx.size();
+    struct Shard {
+        std::vector<const uint8_t*> I1, I2; std::vector<float*> D1, D2; std::vector<int32_t> status; int32_t rc = 0;
+    };
+    std::vector<Shard> shard(nd);
+    for (int i = 0; i < n; i++) {                       // frame i -> device i mod nd
+        Shard& s = shard[i % nd];
+        s.I1.push_back(I1[i]); s.I2.push_back(I2[i]); s.D1.push_back(D1[i]); s.D2.push_back(D2[i]);
+    }
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++) {
+        Shard& s = shard[k];
+        s.status.assign(s.I1.size(), 0);
+        if (s.I1.empty()) continue;
+        th.emplace_back([&s, k, m, bytes_per_line] {
+            s.rc = run_batch(m->ctx[k], (int32_t)s.I1.size(), s.I1.data(), s.I2.data(), s.D1.data(), s.D2.data(),
+                             bytes_per_line, s.status.data(), false);
+        });
+    }
+    for (auto& t : th) t.join();
+    int32_t worst = 0;
+    for (int k = 0; k < nd; k++) worst = std::min(worst, shard[k].rc);
+    if (status) for (int i = 0; i < n; i++) status[i] = shard[i % nd].status[i / nd];
+    return worst;
 }
 
 int32_t elas_b200_process(const elas_b200_params* p, const uint8_t* I1, const uint8_t* I2,

@@ -68,85 +68,23 @@ __device__ void block_bitonic_sort(unsigned long long* k, int npad)
     __syncthreads();
 }
 
-// atomic bit operations on one 16-bit lattice element of shared memory, through its 32-bit word
+// atomic bit operation on one 16-bit lattice element of shared memory, through its 32-bit word
 __device__ __forceinline__ void atomic_or16(int16_t* p, int bits)
 {
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     atomicOr(reinterpret_cast<unsigned*>(a & ~(uintptr_t)3), ((unsigned)bits & 0xFFFFu) << ((a & 2) * 8));
 }
-__device__ __forceinline__ void atomic_and16(int16_t* p, int mask)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    atomicAnd(reinterpret_cast<unsigned*>(a & ~(uintptr_t)3), ~((~(unsigned)mask & 0xFFFFu) << ((a & 2) * 8)));
-}
 
-// One round of the inconsistency filter (mesh::incon_round) on the device.  The cells marked for this round are
-// first compacted into a work list (per segment of kListSegment cells, 16-bit offsets), then evaluated one cell
-// per THREAD: 32 different cells per warp instruction, every lane busy, rows nearest the centre first and the count
-// stops at incon_min_support.  A cell that is invalidated marks its dependents for the next round.
-constexpr int kListSegment = 16384;
-
-__device__ __forceinline__ bool incon_fails_early(const mesh::Lattice& L, const int16_t* c, int x, int win, int thr, int need)
+// count0 of every cell of the unfiltered lattice (mesh::incon_count0): the one part of the inconsistency filter
+// that is proportional to cells x window, spread over the whole GPU (one thread per cell) instead of one CTA
+__global__ void __launch_bounds__(256)
+k_lattice_count(int Wc, int Hc, int win, int thr, const int16_t* __restrict__ dcan_raw, int32_t* __restrict__ work,
+                size_t dcan_stride, size_t work_stride)
 {
-    using namespace mesh;
-    int support = 0;
-    for (int k = 0; k <= 2 * win && support < need; k++) {
-        const int dv = (k & 1) ? (k + 1) / 2 : -(k / 2);                  // v, v+1, v-1, v+2, v-2, ...
-        const int16_t* row = c + dv * L.pitch;
-        for (int du = -win; du <= win; du++) {
-            const int y = row[du];
-            const bool gone = y < 0 || ((y & kRemoved) && (du < 0 || (du == 0 && dv < 0)));
-            support += !gone && iabs((x & kValueMask) - (y & kValueMask)) <= thr;
-        }
-    }
-    return support < need;
-}
-
-__device__ bool incon_round_list(const mesh::Lattice& L, int win, int thr, int need, int round, uint16_t* list, int* list_n)
-{
-    using namespace mesh;
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-    const int now = (round & 1) ? kDirty1 : kDirty0, next = (round & 1) ? kDirty0 : kDirty1;
-    const int cells = L.Wc * L.Hc;
-    bool changed = false;
-    for (int seg = 0; seg < cells; seg += kListSegment) {
-        if (tid == 0) *list_n = 0;
-        __syncthreads();
-        const int seg_end = min(seg + kListSegment, cells);
-        for (int i0 = seg + (tid & ~31); i0 < seg_end; i0 += T) {          // whole warps stay together for the ballot
-            const int i = i0 + lane;
-            bool todo = false;
-            if (i < seg_end) {
-                const int vc = i / L.Wc, uc = i - vc * L.Wc;
-                const int x = L.P[lat_index(L, uc, vc)];
-                todo = x >= 0 && !(x & kRemoved) && (x & now);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, todo);
-            int at = 0;
-            if (lane == 0 && m) at = atomicAdd(list_n, __popc(m));
-            at = __shfl_sync(0xffffffffu, at, 0);
-            if (todo) list[at + __popc(m & ((1u << lane) - 1))] = (uint16_t)(i - seg);
-        }
-        __syncthreads();
-        const int n = *list_n;
-        for (int k = tid; k < n; k += T) {
-            const int i = seg + list[k];
-            const int vc = i / L.Wc, uc = i - vc * L.Wc;
-            int16_t* c = L.P + lat_index(L, uc, vc);
-            const int x = *c;
-            atomic_and16(c, ~now);
-            if (!incon_fails_early(L, c, x, win, thr, need)) continue;
-            atomic_or16(c, kRemoved);
-            changed = true;
-            for (int dv = -win; dv <= win; dv++)
-                for (int du = (dv > 0 ? 0 : 1); du <= win; du++) {          // later in scan order only
-                    int16_t* d = c + dv * L.pitch + du;
-                    if (incon_depends(x, *d, du, dv, thr)) atomic_or16(d, next);
-                }
-        }
-        __syncthreads();
-    }
-    return changed;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Wc * Hc) return;
+    const int vc = i / Wc, uc = i - vc * Wc;
+    work[blockIdx.y * work_stride + i] = mesh::incon_count0(dcan_raw + blockIdx.y * dcan_stride, Wc, Hc, uc, vc, win, thr);
 }
 
 struct LatticeArgs {
@@ -155,8 +93,9 @@ struct LatticeArgs {
     int16_t* dcan;               // after all three filters
     int16_t* dcan_incon;         // after the inconsistency filter only (stage dump; may be null)
     int32_t* support;            // [frames][support_cap][3]
+    int32_t* work;               // [frames][3][cells]: count0 (k_lattice_count), two work lists of the propagation
     FrameHeader* hdr;
-    size_t dcan_stride, support_stride;
+    size_t dcan_stride, support_stride, work_stride;
 };
 
 __global__ void __launch_bounds__(kMeshThreads)
@@ -167,16 +106,30 @@ k_lattice(const LatticeArgs a)
     const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     mesh::Lattice L{a.Wc, a.Hc, a.Wc + 2 * mesh::kPadC, a.step, reinterpret_cast<int16_t*>(smem_raw)};
     const size_t lat_bytes = ((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15;
-    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + lat_bytes);      // [kListSegment] work list of the inconsistency rounds
-    int32_t* col = reinterpret_cast<int32_t*>(smem_raw + lat_bytes);         // [Wc + 1], after the rounds
-    __shared__ int list_n;
+    int32_t* col = reinterpret_cast<int32_t*>(smem_raw + lat_bytes);         // [Wc + 1]
+    __shared__ int n_list[2];
     const int16_t* raw = a.dcan_raw + (size_t)f * a.dcan_stride;
     int16_t* out = a.dcan + (size_t)f * a.dcan_stride;
     int32_t* support = a.support + (size_t)f * a.support_stride;
+    const int cells = a.Wc * a.Hc;
+    int32_t* cnt = a.work + (size_t)f * a.work_stride;
+    int32_t* lists[2] = {cnt + cells, cnt + 2 * cells};
 
     mesh::lattice_load(L, raw, tid, T);
+    if (tid == 0) n_list[0] = n_list[1] = 0;
     __syncthreads();
-    for (int round = 0; __syncthreads_or(incon_round_list(L, a.win, a.thr, a.need, round, list, &list_n)); round++) {}
+    // ---- inconsistency filter by propagation (see mesh_core.h) ---------------------------------------------------
+    auto atomic_add = [](int* p, int v) { return atomicAdd(p, v); };
+    auto or16 = [](int16_t* p, int bits) { atomic_or16(p, bits); };
+    mesh::incon_seed(L, cnt, a.need, lists[0], &n_list[0], tid, T, atomic_add);
+    for (int cur = 0;; cur ^= 1) {
+        __syncthreads();                                 // list `cur` is complete
+        const int n = n_list[cur];
+        if (n == 0) break;
+        mesh::incon_propagate(L, cnt, a.win, a.thr, a.need, lists[cur], n, lists[cur ^ 1], &n_list[cur ^ 1], tid, T, atomic_add, or16);
+        __syncthreads();
+        if (tid == 0) n_list[cur] = 0;                   // consumed: it is the list after next
+    }
     mesh::incon_finish(L, a.dcan_incon ? a.dcan_incon + (size_t)f * a.dcan_stride : nullptr, tid, T);
     __syncthreads();
     mesh::redundant_pass(L, true, tid, T);          // elas.cpp:501
@@ -316,7 +269,7 @@ k_delaunay(const DelaunayArgs a)
 
 size_t lattice_smem_bytes(const FrameGeom& g)
 {
-    return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + std::max<size_t>(((size_t)g.Wc + 1) * 4, (size_t)kListSegment * 2);
+    return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + ((size_t)g.Wc + 1) * 4;
 }
 
 // parameters / sizes the device mesh stage handles; everything else takes the host stage (host_stage.cc)
@@ -330,14 +283,17 @@ bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p)
 }
 
 void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
-                    int32_t* support, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s)
+                    int32_t* support, int32_t* work, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     static unsigned long long optin = 0;
     if (ensure_dynamic_smem(k_lattice, 224 * 1024, &optin) != cudaSuccess) return;
+    ELASB_PREPARE_KERNEL(k_lattice_count);
+    k_lattice_count<<<dim3((g.Wc * g.Hc + 255) / 256, n_frames), 256, 0, s>>>(g.Wc, g.Hc, p.incon_window_size, p.incon_threshold,
+                                                                             dcan_raw, work, st.dcan, st.lat_work);
     LatticeArgs a{g.Wc, g.Hc, g.step, p.incon_window_size, p.incon_threshold, p.incon_min_support,
-                  dcan_raw, dcan, dcan_incon, support, hdr, st.dcan, st.support};
+                  dcan_raw, dcan, dcan_incon, support, work, hdr, st.dcan, st.support, st.lat_work};
     k_lattice<<<n_frames, kMeshThreads, lattice_smem_bytes(g), s>>>(a);
-    count_launch();
+    count_launch(2);
 }
 
 void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, int32_t* tri2, int32_t* units1, int32_t* units2,

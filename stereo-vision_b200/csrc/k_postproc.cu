@@ -36,121 +36,21 @@ __global__ void k_lr_check(int Dw, int Dh, int subsampling, float lr_threshold,
     O1[a] = o1; O2[a] = o2;
 }
 
-// ---------------------------------------------------------------------------------------------
-// K9  speckle removal, elas.cpp:1208-1326.  The reference flood-fills 4-connected segments in
-// which neighbouring valid pixels differ by <= speckle_sim_threshold and invalidates segments with
-// fewer than speckle_size pixels.  Segments are the connected components of a symmetric relation,
-// so the result does not depend on traversal order.  Run-based labelling:
-//   rows:   every maximal horizontal run of connected pixels becomes one union-find node (its first
-//           pixel); the other pixels of the run point at it and are never touched again
-//   merge:  vertically connected pixel pairs union their runs; a pair is skipped when its left
-//           neighbour pair already joins the same two runs
-//   count:  each run adds its length to its root once (and stops adding once the root is known to be
-//           large enough -- only "size < speckle_size" is ever asked)
-//   apply:  pixel -> run -> root -> size
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool seg_conn(float a, float b, float thr)
-{
-    return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr;                    // :1281, :1285
-}
-
-// parent[] is read at L2 (ld.global.cg): other SMs hook roots concurrently.
-__device__ __forceinline__ int uf_find(int32_t* parent, int x)
-{
-    int p = parent[x];
-    while (p != x) {
-        const int gp = parent[p];
-        if (gp != p) parent[x] = gp;           // path halving
-        x = p; p = gp;
-    }
-    return x;
-}
-
-// Hooking order: a root goes under the root with the smaller PRIORITY, a fixed pseudo-random
-// permutation of the pixel index.  Index order would let the thousands of unions of a frame, which run
-// concurrently, build chains as long as the image is high (every run of a vertical structure hooking
-// under the run above it at the same moment), and every later find would walk them at L2 latency;
-// with random priorities simultaneous hooks only chain along decreasing-priority sequences, whose
-// expected length is logarithmic.
-__device__ __forceinline__ uint32_t uf_priority(int x) { return (uint32_t)x * 0x9E3779B1u; }
-
-__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
-{
-    for (;;) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
-        if (a == b) return;
-        if (uf_priority(a) < uf_priority(b)) { const int t = a; a = b; b = t; }   // hook a (larger priority) under b
-        const int old = atomicCAS(parent + a, a, b);
-        if (old == a) return;
-        a = old;
-    }
-}
-
-// one CTA per row: parent[pixel] = index of the first pixel of its run (-1 for invalid pixels).
-// `row` may live in shared memory (k_lr_rows) or in global memory (k_seg_rows).
-__device__ __forceinline__ void label_row_runs(const float* row, int Dw, int base, float thr,
-                                               int32_t* __restrict__ parent, int32_t* __restrict__ size,
-                                               int* warp_last, int* carry_s)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) *carry_s = -1;
-    __syncthreads();
-    for (int u0 = 0; u0 < Dw; u0 += 256) {
-        const int u = u0 + threadIdx.x;
-        const float d = u < Dw ? row[u] : -1.f;
-        const float dl = (u > 0 && u < Dw) ? row[u - 1] : -1.f;
-        const bool valid = d >= 0.f;
-        const bool start = valid && !seg_conn(dl, d, thr);
-        const unsigned starts = __ballot_sync(0xffffffffu, start);
-        const unsigned upto = starts & (0xffffffffu >> (31 - lane));
-        int last = upto ? u0 + (warp << 5) + 31 - __clz(upto) : -1;      // most recent start in this warp
-        if (lane == 31) warp_last[warp] = last;
-        __syncthreads();
-        const int carry = *carry_s;
-        if (last < 0) {
-            for (int w = warp - 1; w >= 0 && last < 0; w--) last = warp_last[w];
-            if (last < 0) last = carry;
-        }
-        if (u < Dw) {
-            parent[base + u] = valid ? base + last : -1;
-            if (start) size[base + u] = 0;          // sizes are only ever read and accumulated at run starts (roots)
-        }
-        __syncthreads();
-        if (threadIdx.x == 255) *carry_s = last >= 0 ? last : carry;     // runs never span an invalid pixel
-        __syncthreads();
-    }
-}
-
+// K8 with the rows staged in shared memory: a CTA owns one row of both maps.  The L/R check of a pixel only reads
+// the other map within the same row (elas.cpp:1164-1197), at a data-dependent column: from shared memory those
+// gathers cost nothing, from global memory they are uncoalesced.  The checked right map optionally leaves as int16.
 __global__ void __launch_bounds__(256)
-k_seg_rows(int Dw, float thr, const float* __restrict__ D, int32_t* __restrict__ parent, int32_t* __restrict__ size, size_t D_stride)
-{
-    __shared__ int warp_last[8];
-    __shared__ int carry_s;
-    const int v = blockIdx.x;
-    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
-    label_row_runs(D + (size_t)v * Dw, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
-}
-
-// K8 + the row step of K9 in one pass: a CTA owns one row of both maps.  The L/R check of a pixel
-// only reads the other map within the same row (elas.cpp:1164-1197), so both raw rows are staged in
-// shared memory, the checked rows are written out, and the checked D1 row -- still in shared memory --
-// is labelled into runs.
-__global__ void __launch_bounds__(256)
-k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
+k_lr_rows(int Dw, int subsampling, float lr_threshold,
           const float* __restrict__ D1, const float* __restrict__ D2,
-          float* __restrict__ O1, OutTable O2_tab, int32_t* __restrict__ parent, int32_t* __restrict__ size,
+          float* __restrict__ O1, OutTable O2_tab,
           int16_t* __restrict__ O2_i16,      // optional: O2 narrowed (exact: raw integer disparities or -10)
           size_t D_stride)
 {
-    extern __shared__ float s_rows[];          // [3][Dw]: raw D1 row, raw D2 row, checked D1 row
-    __shared__ int warp_last[8];
-    __shared__ int carry_s;
-    float* r1 = s_rows; float* r2 = s_rows + Dw; float* c1 = s_rows + 2 * Dw;
+    extern __shared__ float s_rows[];          // [2][Dw]: raw D1 row, raw D2 row
+    float* r1 = s_rows; float* r2 = s_rows + Dw;
     const int v = blockIdx.x;
     // blockIdx.y = frame of the group
     D1 += blockIdx.y * D_stride; D2 += blockIdx.y * D_stride; O1 += blockIdx.y * D_stride;
-    parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
     if (O2_i16) O2_i16 += blockIdx.y * D_stride;
     float* __restrict__ O2 = O2_tab.p[blockIdx.y];
     const size_t row = (size_t)v * Dw;
@@ -167,69 +67,244 @@ k_lr_rows(int Dw, int subsampling, float lr_threshold, float thr,
             if (!(fabsf(__fsub_rn(r1[(int)w2], d2)) > lr_threshold)) o2 = d2;
         O1[row + u] = o1;
         if (O2_i16) O2_i16[row + u] = (int16_t)o2; else O2[row + u] = o2;
-        c1[u] = o1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9  speckle removal, elas.cpp:1208-1326.  The reference flood-fills 4-connected segments in
+// which neighbouring valid pixels differ by <= speckle_sim_threshold and invalidates segments with
+// fewer than speckle_size pixels.  Segments are the connected components of a symmetric relation,
+// so the result does not depend on traversal order.  Only "is my component smaller than
+// speckle_size" is ever asked, which allows a tile-local formulation:
+//   tiles:   every 64x32 tile labels its pixels with a union-find in SHARED memory and counts the local
+//            components.  A local component of >= speckle_size pixels is large whatever lies beyond the tile
+//            (label KEEP); a smaller one that touches no neighbouring tile is final (label DROP).  Only the
+//            small components on tile borders stay open: they become nodes (tile, local root) in global memory.
+//   border:  connected pixel pairs across tile borders: node-node pairs are united (global union-find on the
+//            few open nodes), a node next to a KEEP pixel is flagged as attached to a large component.
+//   sizes:   every open node adds its pixel count (+ speckle_size if flagged) to its root.
+//   apply:   KEEP stays, DROP goes, an open node's pixels stay iff the root's total reaches speckle_size
+//            (k_post_fused, or k_seg_apply for settings outside the fused path).
+// Pointer chasing through global memory is limited to the open nodes, a few percent of the pixels.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool seg_conn(float a, float b, float thr)
+{
+    return a >= 0.f && b >= 0.f && fabsf(__fsub_rn(a, b)) <= thr;                    // :1281, :1285
+}
+
+constexpr int kSegTW = 64, kSegTH = 32, kSegTile = kSegTW * kSegTH, kSegThreads = 256;
+constexpr int kSegKeep = -2, kSegDrop = -1;      // pixel labels besides open node ids (>= 0); invalid pixels are DROP too
+
+// find with path halving (shared memory; concurrent writers only ever replace a parent by an ancestor)
+__device__ __forceinline__ int uf_find_s(int* L, int x)
+{
+    int p = L[x];
+    while (p != x) {
+        const int gp = L[p];
+        if (gp != p) L[x] = gp;
+        x = p; p = gp;
+    }
+    return x;
+}
+// union by minimum index with atomicMin (Playne & Hawick): a root is hooked under the smaller root; if another
+// thread hooked it meanwhile, the union continues with what it was hooked to
+__device__ __forceinline__ void uf_union_s(int* L, int a, int b)
+{
+    for (;;) {
+        a = uf_find_s(L, a);
+        b = uf_find_s(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct SegArgs {
+    int Dw, Dh, tiles_x, tiles_y, speckle;
+    float thr;
+    const float* D;          // frames D_stride apart
+    int32_t* label;          // per pixel: kSegKeep, kSegDrop or an open node id
+    int32_t* nodes;          // per frame [3][node_cap]: parent, pixel count (roots: total), attached-to-large flag
+    size_t D_stride, nodes_stride;
+    int node_cap;            // tiles * kSegTile
+};
+
+// One 64x32 tile per CTA, 8 warps, warp w owns tile rows 4w..4w+3.
+//   1. horizontal runs: every pixel points at the first pixel of its run (ballots, no atomics)
+//   2. vertical unions between runs (a pair is skipped when the pair to its left joins the same two runs)
+//   3. every pixel -> root; pixels per root; does the component touch a neighbouring tile
+__global__ void __launch_bounds__(kSegThreads)
+k_seg_tiles(const SegArgs a)
+{
+    __shared__ float sD[kSegTile];
+    __shared__ int sL[kSegTile];          // union-find parent (local pixel index), -1 for invalid pixels
+    __shared__ int sN[kSegTile];          // pixels per root; bit 30 = the component touches a neighbouring tile
+    const int f = blockIdx.z, x0 = blockIdx.x * kSegTW, y0 = blockIdx.y * kSegTH, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ D = a.D + f * a.D_stride;
+    int32_t* __restrict__ label = a.label + f * a.D_stride;
+    int32_t* __restrict__ node_parent = a.nodes + f * a.nodes_stride;
+    int32_t* __restrict__ node_count = node_parent + a.node_cap;
+    int32_t* __restrict__ node_flag = node_count + a.node_cap;
+    const int tile = blockIdx.y * a.tiles_x + blockIdx.x;
+    // 1. rows 4 warp .. 4 warp + 3, two 32-pixel halves each
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int ly = 4 * warp + r, y = y0 + ly;
+        int carry = -1;                    // run that reaches the end of the left half
+        float prev_last = -1.f;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int lx = 32 * h + lane, x = x0 + lx, p = ly * kSegTW + lx;
+            const float d = (x < a.Dw && y < a.Dh) ? D[(size_t)y * a.Dw + x] : -1.f;
+            float dl = __shfl_up_sync(0xffffffffu, d, 1);
+            if (lane == 0) dl = prev_last;
+            const bool valid = d >= 0.f;
+            const bool start = valid && !seg_conn(dl, d, a.thr);
+            const unsigned starts = __ballot_sync(0xffffffffu, start);
+            const unsigned upto = starts & (0xffffffffu >> (31 - lane));
+            const int run = upto ? ly * kSegTW + 32 * h + 31 - __clz(upto) : carry;     // a run never spans an invalid pixel
+            sD[p] = d;
+            sL[p] = valid ? run : -1;
+            sN[p] = 0;
+            prev_last = __shfl_sync(0xffffffffu, d, 31);
+            carry = __shfl_sync(0xffffffffu, valid ? run : -1, 31);
+        }
     }
     __syncthreads();
-    label_row_runs(c1, Dw, v * Dw, thr, parent, size, warp_last, &carry_s);
-}
-
-// k_seg_merge and k_seg_count are chains of dependent L2 accesses (find, CAS): their warps are stalled
-// almost all the time.  They run as a modest grid-stride grid (kSegCtasPerSm CTAs per SM) instead of one
-// thread per pixel, so that they occupy a quarter of an SM's thread slots while the pipeline's other
-// kernels (other slots' frames) use the issue slots they leave idle.
-constexpr int kSegCtasPerSm = 2;
-
-__global__ void __launch_bounds__(256)
-k_seg_merge(int Dw, int Dh, float thr, const float* __restrict__ D, int32_t* parent, size_t D_stride)
-{
-    const int n = Dw * (Dh - 1);
-    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride;
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        const int u = a % Dw, b = a + Dw;
-        const float da = D[a], db = D[b];
-        if (!seg_conn(da, db, thr)) continue;
-        bool a_start = true, b_start = true;
-        if (u > 0) {
-            const float la = D[a - 1], lb = D[b - 1];
-            a_start = !seg_conn(la, da, thr);
-            b_start = !seg_conn(lb, db, thr);
-            if (!a_start && !b_start && seg_conn(la, lb, thr)) continue;   // the pair to the left joins the same runs
+    // 2. vertical unions
+#pragma unroll
+    for (int k = 0; k < kSegTile / kSegThreads; k++) {
+        const int p = tid + k * kSegThreads;
+        if (p < kSegTW) continue;
+        const float d = sD[p], du = sD[p - kSegTW];
+        if (!seg_conn(du, d, a.thr)) continue;
+        if (p & (kSegTW - 1)) {
+            const float dl = sD[p - 1], dul = sD[p - kSegTW - 1];
+            if (seg_conn(dl, d, a.thr) && seg_conn(dul, du, a.thr) && seg_conn(dul, dl, a.thr)) continue;
         }
-        uf_union(parent, a_start ? a : __ldcg(parent + a), b_start ? b : __ldcg(parent + b));
+        uf_union_s(sL, sL[p], sL[p - kSegTW]);
+    }
+    __syncthreads();
+    // 3. roots, counts, border flag
+    int root[kSegTile / kSegThreads];
+#pragma unroll
+    for (int k = 0; k < kSegTile / kSegThreads; k++) {
+        const int p = tid + k * kSegThreads;
+        root[k] = sL[p] >= 0 ? uf_find_s(sL, sL[p]) : -1;
+        if (root[k] < 0) continue;
+        const int lx = p & (kSegTW - 1), ly = p / kSegTW, x = x0 + lx, y = y0 + ly;
+        // on a tile edge that has a neighbouring tile behind it
+        const bool edge = (lx == 0 && x > 0) || (lx == kSegTW - 1 && x + 1 < a.Dw) || (ly == 0 && y > 0) || (ly == kSegTH - 1 && y + 1 < a.Dh);
+        // one add per warp and root where neighbouring lanes share it
+        const unsigned same = __match_any_sync(__activemask(), root[k]);
+        if (lane == __ffs(same) - 1) atomicAdd(&sN[root[k]], __popc(same));      // counts stay below 2^12
+        if (edge) atomicOr(&sN[root[k]], 1 << 30);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSegTile / kSegThreads; k++) {
+        const int p = tid + k * kSegThreads, x = x0 + (p & (kSegTW - 1)), y = y0 + (p / kSegTW);
+        if (x >= a.Dw || y >= a.Dh) continue;
+        int l = kSegDrop;
+        if (root[k] >= 0) {
+            const int n = sN[root[k]], count = n & 0xFFF, open = n >> 30;
+            if (count >= a.speckle) l = kSegKeep;
+            else if (open) {
+                l = tile * kSegTile + root[k];
+                if (root[k] == p) { node_parent[l] = l; node_count[l] = count; node_flag[l] = 0; }
+            }
+        }
+        label[(size_t)y * a.Dw + x] = l;
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_seg_count(int Dw, int Dh, float thr, int speckle, const float* __restrict__ D,
-            int32_t* parent, int32_t* size, size_t D_stride)
+// global union-find on the open nodes (few, short chains): hook the larger index under the smaller
+__device__ __forceinline__ int uf_find_g(int32_t* parent, int x)
 {
-    const int n = Dw * Dh;
-    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        const int u = a % Dw;
-        const float d = D[a];
-        if (!(d >= 0.f)) continue;
-        if (u + 1 < Dw && seg_conn(d, D[a + 1], thr)) continue;           // not the last pixel of its run
-        const bool is_start = !(u > 0 && seg_conn(D[a - 1], d, thr));
-        const int start = is_start ? a : __ldcg(parent + a);
-        const int root = uf_find(parent, start);
-        __stcg(parent + start, root);                                           // every run ends up one hop from its root
-        if (__ldcg(size + root) < speckle) atomicAdd(size + root, a - start + 1);
+    int p = __ldcg(parent + x);
+    while (p != x) { x = p; p = __ldcg(parent + x); }
+    return x;
+}
+__device__ __forceinline__ void uf_union_g(int32_t* parent, int a, int b)
+{
+    for (;;) {
+        a = uf_find_g(parent, a);
+        b = uf_find_g(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
     }
 }
 
-__global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int32_t* __restrict__ parent,
-                            const int32_t* __restrict__ size, size_t D_stride)
+// one thread per pixel pair across a tile border: items [0, nv) = vertical borders (x = 64k: pixels (x-1,y),(x,y)),
+// items [nv, nv + nh) = horizontal borders (y = 32k: pixels (x,y-1),(x,y))
+__global__ void __launch_bounds__(256)
+k_seg_border(const SegArgs a)
+{
+    const int f = blockIdx.y;
+    const float* __restrict__ D = a.D + f * a.D_stride;
+    const int32_t* __restrict__ label = a.label + f * a.D_stride;
+    int32_t* node_parent = a.nodes + f * a.nodes_stride;
+    int32_t* node_flag = node_parent + 2 * a.node_cap;
+    const int nv = (a.tiles_x - 1) * a.Dh, nh = (a.tiles_y - 1) * a.Dw;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < nv + nh; i += gridDim.x * 256) {
+        int pa, pb;
+        if (i < nv) { const int bx = i / a.Dh, y = i - bx * a.Dh; pb = y * a.Dw + (bx + 1) * kSegTW; pa = pb - 1; }
+        else { const int j = i - nv, by = j / a.Dw, x = j - by * a.Dw; pb = (by + 1) * kSegTH * a.Dw + x; pa = pb - a.Dw; }
+        if (!seg_conn(D[pa], D[pb], a.thr)) continue;
+        const int la = label[pa], lb = label[pb];
+        if (la >= 0 && lb >= 0) uf_union_g(node_parent, la, lb);
+        else if (la >= 0 && lb == kSegKeep) node_flag[la] = 1;
+        else if (lb >= 0 && la == kSegKeep) node_flag[lb] = 1;
+    }
+}
+
+// one thread per pixel: the root pixel of every open local component adds the component to its global root
+__global__ void __launch_bounds__(256)
+k_seg_sizes(const SegArgs a)
+{
+    const int f = blockIdx.y;
+    const int32_t* __restrict__ label = a.label + f * a.D_stride;
+    int32_t* node_parent = a.nodes + f * a.nodes_stride;
+    int32_t* node_count = node_parent + a.node_cap;
+    const int32_t* node_flag = node_count + a.node_cap;
+    const int n = a.Dw * a.Dh;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int l = label[i];
+        if (l < 0) continue;
+        // is this pixel the root pixel of its local component?  node id = tile * kSegTile + local index
+        const int y = i / a.Dw, x = i - y * a.Dw;
+        const int tile = (y / kSegTH) * a.tiles_x + x / kSegTW, local = (y % kSegTH) * kSegTW + (x % kSegTW);
+        if (l != tile * kSegTile + local) continue;
+        const int root = uf_find_g(node_parent, l);
+        const int add = (root != l ? __ldcg(node_count + l) : 0) + (node_flag[l] ? a.speckle : 0);
+        if (add) atomicAdd(node_count + root, add);
+    }
+}
+
+// does the pixel with this label survive speckle removal?  (open nodes: the root's total decides)
+__device__ __forceinline__ bool seg_keeps(int l, const int32_t* __restrict__ node_parent, const int32_t* __restrict__ node_count, int speckle)
+{
+    if (l < 0) return l == kSegKeep;
+    int r = l, p;
+    while ((p = node_parent[r]) != r) r = p;
+    return node_count[r] >= speckle;
+}
+
+__global__ void k_seg_apply(int n, int speckle, float* __restrict__ D, const int32_t* __restrict__ label,
+                            const int32_t* __restrict__ nodes, int node_cap, size_t D_stride, size_t nodes_stride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    D += blockIdx.y * D_stride; parent += blockIdx.y * D_stride; size += blockIdx.y * D_stride;
-    const float d = D[i];
-    if (d >= 0.f) {
-        int root = parent[i];                      // pixel -> run start -> (usually one hop) -> root
-        for (int up = parent[root]; up != root; up = parent[root]) root = up;
-        if (size[root] < speckle) D[i] = (float)kInvalid;                              // :1309-1317
-    } else if (1 < speckle) D[i] = (float)kInvalid;   // an invalid pixel is a segment of one (:1248-1250)
+    D += blockIdx.y * D_stride; label += blockIdx.y * D_stride; nodes += blockIdx.y * nodes_stride;
+    // an invalid pixel is a segment of one (:1248-1250): it is (re)written as invalid whenever speckle_size > 1
+    const bool valid = D[i] >= 0.f;
+    if (valid ? !seg_keeps(label[i], nodes, nodes + node_cap, speckle) : 1 < speckle) D[i] = (float)kInvalid;   // :1309-1317
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,8 +491,10 @@ constexpr int kFuseTW = 64, kFuseTH = 32, kFuseThreads = 512;
 struct FuseArgs {
     int Dw, Dh, gap, speckle, apply;     // apply: fold k_seg_apply in (parent/size valid)
     const float* in;                     // D after the L/R check (apply) or after speckle removal; frames D_stride apart
-    const int32_t* parent;
-    const int32_t* size;
+    const int32_t* label;                // speckle labels and open nodes (k_seg_*)
+    const int32_t* nodes;
+    int node_cap;
+    size_t nodes_stride;
     OutTable out;                        // final map of every frame of the group (must not alias in)
     float* dump_seg;                     // optional stage dumps (tests, single frame): D after speckle removal, after gap interpolation
     float* dump_gap;
@@ -449,7 +526,7 @@ k_post_fused(const FuseArgs a_)
     // blockIdx.z = frame of the group
     FuseArgs a = a_;
     a.in += blockIdx.z * a.D_stride;
-    if (a.apply) { a.parent += blockIdx.z * a.D_stride; a.size += blockIdx.z * a.D_stride; }
+    if (a.apply) { a.label += blockIdx.z * a.D_stride; a.nodes += blockIdx.z * a.nodes_stride; }
     float* __restrict__ out = a.out.p[blockIdx.z];
     constexpr int BACK = MEAN ? (TAPS == 8 ? 4 : 2) : 0, FWD = MEAN ? TAPS - BACK - 1 : 0, G = kFuseGap;
     constexpr int AW = kFuseTW + BACK + FWD + 2 * G, AH = kFuseTH + BACK + FWD + 2 * G;
@@ -466,7 +543,7 @@ k_post_fused(const FuseArgs a_)
     // pixel -> run start -> root -> size is a chain of dependent L2 loads: four elements per thread are
     // walked together so that the chains overlap
     for (int i0 = threadIdx.x; i0 < AH * AW; i0 += 4 * kFuseThreads) {
-        int idx[4], root[4];
+        int idx[4], lab[4];
         float d[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -479,18 +556,12 @@ k_post_fused(const FuseArgs a_)
         for (int k = 0; k < 4; k++) d[k] = idx[k] >= 0 ? a.in[idx[k]] : (float)kInvalid;
         if (a.apply) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) root[k] = d[k] >= 0.f ? a.parent[idx[k]] : -1;      // run start
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (root[k] >= 0) root[k] = a.parent[root[k]];      // its root (k_seg_count left it one hop away)
+            for (int k = 0; k < 4; k++) lab[k] = d[k] >= 0.f ? a.label[idx[k]] : kSegDrop;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (root[k] < 0) continue;
-                for (int up = a.parent[root[k]]; up != root[k]; up = a.parent[root[k]]) root[k] = up;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (root[k] >= 0) { if (a.size[root[k]] < a.speckle) d[k] = (float)kInvalid; }
-                else if (1 < a.speckle) d[k] = (float)kInvalid;     // an invalid pixel is a segment of one (:1248-1250)
+                // an invalid pixel is a segment of one (:1248-1250); 1 < speckle_size in every supported setting of this path
+                if (!(d[k] >= 0.f)) { if (1 < a.speckle) d[k] = (float)kInvalid; }
+                else if (!seg_keeps(lab[k], a.nodes, a.nodes + a.node_cap, a.speckle)) d[k] = (float)kInvalid;
             }
         }
 #pragma unroll
@@ -580,41 +651,49 @@ void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float*
     count_launch();
 }
 
-bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 12 <= 160 * 1024; }
+bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 8 <= 160 * 1024; }
 
-// K8 for both maps + the run labelling of D1 (launch_segments(..., rows_done = true) continues from there)
+// K8 for both maps, rows staged in shared memory
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, const OutTable& O2, int32_t* parent, int32_t* size, int16_t* O2_i16, size_t D_stride,
-                    int n_frames, cudaStream_t s)
+                    float* O1, const OutTable& O2, int16_t* O2_i16, size_t D_stride, int n_frames, cudaStream_t s)
 {
-    const size_t smem = (size_t)g.Dw * 12;
+    const size_t smem = (size_t)g.Dw * 8;
     static unsigned long long optin = 0;
     if (ensure_dynamic_smem(k_lr_rows, 160 * 1024, &optin) != cudaSuccess) return;
-    k_lr_rows<<<dim3(g.Dh, n_frames), 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, p.speckle_sim_threshold,
-                                                      D1, D2, O1, O2, parent, size, O2_i16, D_stride);
+    k_lr_rows<<<dim3(g.Dh, n_frames), 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, D1, D2, O1, O2, O2_i16, D_stride);
     count_launch();
 }
 
-void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* parent,
-                     int32_t* size, size_t D_stride, int n_frames, cudaStream_t s, bool apply, bool rows_done)
+size_t segment_node_ints(const FrameGeom& g)
 {
-    const int n = g.Dw * g.Dh;
-    const int speckle = speckle_size_of(p);
-    const float thr = p.speckle_sim_threshold;
-    if (!rows_done) { k_seg_rows<<<dim3(g.Dh, n_frames), 256, 0, s>>>(g.Dw, thr, D, parent, size, D_stride); count_launch(); }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    static int sms_of[64] = {0};
-    if (!sms_of[dev & 63]) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); sms_of[dev & 63] = sms; }
-    static const int per_sm = [] { const char* e = std::getenv("ELAS_B200_SEG_CTAS_PER_SM"); return e ? std::atoi(e) : kSegCtasPerSm; }();
-    const int seg_grid = std::min(std::max(1, sms_of[dev & 63] * per_sm / std::max(1, std::min(n_frames, 4))), (n + 255) / 256);
-    ELASB_PREPARE_KERNEL(k_seg_merge);
-    ELASB_PREPARE_KERNEL(k_seg_count);
-    k_seg_merge<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, D, parent, D_stride);
-    k_seg_count<<<dim3(seg_grid, n_frames), 256, 0, s>>>(g.Dw, g.Dh, thr, speckle, D, parent, size, D_stride);
-    if (!apply) { count_launch(2); return; }
-    k_seg_apply<<<dim3((n + 255) / 256, n_frames), 256, 0, s>>>(n, speckle, D, parent, size, D_stride);
+    const size_t tiles = (size_t)((g.Dw + kSegTW - 1) / kSegTW) * ((g.Dh + kSegTH - 1) / kSegTH);
+    return 3 * tiles * kSegTile;
+}
+
+// K9: labels + open nodes of D's components (frames D_stride / nodes_stride apart); apply = true also invalidates
+// the small segments in place (settings outside the fused tail), otherwise launch_post_fused applies them
+void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* label, int32_t* nodes,
+                     size_t D_stride, size_t nodes_stride, int n_frames, cudaStream_t s, bool apply)
+{
+    SegArgs a;
+    a.Dw = g.Dw; a.Dh = g.Dh;
+    a.tiles_x = (g.Dw + kSegTW - 1) / kSegTW; a.tiles_y = (g.Dh + kSegTH - 1) / kSegTH;
+    a.speckle = speckle_size_of(p);
+    a.thr = p.speckle_sim_threshold;
+    a.D = D; a.label = label; a.nodes = nodes; a.D_stride = D_stride; a.nodes_stride = nodes_stride;
+    a.node_cap = a.tiles_x * a.tiles_y * kSegTile;
+    ELASB_PREPARE_KERNEL(k_seg_tiles);
+    ELASB_PREPARE_KERNEL(k_seg_border);
+    ELASB_PREPARE_KERNEL(k_seg_sizes);
+    k_seg_tiles<<<dim3(a.tiles_x, a.tiles_y, n_frames), kSegThreads, 0, s>>>(a);
+    const int pairs = (a.tiles_x - 1) * g.Dh + (a.tiles_y - 1) * g.Dw;
+    k_seg_border<<<dim3(std::max(1, (pairs + 255) / 256), n_frames), 256, 0, s>>>(a);
+    k_seg_sizes<<<dim3((g.Dw * g.Dh + 1023) / 1024, n_frames), 256, 0, s>>>(a);
     count_launch(3);
+    if (!apply) return;
+    const int n = g.Dw * g.Dh;
+    k_seg_apply<<<dim3((n + 255) / 256, n_frames), 256, 0, s>>>(n, a.speckle, D, label, nodes, a.node_cap, D_stride, nodes_stride);
+    count_launch();
 }
 
 bool post_fusable(const elas_b200_params& p)
@@ -623,17 +702,19 @@ bool post_fusable(const elas_b200_params& p)
     return gap <= kFuseGap && gap >= 0 && !p.add_corners;
 }
 
-// speckle apply (when parent != nullptr) + gap interpolation + adaptive mean (when filter_adaptive_mean)
-void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* parent,
-                       const int32_t* size, const OutTable& out, float* dump_seg, float* dump_gap, size_t D_stride,
-                       int n_frames, cudaStream_t s)
+// speckle apply (when label != nullptr) + gap interpolation + adaptive mean (when filter_adaptive_mean)
+void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* label,
+                       const int32_t* nodes, size_t nodes_stride, const OutTable& out, float* dump_seg, float* dump_gap,
+                       size_t D_stride, int n_frames, cudaStream_t s)
 {
     FuseArgs a;
     a.Dw = g.Dw; a.Dh = g.Dh;
     a.gap = p.subsampling ? p.ipol_gap_width / 2 + 1 : p.ipol_gap_width;               // :1335-1341
     a.speckle = speckle_size_of(p);
-    a.apply = parent != nullptr;
-    a.in = in; a.parent = parent; a.size = size; a.out = out; a.dump_seg = dump_seg; a.dump_gap = dump_gap;
+    a.apply = label != nullptr;
+    a.in = in; a.label = label; a.nodes = nodes; a.nodes_stride = nodes_stride;
+    a.node_cap = ((g.Dw + kSegTW - 1) / kSegTW) * ((g.Dh + kSegTH - 1) / kSegTH) * kSegTile;
+    a.out = out; a.dump_seg = dump_seg; a.dump_gap = dump_gap;
     a.D_stride = D_stride;
     const dim3 grid((g.Dw + kFuseTW - 1) / kFuseTW, (g.Dh + kFuseTH - 1) / kFuseTH, n_frames);
     ELASB_PREPARE_KERNEL((k_post_fused<8, false>));

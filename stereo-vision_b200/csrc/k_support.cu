@@ -23,6 +23,8 @@ namespace {
 // kept as key = (energy << 16 | d): a lane visits its disparities in ascending order, so among equal
 // energies the smaller key is the earlier d, which is what the strict '<' keeps.  Energies stay below
 // 4 * 16 * 255 < 2^15 and d below 2^12 (checked at context creation).
+constexpr int kStripPad = 12;         // addressable entries before and after every staged strip (see match_point)
+
 struct Best { unsigned key; int e2; };
 constexpr unsigned kNoKey = (32767u << 16) | 0xFFFFu;     // nothing evaluated: e1 = 32767 (elas.cpp:378-381)
 
@@ -91,16 +93,16 @@ __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_p
     const int sgn = right_image ? 1 : -1;                 // warped column = u + sgn * d
     const int lane_off = 12 * (lane >> 2) + (lane & 3);
     Best b = {kNoKey, 32767};                                                        // :378-381
-    for (int d0 = dmin + lane_off; d0 - lane_off <= dmax; d0 += 96) {                // :396-429
-        // the four columns X_j = (u + sgn*d0) + sgn*(4j - 2), j = 0..3, as strip indices; disparities past
-        // dmax are computed but not counted, their columns are clamped into the staged range
+    for (int d0 = dmin + lane_off; d0 <= dmax; d0 += 96) {                           // :396-429
+        // the four columns X_j = (u + sgn*d0) + sgn*(4j - 2), j = 0..3, as strip indices; the disparities d0+4 and
+        // d0+8 may lie past dmax: they are computed but not counted, their columns (at most 10 beyond the staged
+        // range) fall into the kStripPad entries of addressable padding around every strip
         const int c0 = u + sgn * d0 - st.org - 2 * sgn;
         uint4 A[4], B[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int x = min(max(c0 + 4 * sgn * j, 0), st.len - 1);
-            A[j] = othA[x];
-            B[j] = othB[x];
+            A[j] = othA[c0 + 4 * sgn * j];
+            B[j] = othB[c0 + 4 * sgn * j];
         }
 #pragma unroll
         for (int m = 0; m < 3; m++) {
@@ -125,6 +127,7 @@ __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_p
 }
 
 constexpr int kPointsPerCta = 32;     // lattice points of one row handled by a CTA (8 warps x 4 points)
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,8 +155,8 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1_g,
     // reverse match (from u-d) needs desc1 up to x1+2+disp_max
     const int x0 = uc0 * g.step, x1 = (uc0 + npts - 1) * g.step;
     const int lo = max(x0 - 2 - p.disp_max, 0), hi = min(x1 + 2 + p.disp_max + 1, g.W);
-    const int len = hi - lo, cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max;
-    uint4* s = reinterpret_cast<uint4*>(smem_raw);
+    const int len = hi - lo, cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max + 2 * kStripPad;
+    uint4* s = reinterpret_cast<uint4*>(smem_raw) + kStripPad;
     Strips st;
     st.rowA[0] = s; st.rowA[1] = s + cap; st.rowB[0] = s + 2 * cap; st.rowB[1] = s + 3 * cap;
     st.org = lo; st.len = len;
@@ -161,7 +164,7 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1_g,
     // CTA's lattice points in desc1, the reverse matches from (u-d, v) in desc2
     const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
     const int c1lo = max(x0 - p.disp_max, 0);
-    uint4* cen0 = s + 4 * cap;
+    uint4* cen0 = s + 4 * cap - kStripPad;
     uint4* cen1 = cen0 + cen_cap;
     st.cen[0] = cen0; st.cen[1] = cen1; st.cen_org[0] = x0; st.cen_org[1] = c1lo;
     __shared__ int s_next;
@@ -221,7 +224,7 @@ k_support(FrameGeom g, elas_b200_params p, const uint4* __restrict__ desc1_g,
 
 size_t support_smem_bytes(const FrameGeom& g, const elas_b200_params& p)
 {
-    const int cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max;
+    const int cap = (kPointsPerCta - 1) * g.step + 5 + 2 * p.disp_max + 2 * kStripPad;
     const int cen_cap = (kPointsPerCta - 1) * g.step + 1;
     return ((size_t)4 * cap + 2 * cen_cap + p.disp_max) * 16;
 }

@@ -36,9 +36,8 @@ namespace elasb {
 namespace mesh {
 
 constexpr int kPadC = 8, kPadR = 8;        // lattice padding: >= incon_window_size and >= the redundancy reach (5)
-// bits of a valid lattice value (disparities stay below 4096): the inconsistency filter's working state
+// bits of a valid lattice value (disparities stay below 4096) while the inconsistency filter runs
 constexpr int kValueMask = 0x0FFF;
-constexpr int kDirty0 = 0x1000, kDirty1 = 0x2000;   // to be (re-)evaluated in an even / odd round
 constexpr int kRemoved = 0x4000;           // invalidated by the inconsistency filter
 constexpr int kRedunDist = 5, kRedunThr = 1;   // elas.cpp:501-502
 
@@ -51,77 +50,80 @@ MESH_FN int lat_index(const Lattice& L, int uc, int vc) { return (vc + kPadR) * 
 MESH_FN int lat_elems(int Wc, int Hc) { return (Wc + 2 * kPadC) * (Hc + 2 * kPadR); }
 MESH_FN int iabs(int x) { return x < 0 ? -x : x; }
 
-// ---- phase L0: padded copy of the candidate lattice (K2's output, [Hc][Wc]); valid cells start out "dirty" ---
+// ---- phase L0: padded copy of the candidate lattice (K2's output, [Hc][Wc]) ----------------------------
 MESH_FN void lattice_load(const Lattice& L, const int16_t* dcan, int tid, int nthr)
 {
     const int rows = L.Hc + 2 * kPadR, total = rows * L.pitch;
     for (int i = tid; i < total; i += nthr) {
         const int r = i / L.pitch, c = i - r * L.pitch;
         const int vc = r - kPadR, uc = c - kPadC;
-        int x = -1;
-        if (vc >= 0 && vc < L.Hc && uc >= 0 && uc < L.Wc) { x = dcan[vc * L.Wc + uc]; if (x >= 0) x |= kDirty0; }
-        L.P[i] = (int16_t)x;
+        L.P[i] = (vc >= 0 && vc < L.Hc && uc >= 0 && uc < L.Wc) ? dcan[vc * L.Wc + uc] : (int16_t)-1;
     }
 }
 
-// removeInconsistentSupportPoints, elas.cpp:174-209: does cell (uc,vc) with value x keep fewer than `need`
-// supporters?  A window cell that precedes it in scan order (u outer, v inner) counts with its CURRENT state.
-MESH_FN bool incon_fails(const Lattice& L, const int16_t* c, int x, int win, int thr, int need)
+// removeInconsistentSupportPoints (elas.cpp:174-209) invalidates a cell when fewer than incon_min_support cells
+// of its window are valid, similar (|d - d'| <= incon_threshold) and -- if they precede it in scan order (u outer,
+// v inner) -- not invalidated themselves.  With count0 = the supporters in the UNFILTERED lattice (the cell
+// itself included) that reads: invalid(c) <=> count0(c) - #{invalidated earlier similar cells of the window} < need.
+// Solved by propagation: cells with count0 < need seed a work list; every listed cell is invalidated and takes one
+// supporter away from each LATER similar valid cell of its window; a cell whose count thereby drops below need
+// joins the next list.  Counts only fall, a cell crosses the threshold once, the result is the unique solution of
+// the recursive definition -- whatever the processing order.
+
+// ---- phase C (its own kernel on the device, any number of CTAs): count0 of one cell of the unfiltered lattice --
+MESH_FN int incon_count0(const int16_t* dcan, int Wc, int Hc, int uc, int vc, int win, int thr)
 {
+    const int x = dcan[vc * Wc + uc];
+    if (x < 0) return 0;
     int support = 0;
-    for (int dv = -win; dv <= win; dv++) {
-        const int16_t* row = c + dv * L.pitch;
-        for (int du = -win; du <= win; du++) {
-            const int y = row[du];
-            if (y < 0) continue;
-            if ((y & kRemoved) && (du < 0 || (du == 0 && dv < 0))) continue;
-            support += iabs((x & kValueMask) - (y & kValueMask)) <= thr;
+    for (int v2 = (vc - win > 0 ? vc - win : 0); v2 <= vc + win && v2 < Hc; v2++)
+        for (int u2 = (uc - win > 0 ? uc - win : 0); u2 <= uc + win && u2 < Wc; u2++) {
+            const int y = dcan[v2 * Wc + u2];
+            support += y >= 0 && iabs(x - y) <= thr;
         }
-    }
-    return support < need;
-}
-// the cells whose verdict may change when (uc,vc) is invalidated: valid, similar, LATER in scan order
-MESH_FN bool incon_depends(int x, int y, int du, int dv, int thr)
-{
-    return y >= 0 && !(y & kRemoved) && (du > 0 || (du == 0 && dv > 0)) && iabs((x & kValueMask) - (y & kValueMask)) <= thr;
+    return support;
 }
 
-// ---- phase L1 (round r = 0, 1, ...; repeated until no thread reports a change) ----------------------------
-// Evaluates the cells marked for this round; a cell that is invalidated marks its dependents for the next round.
-// or16 / and16: atomic bit operations on a lattice element (plain operations in the CPU emulation).
-template <class Or16, class And16>
-MESH_FN bool incon_round(const Lattice& L, int win, int thr, int need, int round, int tid, int nthr, Or16 or16, And16 and16)
+// ---- phase L1a: the cells that fail on their own seed the first work list (entries = padded lattice indices) ---
+template <class AtomicAdd>
+MESH_FN void incon_seed(const Lattice& L, const int32_t* cnt, int need, int32_t* list, int* list_n, int tid, int nthr, AtomicAdd atomic_add)
 {
-    bool changed = false;
-    const int now = (round & 1) ? kDirty1 : kDirty0, next = (round & 1) ? kDirty0 : kDirty1;
     const int cells = L.Wc * L.Hc;
     for (int i = tid; i < cells; i += nthr) {
         const int vc = i / L.Wc, uc = i - vc * L.Wc;
-        int16_t* c = L.P + lat_index(L, uc, vc);
-        const int x = *c;
-        if (x < 0 || (x & kRemoved) || !(x & now)) continue;
-        and16(c, ~now);
-        if (!incon_fails(L, c, x, win, thr, need)) continue;
+        const int at = lat_index(L, uc, vc);
+        if (L.P[at] >= 0 && cnt[i] < need) list[atomic_add(list_n, 1)] = at;
+    }
+}
+// ---- phase L1b (repeated until the next list stays empty): invalidate the listed cells, propagate --------------
+// atomic_add(int*, int) returns the previous value; or16(int16_t*, bits) sets bits atomically.
+template <class AtomicAdd, class Or16>
+MESH_FN void incon_propagate(const Lattice& L, int32_t* cnt, int win, int thr, int need, const int32_t* cur, int n_cur,
+                             int32_t* next, int* n_next, int tid, int nthr, AtomicAdd atomic_add, Or16 or16)
+{
+    for (int k = tid; k < n_cur; k += nthr) {
+        const int at = cur[k];
+        int16_t* c = L.P + at;
+        const int x = *c & kValueMask;
         or16(c, kRemoved);
-        changed = true;
+        const int vc = at / L.pitch - kPadR, uc = at - (vc + kPadR) * L.pitch - kPadC;
         for (int dv = -win; dv <= win; dv++)
-            for (int du = (dv > 0 ? 0 : 1); du <= win; du++) {          // later in scan order only
-                int16_t* d = c + dv * L.pitch + du;
-                if (incon_depends(x, *d, du, dv, thr)) or16(d, next);
+            for (int du = (dv > 0 ? 0 : 1); du <= win; du++) {              // later in scan order only
+                const int y = c[dv * L.pitch + du];
+                if (y < 0 || iabs(x - (y & kValueMask)) > thr) continue;      // padding, invalid or not similar
+                if (atomic_add(cnt + (vc + dv) * L.Wc + (uc + du), -1) == need) next[atomic_add(n_next, 1)] = at + dv * L.pitch + du;
             }
     }
-    return changed;
 }
 
-// ---- phase L2: invalidated cells become -1, the others plain disparities; optional dump after this filter --
+// ---- phase L2: invalidated cells become -1; optional dump of the lattice after this filter -----------------
 MESH_FN void incon_finish(const Lattice& L, int16_t* dump, int tid, int nthr)
 {
     const int cells = L.Wc * L.Hc;
     for (int i = tid; i < cells; i += nthr) {
         const int vc = i / L.Wc, uc = i - vc * L.Wc;
         int16_t* c = L.P + lat_index(L, uc, vc);
-        const int x = *c;
-        if (x >= 0) *c = (int16_t)((x & kRemoved) ? -1 : (x & kValueMask));
+        if (*c >= 0 && (*c & kRemoved)) *c = -1;
         if (dump) dump[i] = *c;
     }
 }

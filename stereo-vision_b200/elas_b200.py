@@ -54,7 +54,8 @@ _lib = None
 EXPORTS = [
     "elas_b200_default_params", "elas_b200_stereomapper_params", "elas_b200_process",
     "elas_b200_create", "elas_b200_create_ex", "elas_b200_create_grouped", "elas_b200_frames_per_group",
-    "elas_b200_mesh_on_device", "elas_b200_time_matching_ex", "elas_b200_destroy", "elas_b200_process_ctx", "elas_b200_process_batch",
+    "elas_b200_mesh_on_device", "elas_b200_time_matching_ex", "elas_b200_destroy", "elas_b200_multi_create",
+    "elas_b200_multi_destroy", "elas_b200_multi_device_count", "elas_b200_multi_context", "elas_b200_multi_process_batch", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
@@ -89,6 +90,14 @@ def load_library():
     lib.elas_b200_time_matching_ex.restype = C.c_float
     lib.elas_b200_destroy.argtypes = [C.c_void_p]
     lib.elas_b200_destroy.restype = None
+    lib.elas_b200_multi_create.argtypes = [C.POINTER(C.c_void_p), i32p, C.c_int32, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.elas_b200_multi_destroy.argtypes = [C.c_void_p]
+    lib.elas_b200_multi_destroy.restype = None
+    lib.elas_b200_multi_device_count.argtypes = [C.c_void_p]
+    lib.elas_b200_multi_context.argtypes = [C.c_void_p, C.c_int32]
+    lib.elas_b200_multi_context.restype = C.c_void_p
+    lib.elas_b200_multi_process_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, i32p]
     lib.elas_b200_process_ctx.argtypes = [C.c_void_p, C.c_int32, u8p, u8p, f32p, f32p, C.c_int32]
     for fn in (lib.elas_b200_process_batch, lib.elas_b200_process_batch_device):
         fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -327,3 +336,36 @@ class ElasB200:
         if ms < 0:
             raise RuntimeError("elas_b200_time_matching failed (run a frame through the slot first)")
         return ms / frames.value if per_frame else (ms, frames.value)
+
+
+class ElasB200Multi:
+    """elas_b200_multi_*: one context per device in ONE process, frame i of a batch -> device i mod n."""
+
+    def __init__(self, params, width, height, devices, n_groups=2, frames_per_group=0, n_workers=0):
+        self.lib = load_library()
+        self.shape = (height // 2, width // 2) if params.subsampling else (height, width)
+        self.handle = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*devices)
+        rc = self.lib.elas_b200_multi_create(C.byref(self.handle), devs, len(devices), C.byref(params), width, height,
+                                             n_groups, frames_per_group, n_workers)
+        if rc != 0:
+            raise RuntimeError(f"elas_b200_multi_create failed with {rc}")
+
+    def close(self):
+        if self.handle:
+            self.lib.elas_b200_multi_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def process_batch(self, lefts, rights):
+        lefts = [np.ascontiguousarray(a, np.uint8) for a in lefts]
+        rights = [np.ascontiguousarray(a, np.uint8) for a in rights]
+        n = len(lefts)
+        D1 = [np.full(self.shape, -77.0, np.float32) for _ in lefts]
+        D2 = [np.full(self.shape, -77.0, np.float32) for _ in lefts]
+        arr = lambda xs: (C.c_void_p * n)(*[a.ctypes.data for a in xs])
+        status = (C.c_int32 * n)()
+        rc = self.lib.elas_b200_multi_process_batch(self.handle, n, arr(lefts), arr(rights), arr(D1), arr(D2),
+                                                    lefts[0].strides[0], status)
+        if rc < 0:
+            raise RuntimeError(f"elas_b200_multi_process_batch failed with {rc}")
+        return list(status), D1, D2

@@ -36,12 +36,16 @@ int mesh_emulate_lattice(int Wc, int Hc, int step, int win, int thr, int need, i
     emu.phase([&](int t, int n) { lattice_load(L, dcan, t, n); });
     int rounds = 0;
     auto or16 = [](int16_t* p, int bits) { *p = (int16_t)(*p | bits); };
-    auto and16 = [](int16_t* p, int bits) { *p = (int16_t)(*p & bits); };
-    for (;;) {
-        bool changed = false;
-        emu.phase([&](int t, int n) { changed |= incon_round(L, win, thr, need, rounds, t, n, or16, and16); });
+    auto atomic_add = [](int* p, int v) { const int old = *p; *p += v; return old; };
+    std::vector<int32_t> sup_cnt((size_t)Wc * Hc), lists[2] = {std::vector<int32_t>((size_t)Wc * Hc), std::vector<int32_t>((size_t)Wc * Hc)};
+    emu.phase([&](int t, int n) { for (int i = t; i < Wc * Hc; i += n) sup_cnt[i] = incon_count0(dcan, Wc, Hc, i % Wc, i / Wc, win, thr); });
+    int n_cur = 0;
+    emu.phase([&](int t, int n) { incon_seed(L, sup_cnt.data(), need, lists[0].data(), &n_cur, t, n, atomic_add); });
+    for (int cur = 0; n_cur > 0; cur ^= 1) {
+        int n_next = 0;
+        emu.phase([&](int t, int n) { incon_propagate(L, sup_cnt.data(), win, thr, need, lists[cur].data(), n_cur, lists[cur ^ 1].data(), &n_next, t, n, atomic_add, or16); });
+        n_cur = n_next;
         rounds++;
-        if (!changed) break;
     }
     if (rounds_out) *rounds_out = rounds;
     emu.phase([&](int t, int n) { incon_finish(L, dcan_incon, t, n); });

@@ -375,3 +375,22 @@ def test_host_stage_path_equals_device_mesh_stage(oracle, monkeypatch):
         assert not e.mesh_on_device
     finally:
         e.close()
+
+
+def test_multi_device_entry_shards_frames(oracle):
+    """elas_b200_multi_*: one process, one context per device (here the same device twice when the box has one GPU),
+    frame i -> context i mod n; results equal the per-frame oracle results, in order."""
+    n_dev = elas_b200.load_library().elas_b200_device_count()
+    devices = [0, 1] if n_dev >= 2 else [0, 0]
+    p = checkers.stereomapper(95)
+    pairs = [synth.synthetic_pair(416, 200, 95, s)[:2] for s in (61, 62, 63)]
+    frames = [pairs[i % 3] for i in range(11)]
+    m = elas_b200.ElasB200Multi(as_product_params(p), 416, 200, devices, n_groups=2, frames_per_group=2, n_workers=1)
+    try:
+        status, D1, D2 = m.process_batch([a for a, _ in frames], [b for _, b in frames])
+    finally:
+        m.close()
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    assert status == [0] * 11
+    for i in range(11):
+        assert bits_equal(D1[i], want[i % 3][1]) and bits_equal(D2[i], want[i % 3][2]), f"frame {i}"
