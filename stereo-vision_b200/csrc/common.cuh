@@ -43,7 +43,7 @@ struct FrameGeom {
 struct __align__(16) TriRaster {
     float ACa, ACb, ABa, ABb;                 // 16 B: edge lines A-C and A-B
     float BCa, BCb; int uA, uB;               // 16 B: edge line B-C, (int32_t)A_u, (int32_t)B_u after the sort by u
-    float pa, pb, pc; int valid;              // 16 B: plane of this image; valid = |plane_a| < 0.7 && |plane_d| < 0.7 (elas.cpp:1072)
+    float pa, pb, pc; int valid;              // 16 B: plane of this image; valid = 2 if |plane_a| < 0.7 && |plane_d| < 0.7 (elas.cpp:1072), else 0
     int   uC, pad0, pad1, pad2;               // 16 B: (int32_t)C_u
 };
 static_assert(sizeof(TriRaster) == 64, "TriRaster is one 64-byte record");
@@ -140,6 +140,7 @@ struct MatchBuffers {
     const uint32_t* grid[2];
     const uint16_t* lists[2];
     const int32_t* prior;
+    const int32_t* prior_host;           // the same table in host memory (its first entries travel as kernel arguments)
     float* D[2];
     size_t desc_stride, tri_stride, map_stride, grid_stride, lists_stride, D_stride;
     int rows_per_cta;                    // set by launch_matching

@@ -132,6 +132,7 @@ struct elas_b200_ctx {
     int map_tag_shift = 0, map_tag_max = 0;  // map entry = tag << shift | triangle index
     bool mesh_device = true;                 // lattice filters + Delaunay on the GPU (k_mesh.cu); false: host stage (host_stage.cc)
     int32_t* d_prior = nullptr;
+    std::vector<int32_t> prior_host;
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
     bool timing = false;
@@ -372,6 +373,7 @@ MatchBuffers match_buffers(const elas_b200_ctx* c, const Group& s)
         b.lists[k] = s.d_lists[k]; b.D[k] = s.d_raw[k];
     }
     b.prior = c->d_prior;
+    b.prior_host = c->prior_host.data();
     b.desc_stride = c->st.desc; b.tri_stride = c->st.traster; b.map_stride = c->st.map; b.grid_stride = c->st.grid;
     b.lists_stride = c->st.lists; b.D_stride = c->st.D;
     return b;
@@ -874,6 +876,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
         if (prior[k] > 0 || prior[k] < -5000) return ELAS_B200_E_UNSUPPORTED;
     CK(cudaMalloc(&c->d_prior, prior.size() * 4));
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
+    c->prior_host = prior;
     c->launches_at_create = launches_issued();
     if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
     {

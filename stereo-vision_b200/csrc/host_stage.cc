@@ -665,7 +665,7 @@ void raster_records(const std::vector<int32_t>& sup, const std::vector<int32_t>&
         r.ACb = Av - ACa * Au;
         r.BCb = Bv - BCa * Bu;
         r.uA = (int32_t)Au; r.uB = (int32_t)Bu; r.uC = (int32_t)Cu;
-        r.valid = std::fabs(r.pa) < 0.7 && std::fabs(pd) < 0.7;   // :1072 (float |.| compared in double)
+        r.valid = (std::fabs(r.pa) < 0.7 && std::fabs(pd) < 0.7) ? 2 : 0;   // :1072 (float |.| compared in double); bit 1 of K7's packed pixel state
         out[i] = r;
     }
 }

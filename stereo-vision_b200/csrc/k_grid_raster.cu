@@ -179,7 +179,7 @@ __device__ __forceinline__ void planes_body(int gid, const int32_t* __restrict__
     r.ACb = __fsub_rn(Av, __fmul_rn(ACa, Au));
     r.BCb = __fsub_rn(Bv, __fmul_rn(BCa, Bu));
     r.uA = (int)Au; r.uB = (int)Bu; r.uC = (int)Cu;
-    r.valid = (double)fabsf(r.pa) < 0.7 && (double)fabsf(pd) < 0.7;     // :1072
+    r.valid = ((double)fabsf(r.pa) < 0.7 && (double)fabsf(pd) < 0.7) ? 2 : 0;     // :1072; bit 1 of K7's packed pixel state
     r.pad0 = min(sv[0], min(sv[1], sv[2]));     // smallest corner row: anchor of k_raster's row bands
     r.pad1 = max(sv[0], max(sv[1], sv[2]));     // largest corner row (overflow triangles walk all their bands)
     r.pad2 = 0;

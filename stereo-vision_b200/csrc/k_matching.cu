@@ -80,6 +80,7 @@ struct MatchArgs {
     int disp_max, match_texture, grid_size, max_cells, map_pitch;
     int map_tag_bits, map_tag_mask;      // triangle-id map entries are tag_bits | index; other tags = stale = uncovered
     uint32_t grid_magic;                 // floor(u / grid_size) == (u * grid_magic) >> 32 for u, grid_size < 65536
+    int prior4[4];                       // prior of the plane window offsets 0..3 (elas.cpp:984-992)
     MatchBuffers b;
 };
 
@@ -162,8 +163,8 @@ __device__ __forceinline__ int pack_plane(const float4& pl, bool covered, float 
 {
     const float dp = __fadd_rn(__fadd_rn(__fmul_rn(pl.x, fu), __fmul_rn(pl.y, fv)), pl.z);
     const int d_plane = min(max(__float2int_rz(dp), -kPlaneBias), 2 * kPlaneBias);     // cvt.rzi saturates, NaN -> 0
-    const int valid = __float_as_int(pl.w) != 0;
-    return covered ? (((d_plane + kPlaneBias) << 2) | (valid << 1) | 1) : 0;
+    // TriRaster::valid holds 2 or 0: it is bit 1 of the packed state
+    return covered ? (((d_plane + kPlaneBias) << 2) | __float_as_int(pl.w) | 1) : 0;
 }
 
 // plane window of one pixel (elas.cpp:904-913, :934-943): taps d_plane-R..d_plane+R at consecutive shared
@@ -328,7 +329,7 @@ __device__ __forceinline__ void match_pair(const MatchArgs& a, const SegCtx& r, 
 // ROWS = image rows per CTA: 2 = a thread matches (u, v0) and (u, v0+1) together (needs an even grid_size:
 // both lie in one grid cell); 1 = one row per CTA (odd grid sizes; subsampling, where only even rows exist)
 template <int RADIUS, int ROWS, bool SUB>     // plane_radius (elas.cpp:993); 0 = generic
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 5)
 k_matching(const __grid_constant__ MatchArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -353,6 +354,23 @@ k_matching(const __grid_constant__ MatchArgs a)
     const int c0 = (int)__umulhi((uint32_t)x0, a.grid_magic);
     const int ncell = (int)__umulhi((uint32_t)(x1 - 1), a.grid_magic) - c0 + 1;
 
+    // while the copies fly: this thread's four triangle-id entries -> planes -> packed (d_plane, valid, covered)
+    const int u = x0 + threadIdx.x;
+    // columns that are matched at all: inside the segment, inside [2, W-2) (elas.cpp:828), even when subsampling (:1079)
+    const bool col = u < x1 && u >= 2 && u < g.W - 2 && !(SUB && ((u & 1) || (u >> 1) >= g.Dw));
+    int pk[2][2] = {{0, 0}, {0, 0}};
+    int e[2][2];
+    // the triangle-id entries first: their latency (DRAM) overlaps the barrier set-up and the TMA issue
+    {
+        // 32-bit element indices from the group's base pointers (a group's arrays stay far below 2^31 elements)
+        const uint32_t mrow = (uint32_t)z * (uint32_t)b.map_stride + (uint32_t)v0 * (uint32_t)a.map_pitch + (uint32_t)u;
+#pragma unroll
+        for (int row = 0; row < ROWS; row++) {
+            const bool on = col && (row == 0 || rowB);
+            e[0][row] = on ? __ldg(b.map[0] + (mrow + row * a.map_pitch)) : -1;
+            e[1][row] = on ? __ldg(b.map[1] + (mrow + row * a.map_pitch)) : -1;
+        }
+    }
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -377,23 +395,9 @@ k_matching(const __grid_constant__ MatchArgs a)
         tma_bulk_g2s(lists + (uint32_t)a.max_cells * kGridListStride * 2u, b.lists[1] + (size_t)z * b.lists_stride + cell0, bl, &bar);
     }
 
-    // while the copies fly: this thread's four triangle-id entries -> planes -> packed (d_plane, valid, covered)
-    const int u = x0 + threadIdx.x;
-    // columns that are matched at all: inside the segment, inside [2, W-2) (elas.cpp:828), even when subsampling (:1079)
-    const bool col = u < x1 && u >= 2 && u < g.W - 2 && !(SUB && ((u & 1) || (u >> 1) >= g.Dw));
-    int pk[2][2] = {{0, 0}, {0, 0}};
     {
-        // 32-bit element indices from the group's base pointers (a group's arrays stay far below 2^31 elements)
-        const uint32_t mrow = (uint32_t)z * (uint32_t)b.map_stride + (uint32_t)v0 * (uint32_t)a.map_pitch + (uint32_t)u;
         const uint32_t tbase = (uint32_t)z * (uint32_t)b.tri_stride;
-        int e[2][2];
         float4 pl[2][2];
-#pragma unroll
-        for (int row = 0; row < ROWS; row++) {
-            const bool on = col && (row == 0 || rowB);
-            e[0][row] = on ? __ldg(b.map[0] + (mrow + row * a.map_pitch)) : -1;
-            e[1][row] = on ? __ldg(b.map[1] + (mrow + row * a.map_pitch)) : -1;
-        }
 #pragma unroll
         for (int img = 0; img < 2; img++)
 #pragma unroll
@@ -411,9 +415,7 @@ k_matching(const __grid_constant__ MatchArgs a)
             for (int row = 0; row < ROWS; row++)
                 pk[img][row] = pack_plane(pl[img][row], e[img][row] >= 0, fu, (float)(v0 + row));
     }
-    // prior of the plane window offsets 0..3 (elas.cpp:984-992), in registers
-    const int p0 = __ldg(b.prior), p1 = g.dn > 1 ? __ldg(b.prior + 1) : 0, p2 = g.dn > 2 ? __ldg(b.prior + 2) : 0,
-              p3 = g.dn > 3 ? __ldg(b.prior + 3) : 0;
+    const int p0 = a.prior4[0], p1 = a.prior4[1], p2 = a.prior4[2], p3 = a.prior4[3];
     // warp-uniform: every column of this warp keeps every disparity's warped column inside [2, W-2)
     const int uw0 = x0 + (threadIdx.x & ~31), uw1 = uw0 + 31;
     const bool safe0 = uw0 - 2 >= a.disp_max, safe1 = g.W - 3 - uw1 >= a.disp_max;
@@ -428,12 +430,11 @@ k_matching(const __grid_constant__ MatchArgs a)
     match_pair<0, RADIUS, ROWS>(a, r, u, pk[0][0], pk[0][1], safe0, p0, p1, p2, p3, o[0][0], o[0][1]);
     match_pair<1, RADIUS, ROWS>(a, r, u, pk[1][0], pk[1][1], safe1, p0, p1, p2, p3, o[1][0], o[1][1]);
     if (u >= x1 || (SUB && ((u & 1) || (u >> 1) >= g.Dw))) return;
-    const uint32_t at = SUB ? (uint32_t)(v0 >> 1) * g.Dw + (u >> 1) : (uint32_t)v0 * g.W + u;
+    const uint32_t at = (uint32_t)z * (uint32_t)b.D_stride + (SUB ? (uint32_t)(v0 >> 1) * g.Dw + (u >> 1) : (uint32_t)v0 * g.W + u);
 #pragma unroll
     for (int img = 0; img < 2; img++) {
-        float* __restrict__ D = b.D[img] + (size_t)z * b.D_stride + at;
-        D[0] = o[img][0];
-        if (ROWS == 2 && rowB) D[g.W] = o[img][1];
+        b.D[img][at] = o[img][0];
+        if (ROWS == 2 && rowB) b.D[img][at + g.W] = o[img][1];
     }
 }
 
@@ -481,6 +482,7 @@ void launch_matching(const FrameGeom& g, const elas_b200_params& p, const MatchB
     a.map_tag_mask = (1 << map_tag_shift) - 1;
     a.grid_magic = (uint32_t)(0x100000000ull / (uint32_t)p.grid_size) + 1u;
     a.b = b;
+    for (int k = 0; k < 4; k++) a.prior4[k] = b.prior_host && k < g.dn ? b.prior_host[k] : 0;
     const int rows = rows_per_cta(p);
     a.b.rows_per_cta = p.subsampling ? 2 : rows;
     const int items = p.subsampling ? (g.H + 1) / 2 : (g.H + rows - 1) / rows;
