@@ -347,8 +347,10 @@ k_matching(const __grid_constant__ MatchArgs a)
     // is addressable garbage that is never selected (loops that could reach it test the range)
     const int cap = kSegW + a.disp_max + 2 * kPad;
     const uint32_t row_stride = (uint32_t)cap * 16u;
-    const uint32_t strip0 = smem_u32(smem_raw), strip1 = strip0 + ROWS * row_stride;
-    const uint32_t lists = strip1 + ROWS * row_stride;                     // [2][max_cells][kGridListStride]
+    // the candidate lists come first: a thread without any candidate decodes list position 255 of its cell (value
+    // unused), which then falls into the strips instead of beyond the allocation
+    const uint32_t lists = smem_u32(smem_raw);                             // [2][max_cells][kGridListStride]
+    const uint32_t strip0 = lists + 2u * (uint32_t)a.max_cells * (kGridListStride * 2), strip1 = strip0 + ROWS * row_stride;
     const int org0 = x0 - kPad, org1 = x0 - a.disp_max - kPad;
     const int gy = (int)__umulhi((uint32_t)v0, a.grid_magic);              // v0 / grid_size, elas.cpp:867
     const int c0 = (int)__umulhi((uint32_t)x0, a.grid_magic);
@@ -443,8 +445,7 @@ int max_cells_per_segment(int grid_size) { return (kSegW + grid_size - 1) / grid
 size_t smem_bytes_for(const FrameGeom& g, int grid_size, int rows)
 {
     const int dmax = g.dn - 1;
-    // + 512: a thread without any candidate decodes list position 255 of its cell (value unused)
-    return 2 * (size_t)rows * (kSegW + dmax + 2 * kPad) * 16 + 2 * (size_t)max_cells_per_segment(grid_size) * kGridListStride * 2 + 512;
+    return 2 * (size_t)rows * (kSegW + dmax + 2 * kPad) * 16 + 2 * (size_t)max_cells_per_segment(grid_size) * kGridListStride * 2;
 }
 
 template <int RADIUS, int ROWS, bool SUB>
