@@ -895,7 +895,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
         st.lists = cells * kGridListStride;           // uint16
         st.map = (size_t)map_pitch(g) * g.H;          // int32
         st.D = (size_t)g.Dw * g.Dh;                   // float
-        st.mesh_scratch = 18 * (size_t)c->support_cap + 8;
+        st.mesh_scratch = 22 * (size_t)c->support_cap + 8;
         st.lat_work = 3 * (size_t)g.Wc * g.Hc;
         st.seg_nodes = segment_node_ints(g);
     }

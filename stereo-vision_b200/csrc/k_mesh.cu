@@ -96,6 +96,7 @@ struct LatticeArgs {
     int32_t* work;               // [frames][3][cells]: count0 (k_lattice_count), two work lists of the propagation
     FrameHeader* hdr;
     size_t dcan_stride, support_stride, work_stride;
+    int cnt_in_smem;
 };
 
 __global__ void __launch_bounds__(kMeshThreads)
@@ -114,6 +115,12 @@ k_lattice(const LatticeArgs a)
     const int cells = a.Wc * a.Hc;
     int32_t* cnt = a.work + (size_t)f * a.work_stride;
     int32_t* lists[2] = {cnt + cells, cnt + 2 * cells};
+    if (a.cnt_in_smem) {
+        // the supporter counts take thousands of dependent atomic decrements: in shared memory when they fit
+        int32_t* scnt = reinterpret_cast<int32_t*>(smem_raw + lat_bytes + (((size_t)a.Wc + 1) * 4 + 15 & ~(size_t)15));
+        for (int i = tid; i < cells; i += T) scnt[i] = cnt[i];
+        cnt = scnt;
+    }
 
     mesh::lattice_load(L, raw, tid, T);
     if (tid == 0) n_list[0] = n_list[1] = 0;
@@ -158,7 +165,7 @@ struct DelaunayArgs {
     size_t support_stride, tri_stride, units_stride, scratch_stride;
 };
 
-// mem = 18 n ints of working memory.  Inlined twice by the kernel, once with shared memory (the compiler then
+// mem = 22 n ints of working memory.  Inlined twice by the kernel, once with shared memory (the compiler then
 // addresses it with LDS/STS: the merges are chains of dependent loads, their latency is the kernel's run time)
 // and once with the global scratch area.
 __device__ __forceinline__ void delaunay_body(const DelaunayArgs& a, int32_t* mem, FrameHeader* hdr, int n, int img, int f,
@@ -166,8 +173,8 @@ __device__ __forceinline__ void delaunay_body(const DelaunayArgs& a, int32_t* me
 {
     const int tid = threadIdx.x, T = blockDim.x;
     int32_t* x = mem; int32_t* y = mem + n; int32_t* s = mem + 2 * n; int32_t* hull = mem + 3 * n;
-    int32_t* nbr = mem + 5 * n; int32_t* vtx = mem + 11 * n;
-    uint32_t* xy = reinterpret_cast<uint32_t*>(mem + 17 * n);
+    int32_t* nbr = mem + 5 * n; int32_t* vtx = mem + 13 * n;               // 4 ints per triangle, 2n triangles each
+    uint32_t* xy = reinterpret_cast<uint32_t*>(mem + 21 * n);
     const int32_t* support = a.support + (size_t)f * a.support_stride;
     for (int i = tid; i < n; i += T) {                                     // elas.cpp:543-559
         x[i] = img ? support[3 * i] - support[3 * i + 2] : support[3 * i];
@@ -175,7 +182,7 @@ __device__ __forceinline__ void delaunay_body(const DelaunayArgs& a, int32_t* me
         xy[i] = ((uint32_t)x[i] << 16) | (uint32_t)y[i];
     }
     // ---- the two sorted id lists: (x,y) and (y,x), keys are unique (no duplicate points on this path) -----
-    int32_t* R = nbr;                                                      // 12 n ints free until the triangulation starts
+    int32_t* R = nbr;                                                      // 16 n ints free until the triangulation starts
     mesh::Order o{n, s, R, R + n, R + 2 * n, R + 3 * n, R + 4 * n, R + 5 * n, R + 6 * n, R + 7 * n};
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(mem + ((5 * n + 8 * n + 1) & ~1));
     int npad = 1;
@@ -261,7 +268,7 @@ k_delaunay(const DelaunayArgs a)
         if (threadIdx.x == 0) { hdr->n_tri[img] = 0; hdr->n_units[img] = 0; hdr->ovf_from[img] = 0; }
         return;
     }
-    if (18 * n + 2 <= a.smem_ints) delaunay_body(a, reinterpret_cast<int32_t*>(smem_raw), hdr, n, img, f, warp_sums);
+    if (22 * n + 2 <= a.smem_ints) delaunay_body(a, reinterpret_cast<int32_t*>(smem_raw), hdr, n, img, f, warp_sums);
     else delaunay_body(a, a.scratch + ((size_t)f * 2 + img) * a.scratch_stride, hdr, n, img, f, warp_sums);
 }
 
@@ -290,9 +297,12 @@ void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t
     ELASB_PREPARE_KERNEL(k_lattice_count);
     k_lattice_count<<<dim3((g.Wc * g.Hc + 255) / 256, n_frames), 256, 0, s>>>(g.Wc, g.Hc, p.incon_window_size, p.incon_threshold,
                                                                              dcan_raw, work, st.dcan, st.lat_work);
+    // lattice + column table, plus the supporter counts if they fit as well
+    const size_t base = lattice_smem_bytes(g), with_counts = ((base + 15) & ~(size_t)15) + (size_t)g.Wc * g.Hc * 4;
+    const bool cnt_in_smem = with_counts <= 200 * 1024;
     LatticeArgs a{g.Wc, g.Hc, g.step, p.incon_window_size, p.incon_threshold, p.incon_min_support,
-                  dcan_raw, dcan, dcan_incon, support, work, hdr, st.dcan, st.support, st.lat_work};
-    k_lattice<<<n_frames, kMeshThreads, lattice_smem_bytes(g), s>>>(a);
+                  dcan_raw, dcan, dcan_incon, support, work, hdr, st.dcan, st.support, st.lat_work, cnt_in_smem ? 1 : 0};
+    k_lattice<<<n_frames, kMeshThreads, cnt_in_smem ? with_counts : base, s>>>(a);
     count_launch(2);
 }
 

@@ -185,34 +185,38 @@ MESH_FN void lattice_store(const Lattice& L, int16_t* dcan, int tid, int nthr)
 // =============================================================================================
 // Delaunay
 // =============================================================================================
-struct OTri { int t, o; };                  // oriented triangle: edge org->dest of triangle t, apex opposite
+// An oriented triangle (edge org->dest of triangle t, apex opposite) is ONE int e = 4 t + o, o in {0,1,2}: it is
+// at the same time the index of its neighbour link and of its apex in the per-triangle records of four ints
+// (slot 3 unused) -- the merges are chains of dependent loads executed by single threads, every instruction
+// of address arithmetic saved there is run time.
+typedef int OTri;
 
 struct Mesh {
     int n;                                  // vertices
     const uint32_t* xy;                     // coordinates by vertex id, x << 16 | y (both below 2^14)
     int32_t* s;                             // vertex ids in the alternating-cut order (triangle.cpp:6197-6206)
-    int32_t* nbr; int32_t* vtx;             // 3 links / 3 vertices per triangle, 2n-2 triangles; vertex -1 = ghost
+    int32_t* nbr; int32_t* vtx;             // 4 ints per triangle (3 links / 3 vertices), 2n-2 triangles; vertex -1 = ghost
     int32_t* hull;                          // [2n]: (farleft, farright) handles of the subtree that starts at s[lo]
 };
 
 MESH_FN int plus1(int o) { return (0x09 >> (2 * o)) & 3; }      // 0 -> 1, 1 -> 2, 2 -> 0
 MESH_FN int minus1(int o) { return (0x12 >> (2 * o)) & 3; }     // 0 -> 2, 1 -> 0, 2 -> 1
-MESH_FN OTri lnext(OTri a) { return {a.t, plus1(a.o)}; }
-MESH_FN OTri lprev(OTri a) { return {a.t, minus1(a.o)}; }
-MESH_FN int enc(OTri a) { return (a.t << 2) | a.o; }
-MESH_FN OTri dec(int e) { return {e >> 2, e & 3}; }
-MESH_FN OTri sym(const Mesh& m, OTri a) { return dec(m.nbr[3 * a.t + a.o]); }
-MESH_FN int org(const Mesh& m, OTri a) { return m.vtx[3 * a.t + plus1(a.o)]; }
-MESH_FN int dest(const Mesh& m, OTri a) { return m.vtx[3 * a.t + minus1(a.o)]; }
-MESH_FN int apex(const Mesh& m, OTri a) { return m.vtx[3 * a.t + a.o]; }
-MESH_FN void set_org(const Mesh& m, OTri a, int v) { m.vtx[3 * a.t + plus1(a.o)] = v; }
-MESH_FN void set_dest(const Mesh& m, OTri a, int v) { m.vtx[3 * a.t + minus1(a.o)] = v; }
-MESH_FN void set_apex(const Mesh& m, OTri a, int v) { m.vtx[3 * a.t + a.o] = v; }
-MESH_FN void bond(const Mesh& m, OTri a, OTri b) { m.nbr[3 * a.t + a.o] = enc(b); m.nbr[3 * b.t + b.o] = enc(a); }
+MESH_FN OTri lnext(OTri a) { return (a & ~3) | plus1(a & 3); }
+MESH_FN OTri lprev(OTri a) { return (a & ~3) | minus1(a & 3); }
+MESH_FN int enc(OTri a) { return a; }
+MESH_FN OTri dec(int e) { return e; }
+MESH_FN OTri sym(const Mesh& m, OTri a) { return m.nbr[a]; }
+MESH_FN int org(const Mesh& m, OTri a) { return m.vtx[lnext(a)]; }
+MESH_FN int dest(const Mesh& m, OTri a) { return m.vtx[lprev(a)]; }
+MESH_FN int apex(const Mesh& m, OTri a) { return m.vtx[a]; }
+MESH_FN void set_org(const Mesh& m, OTri a, int v) { m.vtx[lnext(a)] = v; }
+MESH_FN void set_dest(const Mesh& m, OTri a, int v) { m.vtx[lprev(a)] = v; }
+MESH_FN void set_apex(const Mesh& m, OTri a, int v) { m.vtx[a] = v; }
+MESH_FN void bond(const Mesh& m, OTri a, OTri b) { m.nbr[a] = b; m.nbr[b] = a; }
 MESH_FN OTri make(const Mesh& m, int t)
 {
-    for (int i = 0; i < 3; i++) { m.nbr[3 * t + i] = -1; m.vtx[3 * t + i] = -1; }
-    return {t, 0};
+    for (int i = 0; i < 3; i++) { m.nbr[4 * t + i] = -1; m.vtx[4 * t + i] = -1; }
+    return 4 * t;
 }
 
 // A vertex with its coordinates in registers: the merge loop keeps the four corners of the knitting edge and
@@ -587,7 +591,7 @@ MESH_FN void real_flags(const Mesh& m, int32_t* flag, int tid, int nthr)
 {
     const int nt = 2 * m.n - 2;
     for (int t = tid; t < nt; t += nthr)
-        flag[t] = m.vtx[3 * t] >= 0 && m.vtx[3 * t + 1] >= 0 && m.vtx[3 * t + 2] >= 0;
+        flag[t] = m.vtx[4 * t] >= 0 && m.vtx[4 * t + 1] >= 0 && m.vtx[4 * t + 2] >= 0;
 }
 // scan = inclusive prefix sum of flag[]; tri_out = (c1,c2,c3) triples
 MESH_FN void write_triangles(const Mesh& m, const int32_t* flag, const int32_t* scan, int32_t* tri_out, int tid, int nthr)
@@ -596,7 +600,7 @@ MESH_FN void write_triangles(const Mesh& m, const int32_t* flag, const int32_t* 
     for (int t = tid; t < nt; t += nthr) {
         if (!flag[t]) continue;
         int32_t* o = tri_out + 3 * (scan[t] - 1);
-        o[0] = m.vtx[3 * t + 1]; o[1] = m.vtx[3 * t + 2]; o[2] = m.vtx[3 * t];
+        o[0] = m.vtx[4 * t + 1]; o[1] = m.vtx[4 * t + 2]; o[2] = m.vtx[4 * t];
     }
 }
 

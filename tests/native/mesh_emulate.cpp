@@ -85,7 +85,7 @@ int mesh_emulate_delaunay(const int32_t* support, int n, int right_image, int W,
         emu.phase([&](int t, int k) { order_scatter(o, axis, t, k); });
         emu.phase([&](int t, int k) { order_commit(o, axis, t, k); });
     }
-    std::vector<int32_t> nbr(3 * (size_t)(2 * n)), vtx(3 * (size_t)(2 * n)), hull(2 * (size_t)n);
+    std::vector<int32_t> nbr(4 * (size_t)(2 * n)), vtx(4 * (size_t)(2 * n)), hull(2 * (size_t)n);
     std::vector<uint32_t> xy(n);
     for (int i = 0; i < n; i++) xy[i] = ((uint32_t)x[i] << 16) | (uint32_t)y[i];
     Mesh m{n, xy.data(), xs.data(), nbr.data(), vtx.data(), hull.data()};
