@@ -247,7 +247,7 @@ def main():
     share = cores // max(world, 1)
     # The whole frame runs on the GPU, so a worker only enqueues launch chains and collects results (the end-to-end
     # path also widens D2 from int16 on the host): a few per GPU, one core per rank stays free for the main thread
-    workers = args.workers or max(1, min(6, share - 1))
+    workers = args.workers or max(1, min(8, share - 1))
     slots = args.slots or max(2, min(24, 3 * workers))
     B = args.batch or CONFIGS[args.config][3]
     args.distinct = min(args.distinct, B)
@@ -302,6 +302,10 @@ def main():
     def step_host():
         return engine.process_batch_ptrs(*host_ptrs, bpl, device=False)
 
+    def step_host_left_only():
+        # opt-in: the right map is not returned (D2[i] == NULL); stereomapper reads only D1 (stereothread.cpp:116-147)
+        return engine.process_batch_ptrs(host_ptrs[0], host_ptrs[1], host_ptrs[2], [0] * B, bpl, device=False)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -338,6 +342,9 @@ def main():
     barrier()
     ms_host, bad_host = timed(step_host, args.steps)
     barrier()
+    ms_left, bad_left = timed(step_host_left_only, max(2, args.steps // 2))
+    ms_left /= max(2, args.steps // 2)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # parity guards inside the bench: device-resident and host paths must give identical maps, and every rank
@@ -355,7 +362,7 @@ def main():
             oracle_mismatch += 1
     oracle_mismatch, oracle_checked = (int(x) for x in sharding.sum_over_ranks([oracle_mismatch, oracle_checked], dev))
 
-    ms_dev_max, ms_host_max = sharding.max_over_ranks([ms_dev, ms_host], dev)
+    ms_dev_max, ms_host_max, ms_left_max = sharding.max_over_ranks([ms_dev, ms_host, ms_left], dev)
 
     # roofline of the matching kernel: isolated launches cycling over all slots' tables (their
     # combined descriptors exceed L2), CUDA events on the launching stream, L2 flushed first
@@ -444,7 +451,11 @@ def main():
                     # D1 as float32; D2 (final after the L/R check: integers or -10) crosses as int16
                     # and is widened into the caller's float map by the library (elas_b200.cu)
                     "d2h_bytes_per_step": world * B * W * H * (4 + 2),
-                    "ms_per_step": round(ms_host_max / args.steps, 4)},
+                    "ms_per_step": round(ms_host_max / args.steps, 4),
+                    "bound": "PCIe device->host: 2.79 MB per pair (D1 float32 + D2 int16)"},
+            "e2e_left_map_only": {"value": round(world * B / (ms_left_max * 1e-3), 2), "unit": "pairs/s",
+                                  "d2h_bytes_per_step": world * B * W * H * 4,
+                                  "note": "opt-in D2 == NULL: only the left map returns (what stereomapper reads, stereothread.cpp:116-147)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right, one launch per frame group)", "frames_per_launch": k7_frames,
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
@@ -457,7 +468,7 @@ def main():
             "drop_in_call": drop_in,
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "checks": {"frames_not_ok": bad_dev + bad_host, "device_and_host_paths_identical": same,
+            "checks": {"frames_not_ok": bad_dev + bad_host + bad_left, "device_and_host_paths_identical": same,
                        "oracle_frames_checked": oracle_checked, "oracle_mismatch": oracle_mismatch},
         }
         print(json.dumps(line), flush=True)

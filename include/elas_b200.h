@@ -119,7 +119,9 @@ int32_t elas_b200_process_ctx(elas_b200_ctx* ctx, int32_t slot,
 
 /* n frames pipelined over all slots.  Host buffers; images are tightly strided by
  * bytes_per_line; I1[i], I2[i], D1[i], D2[i] address frame i.  Host<->device copies are part
- * of the call.  status[i] (optional) receives the per-frame return code. */
+ * of the call.  status[i] (optional) receives the per-frame return code.  D2[i] may be NULL: the right map of
+ * that frame is then not returned (it is still computed, the left/right check needs it) -- stereomapper reads only
+ * D1 (stereothread.cpp:116-147), and the return path is what bounds the end-to-end rate (2/3 of the bytes). */
 int32_t elas_b200_process_batch(elas_b200_ctx* ctx, int32_t n,
                                 const uint8_t* const* I1, const uint8_t* const* I2,
                                 float* const* D1, float* const* D2,

@@ -538,6 +538,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     for (int f = 0; f < n; f++)
         for (int k = 0; k < 2; k++) {
             float* user = k ? s.io[f].D2 : s.io[f].D1;
+            if (!user) continue;                     // batch calls may leave D2 out (stereomapper never reads it)
             direct[k][f] = fused_post && (s.io[f].device_io || classify(user, c->device).device);
             if (k == 1 && direct[k][f]) any_direct_d2 = true;
             if (direct[k][f]) all_host = false;
@@ -625,8 +626,8 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     for (int f = 0; f < n; f++) {
         s.expand_D2[f] = nullptr;
         for (int k = 0; k < 2; k++) {
-            if (direct[k][f]) continue;
             float* user = k ? s.io[f].D2 : s.io[f].D1;
+            if (direct[k][f] || !user) continue;
             if (k == 1 && d2_i16) {
                 CK(cudaMemcpyAsync(s.h_D2_i16 + (size_t)f * gs.D, s.d_D2_i16 + (size_t)f * gs.D, ND * 2, cudaMemcpyDeviceToHost, out_stream));
                 s.expand_D2[f] = user;
