@@ -111,6 +111,7 @@ void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* 
                     const uint4* desc2, int16_t* dcan, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K3  lattice filters + support list (elas.cpp:174-279, :496-517), one CTA per frame; fills hdr[f].n_support
 bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p);
+size_t lattice_work_ints(const FrameGeom& g);
 void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
                     int32_t* support, int32_t* work, FrameHeader* hdr, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K4  Delaunay triangulation of both images + scan-conversion work units (elas.cpp:534-600, triangle.cpp), one CTA

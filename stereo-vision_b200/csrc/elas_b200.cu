@@ -865,7 +865,20 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
     // warp each (FrameHeader::ovf_from), so this is a performance knob, not a limit.
     c->unit_cap = c->tri_cap + 4 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
     c->mesh_device = mesh_on_device(g, *p);
-    if (const char* e = std::getenv("ELAS_B200_HOST_STAGE")) if (std::atoi(e)) c->mesh_device = false;
+    {
+        // A lattice that fits one CTA's shared memory (up to ~1920x1080) is filtered and triangulated on the GPU in
+        // tens to hundreds of microseconds.  Beyond that the single-CTA kernels work out of L2 and take milliseconds:
+        // still the better choice when few host threads serve this GPU (8 GPUs on one host), but with a core per
+        // worker to spare the host stage keeps up and leaves the SMs to the bandwidth kernels.
+        int cores = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+        const int workers_hint = n_workers > 0 ? n_workers : cores;
+        const bool big_lattice = lattice_work_ints(g) * 4 > (size_t)1 << 20 || (size_t)g.Wc * g.Hc > 60000;
+        if (c->mesh_device && big_lattice && workers_hint >= 8) c->mesh_device = false;
+    }
+    // ELAS_B200_HOST_STAGE=1 forces the host stage, =0 the device mesh stage wherever the parameters allow it
+    if (const char* e = std::getenv("ELAS_B200_HOST_STAGE")) c->mesh_device = std::atoi(e) ? false : mesh_on_device(g, *p);
     // both SAD kernels stage their descriptor strips (segment + disparity range) in shared memory: at most
     // 200 KB per CTA, i.e. disp_max up to ~700 for the support search
     if (matching_smem_bytes(g, *p) > 200 * 1024 || support_smem_bytes(g, *p) > 200 * 1024 ||
@@ -897,7 +910,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
         st.map = (size_t)map_pitch(g) * g.H;          // int32
         st.D = (size_t)g.Dw * g.Dh;                   // float
         st.mesh_scratch = 22 * (size_t)c->support_cap + 8;
-        st.lat_work = 3 * (size_t)g.Wc * g.Hc;
+        st.lat_work = lattice_work_ints(g);
         st.seg_nodes = segment_node_ints(g);
     }
     for (int i = 0; i < n_groups; i++) {

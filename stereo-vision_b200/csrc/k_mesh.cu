@@ -97,6 +97,7 @@ struct LatticeArgs {
     FrameHeader* hdr;
     size_t dcan_stride, support_stride, work_stride;
     int cnt_in_smem;
+    int lat_in_smem;             // 0: the padded working copy of a big lattice lives behind the work area (global memory, L2)
 };
 
 __global__ void __launch_bounds__(kMeshThreads)
@@ -105,16 +106,17 @@ k_lattice(const LatticeArgs a)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int32_t warp_sums[32];
     const int f = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
-    mesh::Lattice L{a.Wc, a.Hc, a.Wc + 2 * mesh::kPadC, a.step, reinterpret_cast<int16_t*>(smem_raw)};
-    const size_t lat_bytes = ((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15;
+    const int cells = a.Wc * a.Hc;
+    int32_t* cnt = a.work + (size_t)f * a.work_stride;
+    int32_t* lists[2] = {cnt + cells, cnt + 2 * cells};
+    mesh::Lattice L{a.Wc, a.Hc, a.Wc + 2 * mesh::kPadC, a.step,
+                    a.lat_in_smem ? reinterpret_cast<int16_t*>(smem_raw) : reinterpret_cast<int16_t*>(cnt + 3 * (size_t)cells)};
+    const size_t lat_bytes = a.lat_in_smem ? ((size_t)mesh::lat_elems(a.Wc, a.Hc) * 2 + 15) & ~(size_t)15 : 0;
     int32_t* col = reinterpret_cast<int32_t*>(smem_raw + lat_bytes);         // [Wc + 1]
     __shared__ int n_list[2];
     const int16_t* raw = a.dcan_raw + (size_t)f * a.dcan_stride;
     int16_t* out = a.dcan + (size_t)f * a.dcan_stride;
     int32_t* support = a.support + (size_t)f * a.support_stride;
-    const int cells = a.Wc * a.Hc;
-    int32_t* cnt = a.work + (size_t)f * a.work_stride;
-    int32_t* lists[2] = {cnt + cells, cnt + 2 * cells};
     if (a.cnt_in_smem) {
         // the supporter counts take thousands of dependent atomic decrements: in shared memory when they fit
         int32_t* scnt = reinterpret_cast<int32_t*>(smem_raw + lat_bytes + (((size_t)a.Wc + 1) * 4 + 15 & ~(size_t)15));
@@ -279,14 +281,19 @@ size_t lattice_smem_bytes(const FrameGeom& g)
     return (((size_t)mesh::lat_elems(g.Wc, g.Hc) * 2 + 15) & ~(size_t)15) + ((size_t)g.Wc + 1) * 4;
 }
 
+// ints of k_lattice's work area per frame: supporter counts, two work lists, and room for the padded lattice
+size_t lattice_work_ints(const FrameGeom& g)
+{
+    return 3 * (size_t)g.Wc * g.Hc + ((size_t)mesh::lat_elems(g.Wc, g.Hc) + 1) / 2 + 4;
+}
+
 // parameters / sizes the device mesh stage handles; everything else takes the host stage (host_stage.cc)
 bool mesh_on_device(const FrameGeom& g, const elas_b200_params& p)
 {
     return !p.add_corners &&                                  // elas.cpp:283-318 appends points outside the lattice
            2 * p.lr_threshold < g.step &&                     // no two support points on one right-image pixel
            p.incon_window_size <= mesh::kPadC && p.incon_window_size >= 0 &&
-           p.disp_max < mesh::kRemoved && g.W < 16384 && g.H < 16384 &&
-           lattice_smem_bytes(g) <= 224 * 1024;
+           p.disp_max <= mesh::kValueMask && g.W < 16384 && g.H < 16384;
 }
 
 void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t* dcan_raw, int16_t* dcan, int16_t* dcan_incon,
@@ -297,11 +304,16 @@ void launch_lattice(const FrameGeom& g, const elas_b200_params& p, const int16_t
     ELASB_PREPARE_KERNEL(k_lattice_count);
     k_lattice_count<<<dim3((g.Wc * g.Hc + 255) / 256, n_frames), 256, 0, s>>>(g.Wc, g.Hc, p.incon_window_size, p.incon_threshold,
                                                                              dcan_raw, work, st.dcan, st.lat_work);
-    // lattice + column table, plus the supporter counts if they fit as well
-    const size_t base = lattice_smem_bytes(g), with_counts = ((base + 15) & ~(size_t)15) + (size_t)g.Wc * g.Hc * 4;
-    const bool cnt_in_smem = with_counts <= 200 * 1024;
+    // shared memory: lattice + column table, plus the supporter counts if they fit as well; a lattice beyond that
+    // (4096x2160: 820x432 cells) is worked on in global memory (it stays in L2)
+    size_t base = lattice_smem_bytes(g);
+    const bool lat_in_smem = base <= 200 * 1024;
+    if (!lat_in_smem) base = ((size_t)g.Wc + 1) * 4;
+    const size_t with_counts = ((base + 15) & ~(size_t)15) + (size_t)g.Wc * g.Hc * 4;
+    const bool cnt_in_smem = lat_in_smem && with_counts <= 200 * 1024;
     LatticeArgs a{g.Wc, g.Hc, g.step, p.incon_window_size, p.incon_threshold, p.incon_min_support,
-                  dcan_raw, dcan, dcan_incon, support, work, hdr, st.dcan, st.support, st.lat_work, cnt_in_smem ? 1 : 0};
+                  dcan_raw, dcan, dcan_incon, support, work, hdr, st.dcan, st.support, st.lat_work, cnt_in_smem ? 1 : 0,
+                  lat_in_smem ? 1 : 0};
     k_lattice<<<n_frames, kMeshThreads, cnt_in_smem ? with_counts : base, s>>>(a);
     count_launch(2);
 }
@@ -310,11 +322,17 @@ void launch_delaunay(const FrameGeom& g, const int32_t* support, int32_t* tri1, 
                      int unit_cap, FrameHeader* hdr, int32_t* scratch, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     static unsigned long long optin = 0;
-    constexpr int kSmem = 200 * 1024;
-    if (ensure_dynamic_smem(k_delaunay, kSmem, &optin) != cudaSuccess) return;
-    DelaunayArgs a{g.W, g.H, unit_cap, kSmem / 4, support, {tri1, tri2}, {units1, units2}, hdr, scratch,
+    constexpr int kSmemMax = 200 * 1024;
+    if (ensure_dynamic_smem(k_delaunay, kSmemMax, &optin) != cudaSuccess) return;
+    // A triangulation works in shared memory when its 22 n ints fit, else in the global scratch area.  Frames whose
+    // lattice is so large that the typical support set (about a twelfth of the lattice cells at most) cannot fit
+    // anyway are launched without the shared-memory reservation: their long-running CTAs then leave the SM's
+    // shared memory to the kernels of other frame groups.
+    const bool may_fit = (size_t)(g.Wc * g.Hc / 12) * 22 * 4 <= (size_t)kSmemMax;
+    const int smem = may_fit ? kSmemMax : 1024;
+    DelaunayArgs a{g.W, g.H, unit_cap, smem / 4, support, {tri1, tri2}, {units1, units2}, hdr, scratch,
                    st.support, st.tri, st.units, st.mesh_scratch};
-    k_delaunay<<<dim3(2, n_frames), kDelaunayThreads, kSmem, s>>>(a);
+    k_delaunay<<<dim3(2, n_frames), kDelaunayThreads, smem, s>>>(a);
     count_launch();
 }
 

@@ -119,8 +119,11 @@ def test_cuda_matches_oracle_all_stages(oracle, tag, W, H, dmax, seed, mk):
     check_against(st, st_o, D1, D2, tag)
 
 
-def test_hd_config_all_stages(oracle):
-    """BASELINE config 2: 1920x1080, d_max 128 (two column segments per row in the matching kernel)."""
+@pytest.mark.parametrize("mesh", ["device", "host"])
+def test_hd_config_all_stages(oracle, monkeypatch, mesh):
+    """BASELINE config 2: 1920x1080, d_max 128, with the mesh stage (lattice filters + Delaunay) on the GPU -- the
+    triangulation of ~4000 points works out of the global scratch area -- and on the host."""
+    monkeypatch.setenv("ELAS_B200_HOST_STAGE", "0" if mesh == "device" else "1")
     L, R, _ = synth.synthetic_pair(1920, 1080, 128, 0)
     p = checkers.stereomapper(128)
     rc_o, _, _, st_o = oracle.run_stages(L, R, p)
@@ -252,18 +255,21 @@ def test_batch_scheduler_more_slots_than_workers_and_a_blank_frame(oracle):
         assert status2[i] == status[i] and bits_equal(E1[i], D1[i]) and bits_equal(E2[i], D2[i])
 
 
-def test_bandwidth_config_4096x2160_all_stages(oracle):
+def test_bandwidth_config_4096x2160_all_stages(oracle, monkeypatch):
     """BASELINE.json configs[4] geometry at full size (the oracle takes ~10 s): every stage against the
-    oracle, then the size-independent properties -- two slots agree bit for bit, the batch path agrees with
-    the single-frame path, D2 (L/R-checked only) holds integers."""
+    oracle with the mesh stage on the GPU (820x432 lattice and ~14 600 support points worked on in global
+    memory), then the size-independent properties with the host stage -- two slots agree bit for bit, the batch
+    path agrees with the single-frame path, D2 (L/R-checked only) holds integers."""
     W, H, dmax = 4096, 2160, 256
     L, R, _ = synth.synthetic_pair(W, H, dmax, 1)
     p = checkers.stereomapper(dmax)
     rc_o, _, _, st_o = oracle.run_stages(L, R, p)
+    monkeypatch.setenv("ELAS_B200_HOST_STAGE", "0")
     rc, A1, A2, st = run_cuda(L, R, p)
     assert rc == rc_o == 0
     check_against(st, st_o, A1, A2, "4096x2160")
     del st, st_o
+    monkeypatch.setenv("ELAS_B200_HOST_STAGE", "1")
     e = elas_b200.ElasB200(elas_b200.stereomapper(dmax), W, H, n_slots=2, n_workers=2)
     try:
         rc, B1, B2 = e.process(L, R, slot=1)
