@@ -179,6 +179,20 @@ int32_t elas_b200_reproject(elas_b200_ctx* ctx, int32_t slot, const uint8_t* I1,
                             const float* D1, const elas_b200_view* view,
                             float* I, float* D, float* X, float* Y, float* Z);
 
+/* Fusion of the current map with the previous one: StereoThread::addDisparityMapToReconstruction
+ * (stereothread.cpp:290-437).  cur = the map elas_b200_reproject produced for this frame (I, D, X, Y, Z, width x
+ * height floats each; host or device memory), fused in place: previous points that project onto a current point
+ * closer than 0.2 (L1) are averaged into it, points that land where the current map has none are created there
+ * (D = 1).  prev = the fused map the PREVIOUS call returned in `cur` (the reference hands its own previous map over
+ * through freed memory, :433-434; this is the evident intent), or NULL for the first frame; prev->D comes back with
+ * the merged points invalidated.  view->H = the CURRENT pose.  points_prev / points_curr (capacity width*height x 4
+ * floats each) receive (x, y, z, intensity) of the previous points that were kept and of all valid current points,
+ * both in the reference's push_back order (u outer, v inner); these are the two lists handed to View3D::addPoints. */
+typedef struct elas_b200_map3d { float* I; float* D; float* X; float* Y; float* Z; } elas_b200_map3d;
+int32_t elas_b200_fuse(elas_b200_ctx* ctx, int32_t slot, const elas_b200_view* view,
+                       const elas_b200_map3d* prev, const elas_b200_map3d* cur,
+                       float* points_prev, int32_t* n_prev, float* points_curr, int32_t* n_curr);
+
 /* ------------------------------------------------------------------------------------------
  * 3. Introspection for parity tests and the bench (not used by stereomapper).
  * ------------------------------------------------------------------------------------------ */

@@ -192,6 +192,7 @@ class ViewChecker:
     (kind="oracle") or the reference's own statements compiled by oracle/Makefile (kind="ref")."""
 
     def __init__(self, kind="oracle"):
+        self.kind = kind
         if kind == "ref":
             self.lib, prefix = C.CDLL(VIEW_REF_SO), "ref"
         else:
@@ -204,6 +205,39 @@ class ViewChecker:
         self._reproject = getattr(self.lib, f"{prefix}_reproject")
         self._reproject.restype = None
         self._reproject.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_void_p] * 5
+
+    def fuse(self, I1, D1, view, H, prev=None):
+        """StereoThread::addDisparityMapToReconstruction (stereothread.cpp:290-437) for one frame: builds the current
+        map (createCurrentMap) and fuses it with `prev` (the fused map (I, D, X, Y, Z) the previous call returned, or
+        None).  Returns (fused current map [I, D, X, Y, Z], previous D after the call or None, points_prev, points_curr)."""
+        I1 = np.ascontiguousarray(I1, np.uint8) if I1.strides[1] != 1 else I1
+        D1 = np.ascontiguousarray(D1, np.float32)
+        h, w = D1.shape
+        view = np.ascontiguousarray(view, np.float32)
+        H = np.ascontiguousarray(H, np.float64).reshape(12)
+        n = w * h
+        cur = [np.zeros((h, w), np.float32) for _ in range(5)]
+        pts_prev, pts_curr = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+        n_prev, n_curr = C.c_int32(0), C.c_int32(0)
+        pv = [np.ascontiguousarray(a, np.float32).copy() for a in prev] if prev is not None else None
+        if self.kind == "ref":
+            P5 = C.c_void_p * 5
+            parr = P5(*[a.ctypes.data for a in pv]) if pv else P5(None, None, None, None, None)
+            carr = P5(*[a.ctypes.data for a in cur])
+            self.lib.ref_fuse.restype = None
+            self.lib.ref_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
+            self.lib.ref_fuse(I1.ctypes.data, D1.ctypes.data, w, h, I1.strides[0], view.ctypes.data, H.ctypes.data,
+                              parr, carr, pts_prev.ctypes.data, C.byref(n_prev), pts_curr.ctypes.data, C.byref(n_curr))
+        else:
+            cur = list(self.reproject(I1, D1, view, H))
+            self.lib.oracle_fuse.restype = None
+            self.lib.oracle_fuse.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p] + [C.c_void_p] * 10 + \
+                                            [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]
+            pp = [a.ctypes.data for a in pv] if pv else [None] * 5
+            self.lib.oracle_fuse(w, h, view.ctypes.data, H.ctypes.data, *pp, *[a.ctypes.data for a in cur],
+                                 pts_prev.ctypes.data, C.byref(n_prev), pts_curr.ctypes.data, C.byref(n_curr))
+        return cur, (pv[1] if pv else None), pts_prev[:n_prev.value].copy(), pts_curr[:n_curr.value].copy()
 
     def colormap(self, D1):
         D1 = np.ascontiguousarray(D1, np.float32)

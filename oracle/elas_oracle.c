@@ -1324,3 +1324,118 @@ void oracle_reproject(const uint8_t* I1, const float* D1, int32_t width, int32_t
         }
     }
 }
+
+/* Matrix::inv of a 4x4 (libviso2/src/matrix.cpp:593-604 = eye(4).solve(A), :648-757): Gauss-Jordan elimination with
+ * full pivoting in double; B = identity on entry, the inverse on exit.  Returns 0 when a pivot is below 1e-20. */
+static int oracle_inv4(double A[4][4], double B[4][4])
+{
+    int ipiv[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) B[i][j] = i == j;
+    int irow = 0, icol = 0;
+    for (int i = 0; i < 4; i++) {
+        double big = 0.0;
+        for (int j = 0; j < 4; j++)
+            if (ipiv[j] != 1)
+                for (int k = 0; k < 4; k++)
+                    if (ipiv[k] == 0 && fabs(A[j][k]) >= big) { big = fabs(A[j][k]); irow = j; icol = k; }
+        ++ipiv[icol];
+        if (irow != icol)
+            for (int l = 0; l < 4; l++) {
+                double t = A[irow][l]; A[irow][l] = A[icol][l]; A[icol][l] = t;
+                t = B[irow][l]; B[irow][l] = B[icol][l]; B[icol][l] = t;
+            }
+        if (fabs(A[icol][icol]) < 1e-20) return 0;
+        const double pivinv = 1.0 / A[icol][icol];
+        A[icol][icol] = 1.0;
+        for (int l = 0; l < 4; l++) A[icol][l] *= pivinv;
+        for (int l = 0; l < 4; l++) B[icol][l] *= pivinv;
+        for (int ll = 0; ll < 4; ll++)
+            if (ll != icol) {
+                const double dum = A[ll][icol];
+                A[ll][icol] = 0.0;
+                for (int l = 0; l < 4; l++) A[ll][l] -= A[icol][l] * dum;
+                for (int l = 0; l < 4; l++) B[ll][l] -= B[icol][l] * dum;
+            }
+    }
+    return 1;
+}
+
+/* Fusion of the current map with the previous one, StereoThread::addDisparityMapToReconstruction,
+ * stereothread.cpp:290-437.  The previous map (p*, may all be NULL) is the fused current map of the call before
+ * (the reference's own hand-over, :433-434, frees what it has just copied; see oracle/ref_view_harness.cpp); pD comes
+ * back with the merged points invalidated.  The current map (c*, from oracle_reproject) is fused in place.
+ * view = {f, cu, cv, base, max_dist, gain}; H = rows 0..2 of the current pose.  points_*: (x,y,z,val) quadruples. */
+void oracle_fuse(int32_t width, int32_t height, const float* view, const double* H,
+                 float* pI, float* pD, float* pX, float* pY, float* pZ,
+                 float* cI, float* cD, float* cX, float* cY, float* cZ,
+                 float* points_prev, int32_t* n_prev, float* points_curr, int32_t* n_curr)
+{
+    const float max_dist = view[4];
+    *n_prev = 0;
+    if (pI && pD && pX && pY && pZ) {                                           /* :296-300 */
+        double A[4][4] = {{0}}, Hi[4][4];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) A[r][c] = H[4 * r + c];
+        A[3][3] = 1.0;
+        if (!oracle_inv4(A, Hi)) { /* Matrix::solve returns false and leaves B half reduced; poses are never singular */ }
+        const float hfc20 = (float)Hi[2][0], hfc21 = (float)Hi[2][1], hfc22 = (float)Hi[2][2], hfc23 = (float)Hi[2][3];   /* :303-304 */
+        double K[3][3] = {{view[0], 0, view[1]}, {0, view[0], view[2]}, {0, 0, 1}};      /* :450-455 */
+        float pfc[3][4];
+        for (int i = 0; i < 3; i++)                                              /* :307, Matrix::operator* matrix.cpp:396-418 */
+            for (int j = 0; j < 4; j++) {
+                double acc = 0.0;
+                for (int k = 0; k < 3; k++) acc += K[i][k] * Hi[k][j];
+                pfc[i][j] = (float)acc;
+            }
+        for (int32_t u = 0; u < width; u++)                                      /* :315-403 */
+            for (int32_t v = 0; v < height; v++) {
+                const int32_t addr = v * width + u;
+                const float d = pD[addr];
+                if (!(d > 0)) continue;
+                const float x = pX[addr], y = pY[addr], z = pZ[addr];
+                const float z2 = hfc20 * x + hfc21 * y + hfc22 * z + hfc23;
+                int added = 0;
+                if (((double)z2 > 0.1) && (z2 < max_dist)) {
+                    const float w2 = pfc[2][0] * x + pfc[2][1] * y + pfc[2][2] * z + pfc[2][3];
+                    const float qu = (pfc[0][0] * x + pfc[0][1] * y + pfc[0][2] * z + pfc[0][3]) / w2;
+                    const float qv = (pfc[1][0] * x + pfc[1][1] * y + pfc[1][2] * z + pfc[1][3]) / w2;
+                    /* (int32_t) of a float on x86-64 (cvttss2si): out of range and NaN give INT32_MIN */
+                    const int32_t u2 = (qu >= -2147483648.0f && qu < 2147483648.0f) ? (int32_t)qu : INT32_MIN;
+                    const int32_t v2 = (qv >= -2147483648.0f && qv < 2147483648.0f) ? (int32_t)qv : INT32_MIN;
+                    if (u2 >= 0 && u2 < width && v2 >= 0 && v2 < height) {
+                        const int32_t addr2 = v2 * width + u2;
+                        const float d2 = cD[addr2];
+                        if (d2 > 0) {
+                            if ((double)(fabsf(x - cX[addr2]) + fabsf(y - cY[addr2]) + fabsf(z - cZ[addr2])) < 0.2) {   /* :359 */
+                                cX[addr2] = (float)((cX[addr2] + x) / 2.0);
+                                cY[addr2] = (float)((cY[addr2] + y) / 2.0);
+                                cZ[addr2] = (float)((cZ[addr2] + z) / 2.0);
+                                cI[addr2] = (float)((cI[addr2] + pI[addr]) / 2.0);
+                                added = 1;
+                            }
+                        } else {
+                            cX[addr2] = x; cY[addr2] = y; cZ[addr2] = z;
+                            cI[addr2] = pI[addr];
+                            cD[addr2] = 1;
+                            added = 1;
+                        }
+                    }
+                }
+                if (added) pD[addr] = -1;                                        /* :383 */
+                else {
+                    float* o = points_prev + 4 * (size_t)(*n_prev)++;
+                    o[0] = x; o[1] = y; o[2] = z; o[3] = pI[addr];
+                }
+            }
+    }
+    *n_curr = 0;
+    for (int32_t u = 0; u < width; u++)                                          /* :414-430 */
+        for (int32_t v = 0; v < height; v++) {
+            const int32_t addr = v * width + u;
+            if (cD[addr] > 0) {
+                float* o = points_curr + 4 * (size_t)(*n_curr)++;
+                o[0] = cX[addr]; o[1] = cY[addr]; o[2] = cZ[addr]; o[3] = cI[addr];
+            }
+        }
+}

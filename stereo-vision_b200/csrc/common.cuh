@@ -206,6 +206,11 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long l
         if (::elasb::ensure_dynamic_smem(kernel, 0, &prepared__) != cudaSuccess) return;    \
     } while (0)
 
+// fusion of the current map with the previous one (stereothread.cpp:290-437); maps are device pointers {I, D, X, Y, Z}
+size_t fuse_work_ints(int W, int H);
+bool launch_fuse(int W, int H, const elas_b200_view& view, float* const* prev, float* const* cur, int32_t* work,
+                 float* points_prev, float* points_curr, int32_t* counts, cudaStream_t s);
+
 // number of kernel launches issued through the launchers above (process-wide, relaxed)
 long long launches_issued();
 void count_launch(int n = 1);

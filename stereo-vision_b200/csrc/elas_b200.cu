@@ -111,6 +111,7 @@ struct Group {
     std::vector<float*> expand_D2;             // caller's D2 awaiting widening at finish (null: nothing to do)
     int last_n = 0;                            // frames of the last completed chain (elas_b200_time_matching)
     float* d_view = nullptr;                   // colour map / back-projection outputs (5 planes), allocated on first use
+    float* d_fuse = nullptr;                   // map fusion: previous + current map (10 planes), two point lists, work area
     float* last_D1 = nullptr;                  // frame 0's final left map of the last chain, if it lives in the group's buffers
     int map_tag = 0;                           // frame tag of the triangle-id map entries (k_grid_raster.cu)
     int scratch_phase = 0;                     // which of the two grid scatter buffers this chain uses
@@ -205,7 +206,7 @@ void free_group(Group& s)
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]); cudaFree(s.d_planes[k]);
     }
     cudaFree(s.d_dcan_raw); cudaFree(s.d_dcan); cudaFree(s.d_dcan_incon); cudaFree(s.d_support); cudaFree(s.d_mesh_scratch); cudaFree(s.d_lat_work);
-    cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16); cudaFreeHost(s.h_hdr);
+    cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_fuse); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16); cudaFreeHost(s.h_hdr);
     cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp); cudaFree(s.d_seg_label); cudaFree(s.d_seg_nodes);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -1119,6 +1120,52 @@ int32_t elas_b200_reproject(elas_b200_ctx* c, int32_t slot, const uint8_t* I1, i
     for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(user[k], out[k], n * 4, cudaMemcpyDefault, s.stream));
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
+    return ELAS_B200_OK;
+}
+
+int32_t elas_b200_fuse(elas_b200_ctx* c, int32_t slot, const elas_b200_view* view, const elas_b200_map3d* prev,
+                       const elas_b200_map3d* cur, float* points_prev, int32_t* n_prev, float* points_curr, int32_t* n_curr)
+{
+    if (!c || slot < 0 || slot >= (int)c->groups.size() || !view || !cur || !points_curr || !n_curr) return ELAS_B200_E_BAD_ARG;
+    if (!cur->I || !cur->D || !cur->X || !cur->Y || !cur->Z) return ELAS_B200_E_BAD_ARG;
+    const bool has_prev = prev && prev->I && prev->D && prev->X && prev->Y && prev->Z;      // stereothread.cpp:296-300
+    if (has_prev && (!points_prev || !n_prev)) return ELAS_B200_E_BAD_ARG;
+    if (c->p.subsampling) return ELAS_B200_E_UNSUPPORTED;                 // the maps are full-resolution (createCurrentMap)
+    std::lock_guard<std::mutex> batch(c->batch_mu);
+    CK(cudaSetDevice(c->device));
+    Group& s = *c->groups[slot];
+    const int W = c->g.W, H = c->g.H;
+    const size_t n = (size_t)W * H;
+    // device layout: [prev I D X Y Z | cur I D X Y Z | points_prev 4n | points_curr 4n | work ints | 2 counts]
+    const size_t floats = 18 * n, ints = fuse_work_ints(W, H) + 2;
+    if (!s.d_fuse) CK(cudaMalloc(&s.d_fuse, (floats + ints) * 4));
+    float* pm[5]; float* cm[5];
+    for (int k = 0; k < 5; k++) { pm[k] = s.d_fuse + (size_t)k * n; cm[k] = s.d_fuse + (size_t)(5 + k) * n; }
+    float* d_pp = s.d_fuse + 10 * n; float* d_pc = s.d_fuse + 14 * n;
+    int32_t* work = reinterpret_cast<int32_t*>(s.d_fuse + floats);
+    int32_t* d_counts = work + fuse_work_ints(W, H);
+    float* const user_prev[5] = {has_prev ? prev->I : nullptr, has_prev ? prev->D : nullptr, has_prev ? prev->X : nullptr,
+                                 has_prev ? prev->Y : nullptr, has_prev ? prev->Z : nullptr};
+    float* const user_cur[5] = {cur->I, cur->D, cur->X, cur->Y, cur->Z};
+    cudaStream_t st = s.stream;
+    for (int k = 0; k < 5; k++) {
+        if (has_prev) CK(cudaMemcpyAsync(pm[k], user_prev[k], n * 4, cudaMemcpyDefault, st));
+        CK(cudaMemcpyAsync(cm[k], user_cur[k], n * 4, cudaMemcpyDefault, st));
+    }
+    if (!launch_fuse(W, H, *view, has_prev ? pm : nullptr, cm, work, d_pp, d_pc, d_counts, st)) return ELAS_B200_E_BAD_ARG;   // singular pose
+    CK(cudaGetLastError());
+    int32_t counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(counts, d_counts, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(user_cur[k], cm[k], n * 4, cudaMemcpyDefault, st));
+    if (has_prev) {
+        CK(cudaMemcpyAsync(user_prev[1], pm[1], n * 4, cudaMemcpyDefault, st));
+        if (counts[0]) CK(cudaMemcpyAsync(points_prev, d_pp, (size_t)counts[0] * 16, cudaMemcpyDefault, st));
+        *n_prev = counts[0];
+    } else if (n_prev) *n_prev = 0;
+    if (counts[1]) CK(cudaMemcpyAsync(points_curr, d_pc, (size_t)counts[1] * 16, cudaMemcpyDefault, st));
+    *n_curr = counts[1];
+    CK(cudaStreamSynchronize(st));
     return ELAS_B200_OK;
 }
 

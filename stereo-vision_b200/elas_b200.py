@@ -45,6 +45,11 @@ class View(C.Structure):
                 ("max_dist", C.c_float), ("gain", C.c_float), ("H", C.c_double * 12)]
 
 
+class Map3D(C.Structure):
+    """elas_b200_map3d: the five planes of StereoThread::map3d (stereothread.h:51-60)."""
+    _fields_ = [("I", C.c_void_p), ("D", C.c_void_p), ("X", C.c_void_p), ("Y", C.c_void_p), ("Z", C.c_void_p)]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -55,7 +60,7 @@ EXPORTS = [
     "elas_b200_default_params", "elas_b200_stereomapper_params", "elas_b200_process",
     "elas_b200_create", "elas_b200_create_ex", "elas_b200_create_grouped", "elas_b200_frames_per_group",
     "elas_b200_mesh_on_device", "elas_b200_time_matching_ex", "elas_b200_destroy", "elas_b200_multi_create",
-    "elas_b200_multi_destroy", "elas_b200_multi_device_count", "elas_b200_multi_context", "elas_b200_multi_process_batch", "elas_b200_process_ctx", "elas_b200_process_batch",
+    "elas_b200_fuse", "elas_b200_multi_destroy", "elas_b200_multi_device_count", "elas_b200_multi_context", "elas_b200_multi_process_batch", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
@@ -118,6 +123,8 @@ def load_library():
     lib.elas_b200_colormap.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.elas_b200_reproject.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(View)] + [C.c_void_p] * 5
     lib.elas_b200_time_view.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+    lib.elas_b200_fuse.argtypes = [C.c_void_p, C.c_int32, C.POINTER(View), C.POINTER(Map3D), C.POINTER(Map3D),
+                                   C.c_void_p, i32p, C.c_void_p, i32p]
     lib.elas_b200_version.restype = C.c_char_p
     lib.elas_b200_device_count.restype = C.c_int32
     _lib = lib
@@ -263,6 +270,24 @@ class ElasB200:
         if rc != 0:
             raise RuntimeError(f"elas_b200_reproject failed with {rc}")
         return outs
+
+    def fuse(self, view, H, cur, prev=None, slot=0):
+        """StereoThread::addDisparityMapToReconstruction (stereothread.cpp:290-437).  cur / prev = [I, D, X, Y, Z]
+        (prev: what the previous call returned, or None).  Returns (fused current map, previous D after the call or
+        None, points_prev, points_curr)."""
+        v = View(*[float(x) for x in view], (C.c_double * 12)(*[float(x) for x in np.asarray(H, np.float64).reshape(12)]))
+        cur = [np.ascontiguousarray(a, np.float32).copy() for a in cur]
+        pv = [np.ascontiguousarray(a, np.float32).copy() for a in prev] if prev is not None else None
+        n = self.W * self.H
+        pts_prev, pts_curr = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+        n_prev, n_curr = C.c_int32(0), C.c_int32(0)
+        cm = Map3D(*[a.ctypes.data for a in cur])
+        pm = Map3D(*[a.ctypes.data for a in pv]) if pv else None
+        rc = self.lib.elas_b200_fuse(self.ctx, slot, C.byref(v), C.byref(pm) if pm else None, C.byref(cm),
+                                     pts_prev.ctypes.data, C.byref(n_prev), pts_curr.ctypes.data, C.byref(n_curr))
+        if rc != 0:
+            raise RuntimeError(f"elas_b200_fuse failed with {rc}")
+        return cur, (pv[1] if pv else None), pts_prev[:n_prev.value].copy(), pts_curr[:n_curr.value].copy()
 
     def time_view(self, iters=20, slot=0):
         """Mean ms per launch of (k_colormap, k_reproject) on the slot's device-resident last frame."""

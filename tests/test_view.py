@@ -50,3 +50,36 @@ def test_colormap_properties():
     assert (c[7:] == c[7]).all() and tuple(c[7]) == (1.0, 0.0, 0.0)
     lit = c[3:]
     assert (lit.max(axis=1) == 1).all() and (lit.min(axis=1) == 0).all()
+
+
+def _same_fusion(a, b, tag):
+    cur_a, pd_a, pp_a, pc_a = a
+    cur_b, pd_b, pp_b, pc_b = b
+    valid = cur_a[1] > 0
+    assert same_bits(cur_a[0], cur_b[0]) and same_bits(cur_a[1], cur_b[1]), f"{tag}: I / D"
+    for k, name in ((2, "X"), (3, "Y"), (4, "Z")):      # X/Y/Z are defined where the fused map is valid
+        assert np.array_equal(cur_a[k][valid].view(np.uint32), cur_b[k][valid].view(np.uint32)), f"{tag}: {name}"
+    assert (pd_a is None) == (pd_b is None) and (pd_a is None or same_bits(pd_a, pd_b)), f"{tag}: previous D"
+    assert same_bits(pp_a, pp_b), f"{tag}: points_prev ({len(pp_a)} vs {len(pp_b)})"
+    assert same_bits(pc_a, pc_b), f"{tag}: points_curr ({len(pc_a)} vs {len(pc_b)})"
+
+
+@pytest.mark.skipif(not checkers.have_view_ref(), reason="oracle/_ref/libview_ref.so not built")
+@pytest.mark.parametrize("name", ["street", "tiny", "backwards"])
+def test_fusion_oracle_equals_reference_statements(name):
+    """SURVEY 8(f) rank 4: StereoThread::addDisparityMapToReconstruction (stereothread.cpp:290-437) over a short
+    sequence, the previous map of a frame being the fused map of the frame before."""
+    from view_cases import fusion_sequence
+    ref, ora = checkers.ViewChecker("ref"), checkers.ViewChecker("oracle")
+    prev_r = prev_o = None
+    merged = created = 0
+    for k, (I1, D1, view, H) in enumerate(fusion_sequence(name)):
+        r = ref.fuse(I1, D1, view, H, prev_r)
+        o = ora.fuse(I1, D1, view, H, prev_o)
+        _same_fusion(r, o, f"{name} frame {k}")
+        if k:
+            merged += int(((prev_o[1] > 0) & ~(o[1] > 0)).sum())          # previous points taken over by the fusion
+            created += int((o[0][1] == 1).sum())
+        prev_r, prev_o = r[0], o[0]
+    if name == "street":
+        assert merged > 100 and created > 10      # the sequence exercises the average and the create branches
