@@ -382,6 +382,22 @@ def main():
         view = {"colormap_us": round(ms_c * 1e3, 2), "colormap_gbs": round(16 * n_px / (ms_c * 1e-3) / 1e9, 1),
                 "reproject_us": round(ms_r * 1e3, 2), "reproject_gbs": round(25 * n_px / (ms_r * 1e-3) / 1e9, 1),
                 "note": "L2-resident at this size (7-12 MB per launch)"}
+    # the feature filters of libviso2's Matcher on a device-resident 1248x375 image:
+    # algorithmic bytes 7 N (1 in, du + dv + two int16 maps out)
+    filters = None
+    if rank == 0 and args.config == "K":
+        import ctypes as C
+        lib = elas_b200.load_library()
+        d_img = d_I[0, 0].contiguous()
+        d_du, d_dv = torch.empty_like(d_img), torch.empty_like(d_img)
+        d_f1 = torch.empty(d_img.shape, dtype=torch.int16, device=dev); d_f2 = torch.empty_like(d_f1)
+        ms_f = C.c_float(0)
+        for it in (3, 50):
+            rc_f = lib.elas_b200_matcher_filters(local_rank, d_img.data_ptr(), bpl, H, d_du.data_ptr(), d_dv.data_ptr(),
+                                                 d_f1.data_ptr(), d_f2.data_ptr(), it, C.byref(ms_f))
+        if rc_f == 0:
+            filters = {"us": round(ms_f.value * 1e3, 2), "gbs": round(7 * bpl * H / (ms_f.value * 1e-3) / 1e9, 1),
+                       "note": "sobel5x5 + blob5x5 + checkerboard5x5 fused, one launch per image, L2-resident at this size"}
     # the synchronous drop-in call itself (what Elas::process forwards to, one frame at a time, pageable host
     # buffers, nothing pipelined): the latency-bound number a caller like StereoThread::run sees
     drop_in = None
@@ -464,7 +480,7 @@ def main():
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
             "roofline_hd_config": roof_hd,
-            "view_kernels": view,
+            "view_kernels": view, "matcher_filters": filters,
             "drop_in_call": drop_in,
             "cpu_baseline": cpu,
             "clocks": clocks,

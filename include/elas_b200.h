@@ -256,6 +256,22 @@ float   elas_b200_time_matching_ex(elas_b200_ctx* ctx, int32_t slot, int32_t ite
  * milliseconds per launch in ms_out = {colour map, back-projection}. */
 int32_t elas_b200_time_view(elas_b200_ctx* ctx, int32_t slot, int32_t iters, float ms_out[2]);
 
+/* ------------------------------------------------------------------------------------------
+ * 4. The feature filters of libviso2's Matcher.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces the three calls of Matcher::computeFeatures (libviso2/src/matcher.cpp:799-801):
+ *     filter::sobel5x5(I, I_du, I_dv, dims[2], dims[1]);  filter::blob5x5(I, I_f1, dims[2], dims[1]);
+ *     filter::checkerboard5x5(I, I_f2, dims[2], dims[1]);                     (libviso2/src/filter.cpp:474-530)
+ * I = bytes_per_line x height bytes (bytes_per_line a multiple of 16 as the reference asserts, height >= 6); the four
+ * maps have the same extent (I_du/I_dv uint8, I_f1/I_f2 int16).  Pointers may be host memory or 16-byte-aligned
+ * memory of `device`.  Bit-identical to the reference wherever the reference's result is defined; elements it never
+ * writes are 0, and I_du/I_dv[n-2], [n-1] (for which the reference reads beyond its temporaries) take those as 0.
+ * iters > 1 repeats the kernels (bench); *ms_per_pass, if not NULL, receives the mean device time of one pass. */
+int32_t elas_b200_matcher_filters(int32_t device, const uint8_t* I, int32_t bytes_per_line, int32_t height,
+                                  uint8_t* I_du, uint8_t* I_dv, int16_t* I_f1, int16_t* I_f2,
+                                  int32_t iters, float* ms_per_pass);
+
 /* Library / device description (static string, never freed). */
 const char* elas_b200_version(void);
 int32_t     elas_b200_device_count(void);

@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libelas_ref.so")
 ORACLE_SO = os.path.join(HERE, "_build", "libelas_oracle.so")
 VIEW_REF_SO = os.path.join(HERE, "_ref", "libview_ref.so")
+FILTER_REF_SO = os.path.join(HERE, "_ref", "libvisofilter_ref.so")
 
 PARAM_FIELDS = [
     ("disp_min", C.c_int32), ("disp_max", C.c_int32), ("support_threshold", C.c_float),
@@ -256,6 +257,35 @@ class ViewChecker:
         self._reproject(I1.ctypes.data, D1.ctypes.data, w, h, I1.strides[0], view.ctypes.data, H.ctypes.data,
                         *[o.ctypes.data for o in outs])
         return outs
+
+
+class MatcherFilterChecker:
+    """The feature filters of libviso2's Matcher (filter.cpp:474-530 as called at matcher.cpp:799-801): the plain-C
+    restatement (kind="oracle") or libviso2/src/filter.cpp itself compiled by oracle/Makefile (kind="ref")."""
+
+    def __init__(self, kind="oracle"):
+        if kind == "ref":
+            self.fn = C.CDLL(FILTER_REF_SO).ref_matcher_filters
+        else:
+            if not os.path.exists(ORACLE_SO):
+                build("oracle")
+            self.fn = C.CDLL(ORACLE_SO).oracle_matcher_filters
+        self.fn.restype = None
+        self.fn.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4
+
+    def __call__(self, I):
+        """I: uint8 [h][w], w a multiple of 16 (= bytes per line).  Returns (du, dv, f1, f2)."""
+        I = np.ascontiguousarray(I, np.uint8)
+        h, w = I.shape
+        assert w % 16 == 0
+        du, dv = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
+        f1, f2 = np.zeros((h, w), np.int16), np.zeros((h, w), np.int16)
+        self.fn(I.ctypes.data, w, h, du.ctypes.data, dv.ctypes.data, f1.ctypes.data, f2.ctypes.data)
+        return du, dv, f1, f2
+
+
+def have_filter_ref():
+    return os.path.exists(FILTER_REF_SO)
 
 
 def have_view_ref():

@@ -1439,3 +1439,63 @@ void oracle_fuse(int32_t width, int32_t height, const float* view, const double*
             }
         }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * the feature filters of libviso2's Matcher, libviso2/src/filter.cpp:474-530, as
+ * Matcher::computeFeatures calls them (matcher.cpp:799-801): sobel5x5 -> du, dv; blob5x5 -> f1; checkerboard5x5 -> f2.
+ * The reference walks the image as ONE flat array of w*h elements (w = bytes per line, a multiple of 16): the
+ * horizontal taps of a pixel near a row end come from the neighbouring row.  Plain scalar restatement:
+ *   column pass (filter.cpp:291-349, :353-391): rows 2..h-3, zero elsewhere (memset)
+ *     tv = i(-2) + 4 i(-1) + 6 i(0) + 4 i(+1) + i(+2)        th = i(-2) + 2 i(-1) - 2 i(+1) - i(+2)
+ *     tc = i(-2) + i(-1) - i(+1) - i(+2)
+ *   row pass, flat (filter.cpp:124-173, :180-222, :395-417): for j = 0, 1, ...
+ *     du[j+2] = sat_u8(((tv[j] + 2 tv[j+1] - 2 tv[j+3] - tv[j+4]) >> 7) + 128)          j < w*h  (*)
+ *     dv[j+2] = sat_u8(((th[j] + 4 th[j+1] + 6 th[j+2] + 4 th[j+3] + th[j+4]) >> 7) + 128)
+ *     f2[j+2] = tc[j] + tc[j+1] - tc[j+3] - tc[j+4]                                      j < w*h - 8
+ *   (*) the reference reads tv/th[w*h .. w*h+3] (beyond its buffers) for the last outputs and stores du/dv[w*h],
+ *   [w*h+1]; here the temporaries read as 0 there and nothing is stored outside: du/dv[w*h-2 .. w*h) are not
+ *   comparable with the reference.
+ *   blob (filter.cpp:507-530): 2-d integral image in int32 (wrapping), then for p = 0 .. w*h-5-5w-1 (flat!)
+ *     f1[p+3+3w] = (int16)(-(I[p+5+5w] - I[p+5] - I[p+5w] + I[p]) + 2 (I[p+4+4w] - I[p+4+w] - I[p+1+4w] + I[p+1+w])
+ *                          + 7 in[p+3+3w])
+ * Elements the reference leaves unwritten are 0. */
+void oracle_matcher_filters(const uint8_t* in, int32_t w, int32_t h, uint8_t* du, uint8_t* dv, int16_t* f1, int16_t* f2)
+{
+    const size_t n = (size_t)w * h;
+    int16_t* tv = (int16_t*)calloc(n + 8, sizeof(int16_t));
+    int16_t* th = (int16_t*)calloc(n + 8, sizeof(int16_t));
+    int16_t* tc = (int16_t*)calloc(n + 8, sizeof(int16_t));
+    uint32_t* I = (uint32_t*)calloc(n, sizeof(uint32_t));
+    memset(du, 0, n); memset(dv, 0, n); memset(f1, 0, 2 * n); memset(f2, 0, 2 * n);
+    for (int32_t v = 2; v < h - 2; v++)
+        for (int32_t u = 0; u < w; u++) {
+            const size_t q = (size_t)v * w + u;
+            const int a = in[q - 2 * (size_t)w], b = in[q - w], c = in[q], d = in[q + w], e = in[q + 2 * (size_t)w];
+            tv[q] = (int16_t)(a + 4 * b + 6 * c + 4 * d + e);
+            th[q] = (int16_t)(a + 2 * b - 2 * d - e);
+            tc[q] = (int16_t)(a + b - d - e);
+        }
+    for (size_t j = 0; j + 2 < n; j++) {
+        const int su = ((tv[j] + 2 * tv[j + 1] - 2 * tv[j + 3] - tv[j + 4]) >> 7) + 128;
+        const int sv = ((th[j] + 4 * th[j + 1] + 6 * th[j + 2] + 4 * th[j + 3] + th[j + 4]) >> 7) + 128;
+        du[j + 2] = (uint8_t)(su < 0 ? 0 : su > 255 ? 255 : su);
+        dv[j + 2] = (uint8_t)(sv < 0 ? 0 : sv > 255 ? 255 : sv);
+        if (j + 8 < n) f2[j + 2] = (int16_t)(tc[j] + tc[j + 1] - tc[j + 3] - tc[j + 4]);
+    }
+    for (int32_t v = 0; v < h; v++) {                       /* integral_image, filter.cpp:48-72 */
+        uint32_t line = 0;
+        for (int32_t u = 0; u < w; u++) {
+            line += in[(size_t)v * w + u];
+            I[(size_t)v * w + u] = (v ? I[(size_t)(v - 1) * w + u] : 0u) + line;
+        }
+    }
+    if (n > 5 + 5 * (size_t)w)
+        for (size_t p = 0; p + 5 + 5 * (size_t)w < n; p++) {
+            const size_t W = (size_t)w;
+            uint32_t r = 0u - (I[p + 5 + 5 * W] - I[p + 5] - I[p + 5 * W] + I[p]);
+            r += 2u * (I[p + 4 + 4 * W] - I[p + 4 + W] - I[p + 1 + 4 * W] + I[p + 1 + W]);
+            r += 7u * in[p + 3 + 3 * W];
+            f1[p + 3 + 3 * W] = (int16_t)(uint16_t)r;
+        }
+    free(tv); free(th); free(tc); free(I);
+}

@@ -211,6 +211,9 @@ size_t fuse_work_ints(int W, int H);
 bool launch_fuse(int W, int H, const elas_b200_view& view, float* const* prev, float* const* cur, int32_t* work,
                  float* points_prev, float* points_curr, int32_t* counts, cudaStream_t s);
 
+// feature filters of libviso2's Matcher (filter.cpp:474-530), one launch
+void launch_matcher_filters(const uint8_t* in, int w, int h, uint8_t* du, uint8_t* dv, int16_t* f1, int16_t* f2, cudaStream_t s);
+
 // number of kernel launches issued through the launchers above (process-wide, relaxed)
 long long launches_issued();
 void count_launch(int n = 1);

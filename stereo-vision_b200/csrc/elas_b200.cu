@@ -1169,6 +1169,63 @@ int32_t elas_b200_fuse(elas_b200_ctx* c, int32_t slot, const elas_b200_view* vie
     return ELAS_B200_OK;
 }
 
+// ---- the feature filters of libviso2's Matcher ------------------------------------------------
+namespace {
+// device scratch of elas_b200_matcher_filters, kept per device and grown on demand (the Matcher calls it per image)
+struct FilterScratch { uint8_t* base = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; };
+std::mutex g_filter_mu;
+std::map<int, FilterScratch> g_filter_scratch;
+}  // namespace
+
+int32_t elas_b200_matcher_filters(int32_t device, const uint8_t* I, int32_t w, int32_t h, uint8_t* I_du, uint8_t* I_dv,
+                                  int16_t* I_f1, int16_t* I_f2, int32_t iters, float* ms_per_pass)
+{
+    if (!I || !I_du || !I_dv || !I_f1 || !I_f2 || w < 16 || w % 16 || h < 6 || iters < 1) return ELAS_B200_E_BAD_ARG;   // filter.cpp:294 asserts w % 16
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); return ELAS_B200_E_NO_DEVICE; }
+    if (device < 0 || device >= n_dev) return ELAS_B200_E_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g_filter_mu);
+    CK(cudaSetDevice(device));
+    const size_t n = (size_t)w * h;
+    // [in n | du n | dv n | f1 2n | f2 2n], every part 256-byte aligned
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = 3 * up(n) + 2 * up(2 * n);
+    FilterScratch& fs = g_filter_scratch[device];
+    if (fs.bytes < need) {
+        if (fs.base) CK(cudaFree(fs.base));
+        fs.base = nullptr; fs.bytes = 0;
+        CK(cudaMalloc(&fs.base, need));
+        fs.bytes = need;
+    }
+    if (!fs.stream) CK(cudaStreamCreateWithFlags(&fs.stream, cudaStreamNonBlocking));
+    uint8_t* d_in = fs.base; uint8_t* d_du = d_in + up(n); uint8_t* d_dv = d_du + up(n);
+    int16_t* d_f1 = reinterpret_cast<int16_t*>(d_dv + up(n)); int16_t* d_f2 = reinterpret_cast<int16_t*>(d_dv + up(n) + up(2 * n));
+    // memory of this device is used in place (it must be 16-byte aligned: the kernels move words)
+    auto on_device = [&](const void* ptr) { return classify(ptr, device).device; };
+    const void* all[5] = {I, I_du, I_dv, I_f1, I_f2};
+    for (const void* ptr : all) if (on_device(ptr) && (reinterpret_cast<uintptr_t>(ptr) & 15)) return ELAS_B200_E_BAD_ARG;
+    const uint8_t* k_in = I;
+    if (!on_device(I)) { CK(cudaMemcpyAsync(d_in, I, n, cudaMemcpyDefault, fs.stream)); k_in = d_in; }
+    uint8_t* k_du = on_device(I_du) ? I_du : d_du; uint8_t* k_dv = on_device(I_dv) ? I_dv : d_dv;
+    int16_t* k_f1 = on_device(I_f1) ? I_f1 : d_f1; int16_t* k_f2 = on_device(I_f2) ? I_f2 : d_f2;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms_per_pass) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, fs.stream)); }
+    for (int i = 0; i < iters; i++) launch_matcher_filters(k_in, w, h, k_du, k_dv, k_f1, k_f2, fs.stream);
+    CK(cudaGetLastError());
+    if (ms_per_pass) CK(cudaEventRecord(e1, fs.stream));
+    if (k_du != I_du) CK(cudaMemcpyAsync(I_du, k_du, n, cudaMemcpyDefault, fs.stream));
+    if (k_dv != I_dv) CK(cudaMemcpyAsync(I_dv, k_dv, n, cudaMemcpyDefault, fs.stream));
+    if (k_f1 != I_f1) CK(cudaMemcpyAsync(I_f1, k_f1, 2 * n, cudaMemcpyDefault, fs.stream));
+    if (k_f2 != I_f2) CK(cudaMemcpyAsync(I_f2, k_f2, 2 * n, cudaMemcpyDefault, fs.stream));
+    CK(cudaStreamSynchronize(fs.stream));
+    if (ms_per_pass) {
+        CK(cudaEventElapsedTime(ms_per_pass, e0, e1));
+        *ms_per_pass /= iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return ELAS_B200_OK;
+}
+
 int32_t elas_b200_time_view(elas_b200_ctx* c, int32_t slot, int32_t iters, float ms_out[2])
 {
     if (!c || slot < 0 || slot >= (int)c->groups.size() || iters < 1 || !ms_out || c->p.subsampling) return ELAS_B200_E_BAD_ARG;

@@ -60,7 +60,7 @@ EXPORTS = [
     "elas_b200_default_params", "elas_b200_stereomapper_params", "elas_b200_process",
     "elas_b200_create", "elas_b200_create_ex", "elas_b200_create_grouped", "elas_b200_frames_per_group",
     "elas_b200_mesh_on_device", "elas_b200_time_matching_ex", "elas_b200_destroy", "elas_b200_multi_create",
-    "elas_b200_fuse", "elas_b200_multi_destroy", "elas_b200_multi_device_count", "elas_b200_multi_context", "elas_b200_multi_process_batch", "elas_b200_process_ctx", "elas_b200_process_batch",
+    "elas_b200_fuse", "elas_b200_matcher_filters", "elas_b200_multi_destroy", "elas_b200_multi_device_count", "elas_b200_multi_context", "elas_b200_multi_process_batch", "elas_b200_process_ctx", "elas_b200_process_batch",
     "elas_b200_process_batch_device", "elas_b200_stage_capture", "elas_b200_stage_bytes",
     "elas_b200_stage_read", "elas_b200_host_stage", "elas_b200_launch_count",
     "elas_b200_stage_timing", "elas_b200_stage_times", "elas_b200_host_times", "elas_b200_time_matching",
@@ -125,6 +125,7 @@ def load_library():
     lib.elas_b200_time_view.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     lib.elas_b200_fuse.argtypes = [C.c_void_p, C.c_int32, C.POINTER(View), C.POINTER(Map3D), C.POINTER(Map3D),
                                    C.c_void_p, i32p, C.c_void_p, i32p]
+    lib.elas_b200_matcher_filters.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.POINTER(C.c_float)]
     lib.elas_b200_version.restype = C.c_char_p
     lib.elas_b200_device_count.restype = C.c_int32
     _lib = lib
@@ -394,3 +395,19 @@ class ElasB200Multi:
         if rc < 0:
             raise RuntimeError(f"elas_b200_multi_process_batch failed with {rc}")
         return list(status), D1, D2
+
+
+def matcher_filters(I, device=0, iters=1, timing=False):
+    """The feature filters of libviso2's Matcher (filter::sobel5x5 / blob5x5 / checkerboard5x5 as called at
+    matcher.cpp:799-801) on a uint8 image [h][bytes_per_line]; returns (du, dv, f1, f2) [+ ms per pass]."""
+    lib = load_library()
+    I = np.ascontiguousarray(I, np.uint8)
+    h, w = I.shape
+    du, dv = np.empty((h, w), np.uint8), np.empty((h, w), np.uint8)
+    f1, f2 = np.empty((h, w), np.int16), np.empty((h, w), np.int16)
+    ms = C.c_float(0)
+    rc = lib.elas_b200_matcher_filters(device, I.ctypes.data, w, h, du.ctypes.data, dv.ctypes.data, f1.ctypes.data,
+                                       f2.ctypes.data, iters, C.byref(ms) if timing else None)
+    if rc != 0:
+        raise RuntimeError(f"elas_b200_matcher_filters failed with {rc}")
+    return (du, dv, f1, f2, ms.value) if timing else (du, dv, f1, f2)
