@@ -779,8 +779,13 @@ struct CacheKey {
     elas_b200_params p;
     bool operator<(const CacheKey& o) const { return std::memcmp(this, &o, sizeof *this) < 0; }
 };
+// at most kCacheMax contexts stay cached (each pins a frame group of device memory and a worker thread); the least
+// recently used one is destroyed when another (device, size, parameter block) combination shows up
+constexpr size_t kCacheMax = 4;
+struct CacheEntry { elas_b200_ctx* ctx; uint64_t last_use; };
 std::mutex g_cache_mu;
-std::map<CacheKey, elas_b200_ctx*> g_cache;
+std::map<CacheKey, CacheEntry> g_cache;
+uint64_t g_cache_tick = 0;
 
 }  // namespace
 
@@ -1058,9 +1063,18 @@ int32_t elas_b200_process(const elas_b200_params* p, const uint8_t* I1, const ui
     std::lock_guard<std::mutex> lk(g_cache_mu);          // one call at a time, from any thread
     auto it = g_cache.find(key);
     if (it == g_cache.end()) {
+        if (g_cache.size() >= kCacheMax) {
+            auto victim = g_cache.begin();
+            for (auto j = g_cache.begin(); j != g_cache.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+            elas_b200_destroy(victim->second.ctx);
+            g_cache.erase(victim);
+        }
         if (int32_t rc = elas_b200_create(&c, device, p, dims[0], dims[1], 1)) return rc;
-        g_cache[key] = c;
-    } else c = it->second;
+        g_cache[key] = CacheEntry{c, ++g_cache_tick};
+    } else {
+        c = it->second.ctx;
+        it->second.last_use = ++g_cache_tick;
+    }
     return elas_b200_process_ctx(c, 0, I1, I2, D1, D2, dims[2]);
 }
 

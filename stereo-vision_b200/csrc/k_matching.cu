@@ -328,8 +328,11 @@ __device__ __forceinline__ void match_pair(const MatchArgs& a, const SegCtx& r, 
 
 // ROWS = image rows per CTA: 2 = a thread matches (u, v0) and (u, v0+1) together (needs an even grid_size:
 // both lie in one grid cell); 1 = one row per CTA (odd grid sizes; subsampling, where only even rows exist)
+#ifndef K7_MINBLOCKS
+#define K7_MINBLOCKS 5
+#endif
 template <int RADIUS, int ROWS, bool SUB>     // plane_radius (elas.cpp:993); 0 = generic
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, K7_MINBLOCKS)
 k_matching(const __grid_constant__ MatchArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];

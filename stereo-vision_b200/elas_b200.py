@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libelas_b200.so")
+LIB_PATH = os.environ.get("ELAS_B200_LIB") or os.path.join(HERE, "libelas_b200.so")     # same variable as the drop-in elas.cpp
 
 E_FEW_SUPPORT = 1
 

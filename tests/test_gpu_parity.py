@@ -400,3 +400,22 @@ def test_multi_device_entry_shards_frames(oracle):
     assert status == [0] * 11
     for i in range(11):
         assert bits_equal(D1[i], want[i % 3][1]) and bits_equal(D2[i], want[i % 3][2]), f"frame {i}"
+
+
+def test_drop_in_call_cache_evicts_and_recreates(oracle):
+    """elas_b200_process keeps at most four cached contexts (one per device / size / parameter block); a seventh
+    combination evicts the least recently used one, and coming back to an evicted combination builds it again."""
+    sizes = [(160 + 16 * k, 96 + 8 * k) for k in range(6)]
+    first = None
+    for rnd in range(2):
+        for W, H in sizes:
+            L, R, _ = synth.synthetic_pair(W, H, 31, seed=W)
+            rc, D1, D2 = elas_b200.process(L, R, elas_b200.stereomapper(31))
+            assert rc == 0
+            if (W, H) == sizes[0]:
+                if first is None:
+                    _, O1, O2 = oracle.process(L, R, checkers.stereomapper(31))
+                    assert np.array_equal(D1.view(np.uint32), O1.view(np.uint32)) and np.array_equal(D2.view(np.uint32), O2.view(np.uint32))
+                    first = D1
+                else:
+                    assert np.array_equal(D1.view(np.uint32), first.view(np.uint32))
