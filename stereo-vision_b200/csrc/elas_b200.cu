@@ -115,6 +115,7 @@ struct Group {
     float* last_D1 = nullptr;                  // frame 0's final left map of the last chain, if it lives in the group's buffers
     int map_tag = 0;                           // frame tag of the triangle-id map entries (k_grid_raster.cu)
     int scratch_phase = 0;                     // which of the two grid scatter buffers this chain uses
+    int scratch_dirty_lo[2] = {0, 0}, scratch_dirty_hi[2] = {0, 0};   // frames [lo, hi) of a scatter buffer may hold marks of an earlier chain
     bool tables_valid = false;
     // introspection (single-frame calls)
     bool capture = false;
@@ -495,9 +496,21 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     }
     // ---- planes, candidate grid, triangle-id maps, dense matching ------------------------------------------------------------
     const size_t scratch_words = 2 * (size_t)g.gw * g.gh * g.gwords;
-    uint32_t* scratch_cur = s.d_grid_scratch + (size_t)s.scratch_phase * scratch_words;
-    uint32_t* scratch_next = s.d_grid_scratch + (size_t)(1 - s.scratch_phase) * scratch_words;
+    const int ph = s.scratch_phase;
+    uint32_t* scratch_cur = s.d_grid_scratch + (size_t)ph * scratch_words;
+    uint32_t* scratch_next = s.d_grid_scratch + (size_t)(1 - ph) * scratch_words;
     s.scratch_phase ^= 1;
+    // A chain zeroes the OTHER buffer for its own n frames only.  After a short chain (the tail of a batch) the
+    // frames beyond it still hold the marks of the chain before: clear them before a longer chain reads them.
+    if (s.scratch_dirty_lo[ph] < std::min(s.scratch_dirty_hi[ph], n)) {
+        const int lo = s.scratch_dirty_lo[ph], hi = s.scratch_dirty_hi[ph];
+        CK(cudaMemset2DAsync(scratch_cur + (size_t)lo * gs.scratch, gs.scratch * 4, 0, scratch_words * 4, (size_t)(hi - lo), st));
+        s.scratch_dirty_lo[ph] = s.scratch_dirty_hi[ph] = 0;
+    }
+    s.scratch_dirty_hi[ph] = std::max(s.scratch_dirty_hi[ph], n);            // this chain scatters into frames [0, n) ...
+    s.scratch_dirty_lo[ph] = 0;
+    if (s.scratch_dirty_hi[1 - ph] <= n) s.scratch_dirty_lo[1 - ph] = s.scratch_dirty_hi[1 - ph] = 0;      // ... and zeroes them in the other buffer
+    else s.scratch_dirty_lo[1 - ph] = std::max(s.scratch_dirty_lo[1 - ph], n);
     if (++s.map_tag > c->map_tag_max) {
         // tag space used up: start over from cleared maps
         for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s.d_map[k], 0xFF, (size_t)s.cap * gs.map * 4, st));
@@ -859,7 +872,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
     c->g = make_geom(*p, width, height);
     const FrameGeom& g = c->g;
     // frames per launch chain: small frames are batched so that every kernel spans several waves of CTAs
-    if (frames_per_group == 0) frames_per_group = (int)std::max<long long>(1, std::min<long long>(kMaxGroupFrames, 4000000ll / ((long long)width * height)));
+    if (frames_per_group == 0) frames_per_group = (int)std::max<long long>(1, std::min<long long>(kMaxGroupFrames, 8500000ll / ((long long)width * height)));
     frames_per_group = std::min(frames_per_group, (int)kMaxGroupFrames);
     c->support_cap = g.Wc * g.Hc + 6;
     c->tri_cap = 2 * c->support_cap + 8;

@@ -419,3 +419,36 @@ def test_drop_in_call_cache_evicts_and_recreates(oracle):
                     first = D1
                 else:
                     assert np.array_equal(D1.view(np.uint32), first.view(np.uint32))
+
+
+def test_frame_groups_at_hd(oracle):
+    """1920x1080 d_max 128: four frames per launch chain (the default group size at this frame size), the triangulations
+    of a chain working side by side in the global scratch area; six frames = one full and one partial chain."""
+    W, H, dmax = 1920, 1080, 128
+    p = checkers.stereomapper(dmax)
+    pairs = [synth.synthetic_pair(W, H, dmax, s)[:2] for s in (60, 61)]
+    e = elas_b200.ElasB200(as_product_params(p), W, H, n_slots=1, n_workers=1, frames_per_group=0)
+    try:
+        assert e.frames_per_group == 4 and e.mesh_on_device
+        status, D1, D2 = e.process_batch([pairs[i % 2][0] for i in range(6)], [pairs[i % 2][1] for i in range(6)])
+    finally:
+        e.close()
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    for i in range(6):
+        assert status[i] == 0 and bits_equal(D1[i], want[i % 2][1]) and bits_equal(D2[i], want[i % 2][2]), f"frame {i}"
+
+
+def test_full_chain_after_a_short_chain(oracle):
+    """One group of four frames: chains of 4, 3 and 4 frames.  A chain leaves the grid scatter planes of its own
+    frames zeroed for the chain after it; frame 3 of the third chain must not see what the first chain left there."""
+    p = checkers.stereomapper(95)
+    pairs = [synth.synthetic_pair(416, 200, 95, s)[:2] for s in (71, 72, 73, 74)]
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    e = elas_b200.ElasB200(as_product_params(p), 416, 200, n_slots=1, n_workers=1, frames_per_group=4)
+    try:
+        for n in (4, 3, 4, 1, 2, 4):
+            status, D1, D2 = e.process_batch([pairs[i][0] for i in range(n)], [pairs[i][1] for i in range(n)])
+            for i in range(n):
+                assert status[i] == 0 and bits_equal(D1[i], want[i][1]) and bits_equal(D2[i], want[i][2]), f"chain of {n}, frame {i}"
+    finally:
+        e.close()

@@ -1,6 +1,6 @@
 """K7 timing as the bench measures it (one launch per frame group, CUDA events, L2 flushed) at K (8 frames per launch)
 and 4096x2160 (1 frame), plus a checksum of the final maps so that kernel variants can be compared for identical
-results.  Usage: [ELAS_B200_LIB=path/libelas_b200.so] python tools/k7_group_time.py [K|4K|both]"""
+results.  Usage: [ELAS_B200_LIB=path/libelas_b200.so] python tools/k7_group_time.py [K|HD|4K|both]"""
 import os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200"))
@@ -9,7 +9,7 @@ import elas_b200, synth
 def bmatch(w, h, dmax, gs=20):
     return 72 * w * h + 8 * (-(-w // gs)) * (-(-h // gs)) * (dmax + 2)
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
-for tag, (W, H, D) in (("K", (1242, 375, 255)), ("4K", (4096, 2160, 256))):
+for tag, (W, H, D) in (("K", (1242, 375, 255)), ("HD", (1920, 1080, 128)), ("4K", (4096, 2160, 256))):
     if which not in (tag, "both"):
         continue
     e = elas_b200.ElasB200(elas_b200.stereomapper(D), W, H, n_slots=1, frames_per_group=0)

@@ -18,3 +18,33 @@ for name, p, (W, H, D) in (("stereomapper", elas_b200.stereomapper(63), (320, 12
     e.close()
     same = all(np.array_equal(b.view(np.uint32), D1.view(np.uint32)) for b in B1)
     print(name, "rc", rc, "valid", int((D1 >= 0).sum()), "batch==single", same, flush=True)
+
+# map fusion (short and long lists) and the Matcher feature filters
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from view_cases import fusion_sequence
+for name in ("tiny", "backwards"):
+    seq = fusion_sequence(name, frames=2)
+    h, w = seq[0][1].shape
+    e = elas_b200.ElasB200(elas_b200.stereomapper(63), w, h, n_slots=1)
+    prev = None
+    for I1, D1, view, H in seq:
+        cur = e.reproject(view, H, I1=I1, D1=D1)
+        fused = e.fuse(view, H, cur, prev)
+        prev = fused[0]
+    e.close()
+    print("fusion", name, "points", len(fused[2]), len(fused[3]), flush=True)
+w, h = 96, 64
+e = elas_b200.ElasB200(elas_b200.stereomapper(63), w, h, n_slots=1)
+view = np.array([300.0, 48.0, 32.0, 0.54, 30.0, 1.2], np.float32)
+Hm = np.hstack([np.eye(3), np.zeros((3, 1))])
+base = list(e.reproject(view, Hm, I1=np.full((h, w), 9, np.uint8), D1=np.full((h, w), 20.0, np.float32)))
+prev = [a.copy() for a in base]
+for k in (2, 3, 4):
+    prev[k][:] = base[k][30, 40]           # every previous point on one pixel: the long-list path
+fused = e.fuse(view, Hm, base, prev)
+e.close()
+print("fusion one-pixel", len(fused[2]), len(fused[3]), flush=True)
+rng = np.random.default_rng(0)
+for shape in ((6, 16), (53, 112), (375, 1248)):
+    out = elas_b200.matcher_filters(rng.integers(0, 256, shape, dtype=np.uint8))
+    print("filters", shape, int(out[2].astype(np.int64).sum()), flush=True)
