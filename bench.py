@@ -363,6 +363,10 @@ def main():
     oracle_mismatch, oracle_checked = (int(x) for x in sharding.sum_over_ranks([oracle_mismatch, oracle_checked], dev))
 
     ms_dev_max, ms_host_max, ms_left_max = sharding.max_over_ranks([ms_dev, ms_host, ms_left], dev)
+    narrow_mode = int(os.environ.get("ELAS_B200_NARROW_D2", "2"))
+    d2_bytes = 4 * W * H if narrow_mode == 0 else 2 * W * H if (narrow_mode == 1 or DMAX > 255) else \
+        ((W * H + 15) // 16 * 16 + H * ((W + 31) // 32) * 4)
+    d2h_bytes_per_pair = 4 * W * H + d2_bytes
 
     # roofline of the matching kernel: isolated launches cycling over all slots' tables (their
     # combined descriptors exceed L2), CUDA events on the launching stream, L2 flushed first
@@ -464,11 +468,12 @@ def main():
             "e2e": {"value": round(total_pairs / (ms_host_max * 1e-3), 2), "unit": "pairs/s",
                     # whole job, like `value`
                     "h2d_bytes_per_step": world * B * 2 * W * H,
-                    # D1 as float32; D2 (final after the L/R check: integers or -10) crosses as int16
-                    # and is widened into the caller's float map by the library (elas_b200.cu)
-                    "d2h_bytes_per_step": world * B * W * H * (4 + 2),
+                    # D1 as float32; D2 (final after the L/R check: integers or -10) crosses narrowed -- one byte per
+                    # pixel plus a validity bit per pixel when disp_max <= 255, int16 otherwise -- and is widened into the
+                    # caller's float map by the library (elas_b200.cu)
+                    "d2h_bytes_per_step": world * B * d2h_bytes_per_pair,
                     "ms_per_step": round(ms_host_max / args.steps, 4),
-                    "bound": "PCIe device->host: 2.79 MB per pair (D1 float32 + D2 int16)"},
+                    "bound": f"PCIe device->host: {d2h_bytes_per_pair / 1e6:.2f} MB per pair (D1 float32 + D2 narrowed)"},
             "e2e_left_map_only": {"value": round(world * B / (ms_left_max * 1e-3), 2), "unit": "pairs/s",
                                   "d2h_bytes_per_step": world * B * W * H * 4,
                                   "note": "opt-in D2 == NULL: only the left map returns (what stereomapper reads, stereothread.cpp:116-147)"},

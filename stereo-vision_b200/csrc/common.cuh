@@ -159,10 +159,13 @@ void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float*
 size_t segment_node_ints(const FrameGeom& g);
 void launch_segments(const FrameGeom& g, const elas_b200_params& p, float* D, int32_t* label, int32_t* nodes,
                      size_t D_stride, size_t nodes_stride, int n_frames, cudaStream_t s, bool apply = true);
-// K8 with both rows staged in shared memory
+// K8 with both rows staged in shared memory.  The checked right map may leave narrowed for the copy to the host
+// (mode 0: not at all; see narrow_d2_layout in k_postproc.cu)
+struct NarrowD2 { void* base; int mode; int mask_words_per_row; size_t stride_bytes, mask_offset, bytes; };
+NarrowD2 narrow_d2_layout(const FrameGeom& g, int mode, void* base, size_t stride_bytes);
 bool lr_rows_fusable(const FrameGeom& g);
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, const OutTable& O2, int16_t* O2_i16, size_t D_stride, int n_frames, cudaStream_t s);
+                    float* O1, const OutTable& O2, const NarrowD2& narrow, size_t D_stride, int n_frames, cudaStream_t s);
 // K9 apply + K10 + K11 in one tiled kernel (ipol_gap_width <= 3, no add_corners); out must not alias in
 bool post_fusable(const elas_b200_params& p);
 void launch_post_fused(const FrameGeom& g, const elas_b200_params& p, const float* in, const int32_t* label,

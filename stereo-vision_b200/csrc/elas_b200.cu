@@ -110,6 +110,7 @@ struct Group {
     std::vector<FrameIO> io;
     std::vector<float*> expand_D2;             // caller's D2 awaiting widening at finish (null: nothing to do)
     int last_n = 0;                            // frames of the last completed chain (elas_b200_time_matching)
+    int d2_mode = 0;                           // how the chain in flight narrowed D2 for the copy out (NarrowD2::mode)
     float* d_view = nullptr;                   // colour map / back-projection outputs (5 planes), allocated on first use
     float* d_fuse = nullptr;                   // map fusion: previous + current map (10 planes), two point lists, work area
     float* last_D1 = nullptr;                  // frame 0's final left map of the last chain, if it lives in the group's buffers
@@ -138,7 +139,7 @@ struct elas_b200_ctx {
     void* d_flush = nullptr;                 // > L2-sized buffer for elas_b200_time_matching
     size_t flush_bytes = 0;
     bool timing = false;
-    bool narrow_d2 = true;                   // host output: D2 crosses PCIe as int16 when that is exact (ELAS_B200_NARROW_D2=0 disables)
+    int narrow_d2 = 2;                       // host output: D2 crosses PCIe narrowed when that is exact: 2 = u8 + validity bits where disp_max <= 255, else int16; 1 = int16; 0 = float32 (ELAS_B200_NARROW_D2)
     long long launches_at_create = 0;
     // host-side wall time, summed over all groups (nanoseconds)
     std::atomic<long long> ns_submit{0}, ns_host{0}, ns_wait{0}, ns_finish{0}, frames{0};
@@ -367,6 +368,39 @@ void widen_i16_to_f32(const int16_t* src, float* dst, size_t n)
     for (; i < n; i++) dst[i] = (float)src[i];
 }
 
+// u8 values + one validity bit per pixel (rows of 32-bit words) -> float, invalid = -10 (NarrowD2 mode 2)
+void widen_u8_mask_to_f32(const uint8_t* vals, const uint32_t* mask, int words_per_row, float* dst, int Dw, int Dh)
+{
+    alignas(16) static const uint32_t lane_mask[16][4] = {
+        {0, 0, 0, 0}, {~0u, 0, 0, 0}, {0, ~0u, 0, 0}, {~0u, ~0u, 0, 0}, {0, 0, ~0u, 0}, {~0u, 0, ~0u, 0}, {0, ~0u, ~0u, 0}, {~0u, ~0u, ~0u, 0},
+        {0, 0, 0, ~0u}, {~0u, 0, 0, ~0u}, {0, ~0u, 0, ~0u}, {~0u, ~0u, 0, ~0u}, {0, 0, ~0u, ~0u}, {~0u, 0, ~0u, ~0u}, {0, ~0u, ~0u, ~0u}, {~0u, ~0u, ~0u, ~0u}};
+    const __m128 invalid = _mm_set1_ps((float)kInvalid);
+    const __m128i zero = _mm_setzero_si128();
+    for (int v = 0; v < Dh; v++) {
+        const uint8_t* src = vals + (size_t)v * Dw;
+        const uint32_t* m = mask + (size_t)v * words_per_row;
+        float* d = dst + (size_t)v * Dw;
+        auto bit = [&](int u) { return (m[u >> 5] >> (u & 31)) & 1u; };
+        int u = 0;
+        for (; u < Dw && (reinterpret_cast<uintptr_t>(d + u) & 15); u++) d[u] = bit(u) ? (float)src[u] : (float)kInvalid;
+        for (; u + 16 <= Dw; u += 16) {
+            // 16 validity bits starting at bit u of the row (they may straddle two words)
+            const int w = u >> 5, sh = u & 31;
+            uint32_t bits = m[w] >> sh;
+            if (sh > 16) bits |= m[w + 1] << (32 - sh);          // w + 1 < words_per_row: u + 16 <= Dw lies beyond word w
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + u));
+            const __m128i lo = _mm_unpacklo_epi8(b, zero), hi = _mm_unpackhi_epi8(b, zero);
+            const __m128i q[4] = {_mm_unpacklo_epi16(lo, zero), _mm_unpackhi_epi16(lo, zero), _mm_unpacklo_epi16(hi, zero), _mm_unpackhi_epi16(hi, zero)};
+            for (int k = 0; k < 4; k++) {
+                const __m128 keep = _mm_load_ps(reinterpret_cast<const float*>(lane_mask[(bits >> (4 * k)) & 15]));
+                _mm_stream_ps(d + u + 4 * k, _mm_or_ps(_mm_and_ps(keep, _mm_cvtepi32_ps(q[k])), _mm_andnot_ps(keep, invalid)));
+            }
+        }
+        for (; u < Dw; u++) d[u] = bit(u) ? (float)src[u] : (float)kInvalid;
+    }
+    _mm_sfence();
+}
+
 MatchBuffers match_buffers(const elas_b200_ctx* c, const Group& s)
 {
     MatchBuffers b{};
@@ -559,10 +593,14 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         }
     // Copy path, D2 final after the L/R check: its values are raw integer disparities or -10, so it crosses
     // PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.
-    const bool d2_i16 = all_host && !any_direct_d2 && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
+    // ... or, when every disparity fits a byte, as u8 plus one validity bit per pixel (1.125 bytes per pixel)
+    const bool d2_narrow = all_host && !any_direct_d2 && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
+    const int d2_mode = !d2_narrow ? 0 : (p.disp_max <= 255 && c->narrow_d2 > 1) ? 2 : 1;
+    const NarrowD2 narrow = narrow_d2_layout(g, d2_mode, s.d_D2_i16, gs.D * 2);
+    s.d2_mode = d2_mode;
     OutTable lr_d2 = out_table(s.d_D[1], gs.D, n);
     if (n_post == 1) for (int f = 0; f < n; f++) if (direct[1][f]) lr_d2.p[f] = s.io[f].D2;
-    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, d2_i16 ? s.d_D2_i16 : nullptr, gs.D, n, st);
+    if (rows_fused) launch_lr_rows(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, narrow, gs.D, n, st);
     else launch_lr_check(g, p, s.d_raw[0], s.d_raw[1], s.d_D[0], lr_d2, gs.D, n, st);       // elas.cpp:116
     mark(c, s, "lr_check");
     if (s.capture) {
@@ -642,8 +680,8 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         for (int k = 0; k < 2; k++) {
             float* user = k ? s.io[f].D2 : s.io[f].D1;
             if (direct[k][f] || !user) continue;
-            if (k == 1 && d2_i16) {
-                CK(cudaMemcpyAsync(s.h_D2_i16 + (size_t)f * gs.D, s.d_D2_i16 + (size_t)f * gs.D, ND * 2, cudaMemcpyDeviceToHost, out_stream));
+            if (k == 1 && d2_mode) {
+                CK(cudaMemcpyAsync(s.h_D2_i16 + (size_t)f * gs.D, s.d_D2_i16 + (size_t)f * gs.D, narrow.bytes, cudaMemcpyDeviceToHost, out_stream));
                 s.expand_D2[f] = user;
             } else {
                 CK(cudaMemcpyAsync(user, final_map[k].p[f], ND * 4, cudaMemcpyDefault, out_stream));
@@ -670,7 +708,13 @@ int32_t finish_group(elas_b200_ctx* c, Group& s, int32_t* status_out)
         const FrameHeader& h = s.h_hdr[f];
         status_out[f] = h.status < 0 ? h.status : h.n_support < 3 ? ELAS_B200_E_FEW_SUPPORT : ELAS_B200_OK;
         if (s.expand_D2[f]) {
-            widen_i16_to_f32(s.h_D2_i16 + (size_t)f * c->st.D, s.expand_D2[f], ND);
+            const int16_t* landed = s.h_D2_i16 + (size_t)f * c->st.D;
+            if (s.d2_mode == 2) {
+                const NarrowD2 lay = narrow_d2_layout(c->g, 2, nullptr, 0);
+                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(landed);
+                widen_u8_mask_to_f32(bytes, reinterpret_cast<const uint32_t*>(bytes + lay.mask_offset), lay.mask_words_per_row,
+                                     s.expand_D2[f], c->g.Dw, c->g.Dh);
+            } else widen_i16_to_f32(landed, s.expand_D2[f], ND);
             s.expand_D2[f] = nullptr;
         }
     }
@@ -911,7 +955,7 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
     CK(cudaMemcpy(c->d_prior, prior.data(), prior.size() * 4, cudaMemcpyHostToDevice));
     c->prior_host = prior;
     c->launches_at_create = launches_issued();
-    if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ELAS_B200_NARROW_D2")) c->narrow_d2 = std::max(0, std::min(2, std::atoi(e)));
     {
         GroupStrides& st = c->st;
         const size_t cells = (size_t)g.gw * g.gh;

@@ -38,35 +38,47 @@ __global__ void k_lr_check(int Dw, int Dh, int subsampling, float lr_threshold,
 
 // K8 with the rows staged in shared memory: a CTA owns one row of both maps.  The L/R check of a pixel only reads
 // the other map within the same row (elas.cpp:1164-1197), at a data-dependent column: from shared memory those
-// gathers cost nothing, from global memory they are uncoalesced.  The checked right map optionally leaves as int16.
+// gathers cost nothing, from global memory they are uncoalesced.  The checked right map optionally leaves NARROWED for
+// the trip across PCIe (exact: it holds raw integer disparities or -10): as int16, or -- disp_max <= 255 -- as one
+// byte per pixel plus a validity bit per pixel (rows of 32-bit ballot words), 1.125 instead of 4 bytes per pixel.
 __global__ void __launch_bounds__(256)
 k_lr_rows(int Dw, int subsampling, float lr_threshold,
           const float* __restrict__ D1, const float* __restrict__ D2,
-          float* __restrict__ O1, OutTable O2_tab,
-          int16_t* __restrict__ O2_i16,      // optional: O2 narrowed (exact: raw integer disparities or -10)
-          size_t D_stride)
+          float* __restrict__ O1, OutTable O2_tab, NarrowD2 narrow, size_t D_stride)
 {
     extern __shared__ float s_rows[];          // [2][Dw]: raw D1 row, raw D2 row
     float* r1 = s_rows; float* r2 = s_rows + Dw;
     const int v = blockIdx.x;
     // blockIdx.y = frame of the group
     D1 += blockIdx.y * D_stride; D2 += blockIdx.y * D_stride; O1 += blockIdx.y * D_stride;
-    if (O2_i16) O2_i16 += blockIdx.y * D_stride;
+    uint8_t* nbase = narrow.mode ? static_cast<uint8_t*>(narrow.base) + blockIdx.y * narrow.stride_bytes : nullptr;
+    int16_t* __restrict__ O2_i16 = reinterpret_cast<int16_t*>(nbase);
+    uint32_t* __restrict__ O2_mask = reinterpret_cast<uint32_t*>(nbase + narrow.mask_offset) + (size_t)v * narrow.mask_words_per_row;
     float* __restrict__ O2 = O2_tab.p[blockIdx.y];
     const size_t row = (size_t)v * Dw;
     for (int u = threadIdx.x; u < Dw; u += 256) { r1[u] = D1[row + u]; r2[u] = D2[row + u]; }
     __syncthreads();
-    for (int u = threadIdx.x; u < Dw; u += 256) {
-        const float d1 = r1[u], d2 = r2[u];
-        const float w1 = subsampling ? __fsub_rn((float)u, __fmul_rn(d1, 0.5f)) : __fsub_rn((float)u, d1);  // :1152-1161
-        const float w2 = subsampling ? __fadd_rn((float)u, __fmul_rn(d2, 0.5f)) : __fadd_rn((float)u, d2);
+    for (int u0 = 0; u0 < Dw; u0 += 256) {                 // whole warps stay in the loop (the validity ballot)
+        const int u = u0 + threadIdx.x;
+        const bool in = u < Dw;
         float o1 = (float)kInvalid, o2 = (float)kInvalid;
-        if (d1 >= 0.f && w1 >= 0.f && w1 < (float)Dw)                                                       // :1164-1179
-            if (!(fabsf(__fsub_rn(r2[(int)w1], d1)) > lr_threshold)) o1 = d1;
-        if (d2 >= 0.f && w2 >= 0.f && w2 < (float)Dw)                                                       // :1182-1197
-            if (!(fabsf(__fsub_rn(r1[(int)w2], d2)) > lr_threshold)) o2 = d2;
-        O1[row + u] = o1;
-        if (O2_i16) O2_i16[row + u] = (int16_t)o2; else O2[row + u] = o2;
+        if (in) {
+            const float d1 = r1[u], d2 = r2[u];
+            const float w1 = subsampling ? __fsub_rn((float)u, __fmul_rn(d1, 0.5f)) : __fsub_rn((float)u, d1);  // :1152-1161
+            const float w2 = subsampling ? __fadd_rn((float)u, __fmul_rn(d2, 0.5f)) : __fadd_rn((float)u, d2);
+            if (d1 >= 0.f && w1 >= 0.f && w1 < (float)Dw)                                                       // :1164-1179
+                if (!(fabsf(__fsub_rn(r2[(int)w1], d1)) > lr_threshold)) o1 = d1;
+            if (d2 >= 0.f && w2 >= 0.f && w2 < (float)Dw)                                                       // :1182-1197
+                if (!(fabsf(__fsub_rn(r1[(int)w2], d2)) > lr_threshold)) o2 = d2;
+            O1[row + u] = o1;
+        }
+        if (narrow.mode == 2) {
+            const unsigned valid = __ballot_sync(0xffffffffu, in && o2 >= 0.f);
+            if (in) nbase[row + u] = o2 >= 0.f ? (uint8_t)o2 : (uint8_t)0;
+            if ((threadIdx.x & 31) == 0 && in) O2_mask[u >> 5] = valid;
+        } else if (in) {
+            if (narrow.mode == 1) O2_i16[row + u] = (int16_t)o2; else O2[row + u] = o2;
+        }
     }
 }
 
@@ -653,14 +665,27 @@ void launch_lr_check(const FrameGeom& g, const elas_b200_params& p, const float*
 
 bool lr_rows_fusable(const FrameGeom& g) { return (size_t)g.Dw * 8 <= 160 * 1024; }
 
+// the narrowed right map of one frame: mode 1 = int16 [Dh][Dw]; mode 2 = u8 [Dh][Dw], then (16-byte aligned) one validity
+// bit per pixel as [Dh][mask_words_per_row] ballot words
+NarrowD2 narrow_d2_layout(const FrameGeom& g, int mode, void* base, size_t stride_bytes)
+{
+    NarrowD2 n{};
+    n.base = base; n.mode = mode; n.stride_bytes = stride_bytes;
+    const size_t nd = (size_t)g.Dw * g.Dh;
+    n.mask_words_per_row = (g.Dw + 31) / 32;
+    n.mask_offset = (nd + 15) & ~(size_t)15;
+    n.bytes = mode == 1 ? nd * 2 : mode == 2 ? n.mask_offset + (size_t)g.Dh * n.mask_words_per_row * 4 : 0;
+    return n;
+}
+
 // K8 for both maps, rows staged in shared memory
 void launch_lr_rows(const FrameGeom& g, const elas_b200_params& p, const float* D1, const float* D2,
-                    float* O1, const OutTable& O2, int16_t* O2_i16, size_t D_stride, int n_frames, cudaStream_t s)
+                    float* O1, const OutTable& O2, const NarrowD2& narrow, size_t D_stride, int n_frames, cudaStream_t s)
 {
     const size_t smem = (size_t)g.Dw * 8;
     static unsigned long long optin = 0;
     if (ensure_dynamic_smem(k_lr_rows, 160 * 1024, &optin) != cudaSuccess) return;
-    k_lr_rows<<<dim3(g.Dh, n_frames), 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, D1, D2, O1, O2, O2_i16, D_stride);
+    k_lr_rows<<<dim3(g.Dh, n_frames), 256, smem, s>>>(g.Dw, p.subsampling, (float)p.lr_threshold, D1, D2, O1, O2, narrow, D_stride);
     count_launch();
 }
 

@@ -452,3 +452,57 @@ def test_full_chain_after_a_short_chain(oracle):
                 assert status[i] == 0 and bits_equal(D1[i], want[i][1]) and bits_equal(D2[i], want[i][2]), f"chain of {n}, frame {i}"
     finally:
         e.close()
+
+
+def _shifted_pair(W, H, d_const, seed):
+    """A textured pair whose lower half has the constant disparity d_const (up to disp_max itself) and whose upper
+    half has disparity 7: left(u) = texture(u - d)."""
+    rng = np.random.default_rng(seed)
+    tex = rng.integers(0, 256, (H, W + d_const), dtype=np.uint8)
+    tex = (0.5 * tex + 0.5 * np.repeat(np.repeat(rng.integers(0, 256, (H // 4 + 1, (W + d_const) // 4 + 1)), 4, 0), 4, 1)[:H, :W + d_const]).astype(np.uint8)
+    R = tex[:, d_const:d_const + W].copy()
+    L = np.empty_like(R)
+    L[: H // 2] = tex[: H // 2, d_const - 7:d_const - 7 + W]
+    L[H // 2:] = tex[H // 2:, :W]
+    return L, R
+
+
+@pytest.mark.parametrize("mode", ["2", "1", "0"])
+def test_narrowed_right_map_reaches_disp_max(oracle, monkeypatch, mode):
+    """The right map crosses PCIe as u8 + validity bits (ELAS_B200_NARROW_D2=2, disp_max <= 255), as int16 (=1) or as
+    float32 (=0); a scene at disparity 255 = disp_max puts the largest byte value next to invalid pixels.  Unaligned
+    caller buffers and a width that is no multiple of 32 exercise the edges of the widening code."""
+    monkeypatch.setenv("ELAS_B200_NARROW_D2", mode)
+    W, H, dmax = 629, 120, 255
+    L, R = _shifted_pair(W, H, 255, 5)
+    p = checkers.stereomapper(dmax)
+    _, O1, O2 = oracle.process(L, R, p)
+    assert (O2 == 255).sum() > 1000 and (O2 == -10).sum() > 1000
+    e = elas_b200.ElasB200(as_product_params(p), W, H, n_slots=2, n_workers=1, frames_per_group=2)
+    try:
+        # caller's maps at addresses that are 4 mod 16
+        store = [np.zeros(W * H + 8, np.float32) for _ in range(6)]
+        maps = [a[(1 + (-a.ctypes.data // 4)) % 4:][:W * H].reshape(H, W) for a in store]
+        assert all(m.ctypes.data % 16 == 4 for m in maps)
+        st = e.process_batch_ptrs([L.ctypes.data] * 3, [R.ctypes.data] * 3, [m.ctypes.data for m in maps[:3]],
+                                  [m.ctypes.data for m in maps[3:]], L.strides[0])
+    finally:
+        e.close()
+    assert st == [0, 0, 0]
+    for i in range(3):
+        assert bits_equal(maps[i], O1) and bits_equal(maps[3 + i], O2), f"mode {mode} frame {i}"
+
+
+def test_narrowed_right_map_beyond_a_byte(oracle):
+    """disp_max = 300: the narrowed right map falls back to int16."""
+    W, H, dmax = 700, 96, 300
+    L, R = _shifted_pair(W, H, 290, 6)
+    p = checkers.stereomapper(dmax)
+    _, O1, O2 = oracle.process(L, R, p)
+    assert (O2 > 255).sum() > 500
+    e = elas_b200.ElasB200(as_product_params(p), W, H, n_slots=1, n_workers=1)
+    try:
+        st, D1, D2 = e.process_batch([L, L], [R, R])
+    finally:
+        e.close()
+    assert st == [0, 0] and bits_equal(D1[1], O1) and bits_equal(D2[1], O2)
