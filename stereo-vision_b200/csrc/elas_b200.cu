@@ -96,10 +96,10 @@ struct Group {
     float* d_tmp = nullptr;                    // two planes of scratch per frame
     int32_t* d_seg_label = nullptr;            // speckle removal: label per pixel
     int32_t* d_seg_nodes = nullptr;            // ... and the open components on tile borders
-    int16_t* d_D2_i16 = nullptr;               // D2 after the L/R check as int16 (exact: integers or -10), host-output path
+    uint8_t* d_D2_narrow = nullptr;            // D2 after the L/R check narrowed for the host-output path (NarrowD2), narrow_stride bytes per frame
     // pinned host
     uint8_t* h_img[2] = {nullptr, nullptr};    // staging for images that arrive in pageable host memory
-    int16_t* h_D2_i16 = nullptr;               // landing buffer; widened to float into the caller's D2 by the worker
+    uint8_t* h_D2_narrow = nullptr;            // landing buffer; widened to float into the caller's D2 by the worker
     FrameHeader* h_hdr = nullptr;
     int16_t* h_dcan = nullptr;                 // host-stage path only
     int32_t* h_tables = nullptr;               // host-stage path only: [support | tri1 | tri2 | units] of one frame
@@ -200,6 +200,10 @@ std::vector<int32_t> make_prior(const elas_b200_params& p, int dn)
     return P;
 }
 
+// bytes between the narrowed right maps of consecutive frames: room for int16 per pixel (the u8 + validity-bit layout
+// is smaller), a multiple of 16 so that every frame's words stay aligned
+inline size_t narrow_stride(const GroupStrides& st) { return (2 * st.D + 15) & ~(size_t)15; }
+
 void free_group(Group& s)
 {
     for (int k = 0; k < 2; k++) {
@@ -208,7 +212,7 @@ void free_group(Group& s)
         cudaFree(s.d_map[k]); cudaFree(s.d_raw[k]); cudaFree(s.d_D[k]); cudaFree(s.d_planes[k]);
     }
     cudaFree(s.d_dcan_raw); cudaFree(s.d_dcan); cudaFree(s.d_dcan_incon); cudaFree(s.d_support); cudaFree(s.d_mesh_scratch); cudaFree(s.d_lat_work);
-    cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_fuse); cudaFree(s.d_D2_i16); cudaFreeHost(s.h_D2_i16); cudaFreeHost(s.h_hdr);
+    cudaFree(s.d_hdr); cudaFree(s.d_view); cudaFree(s.d_fuse); cudaFree(s.d_D2_narrow); cudaFreeHost(s.h_D2_narrow); cudaFreeHost(s.h_hdr);
     cudaFree(s.d_grid_scratch); cudaFree(s.d_tmp); cudaFree(s.d_seg_label); cudaFree(s.d_seg_nodes);
     cudaFreeHost(s.h_dcan); cudaFreeHost(s.h_tables);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -270,8 +274,8 @@ int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
     CK(cudaMalloc(&s.d_tmp, n * 2 * st.D * 4));
     CK(cudaMalloc(&s.d_seg_label, n * st.D * 4));
     CK(cudaMalloc(&s.d_seg_nodes, n * st.seg_nodes * 4));
-    CK(cudaMalloc(&s.d_D2_i16, n * st.D * 2));
-    CK(cudaMallocHost(&s.h_D2_i16, n * st.D * 2));
+    CK(cudaMalloc(&s.d_D2_narrow, n * narrow_stride(st)));
+    CK(cudaMallocHost(&s.h_D2_narrow, n * narrow_stride(st)));
     return ELAS_B200_OK;
 }
 
@@ -596,7 +600,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
     // ... or, when every disparity fits a byte, as u8 plus one validity bit per pixel (1.125 bytes per pixel)
     const bool d2_narrow = all_host && !any_direct_d2 && n_post == 1 && rows_fused && !s.capture && !c->timing && c->narrow_d2;
     const int d2_mode = !d2_narrow ? 0 : (p.disp_max <= 255 && c->narrow_d2 > 1) ? 2 : 1;
-    const NarrowD2 narrow = narrow_d2_layout(g, d2_mode, s.d_D2_i16, gs.D * 2);
+    const NarrowD2 narrow = narrow_d2_layout(g, d2_mode, s.d_D2_narrow, narrow_stride(gs));
     s.d2_mode = d2_mode;
     OutTable lr_d2 = out_table(s.d_D[1], gs.D, n);
     if (n_post == 1) for (int f = 0; f < n; f++) if (direct[1][f]) lr_d2.p[f] = s.io[f].D2;
@@ -681,7 +685,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
             float* user = k ? s.io[f].D2 : s.io[f].D1;
             if (direct[k][f] || !user) continue;
             if (k == 1 && d2_mode) {
-                CK(cudaMemcpyAsync(s.h_D2_i16 + (size_t)f * gs.D, s.d_D2_i16 + (size_t)f * gs.D, narrow.bytes, cudaMemcpyDeviceToHost, out_stream));
+                CK(cudaMemcpyAsync(s.h_D2_narrow + f * narrow_stride(gs), s.d_D2_narrow + f * narrow_stride(gs), narrow.bytes, cudaMemcpyDeviceToHost, out_stream));
                 s.expand_D2[f] = user;
             } else {
                 CK(cudaMemcpyAsync(user, final_map[k].p[f], ND * 4, cudaMemcpyDefault, out_stream));
@@ -708,13 +712,12 @@ int32_t finish_group(elas_b200_ctx* c, Group& s, int32_t* status_out)
         const FrameHeader& h = s.h_hdr[f];
         status_out[f] = h.status < 0 ? h.status : h.n_support < 3 ? ELAS_B200_E_FEW_SUPPORT : ELAS_B200_OK;
         if (s.expand_D2[f]) {
-            const int16_t* landed = s.h_D2_i16 + (size_t)f * c->st.D;
+            const uint8_t* landed = s.h_D2_narrow + f * narrow_stride(c->st);
             if (s.d2_mode == 2) {
                 const NarrowD2 lay = narrow_d2_layout(c->g, 2, nullptr, 0);
-                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(landed);
-                widen_u8_mask_to_f32(bytes, reinterpret_cast<const uint32_t*>(bytes + lay.mask_offset), lay.mask_words_per_row,
+                widen_u8_mask_to_f32(landed, reinterpret_cast<const uint32_t*>(landed + lay.mask_offset), lay.mask_words_per_row,
                                      s.expand_D2[f], c->g.Dw, c->g.Dh);
-            } else widen_i16_to_f32(landed, s.expand_D2[f], ND);
+            } else widen_i16_to_f32(reinterpret_cast<const int16_t*>(landed), s.expand_D2[f], ND);
             s.expand_D2[f] = nullptr;
         }
     }

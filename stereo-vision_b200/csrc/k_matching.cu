@@ -85,7 +85,8 @@ struct MatchArgs {
 };
 
 constexpr int kInitKey = (10000 << 8) | 255;     // elas.cpp:878-879: min_val = 10000, nothing found
-constexpr int kPad = 4;     // strip entries before/after the addressed range: window taps may step outside [0, disp_max]
+constexpr int kPad = 6;     // strip entries before/after the addressed range: the taps of every plane window that reaches [0, disp_max]
+                            // (d_plane in [-R, disp_max + R]) must be addressable around d_plane itself: kPad >= 2 R for R = 2, 3
 
 // ---- shared-memory access by 32-bit shared address (no generic-pointer conversion in the loops) ----
 __device__ __forceinline__ uint4 lds128(uint32_t addr)

@@ -473,7 +473,7 @@ def test_narrowed_right_map_reaches_disp_max(oracle, monkeypatch, mode):
     float32 (=0); a scene at disparity 255 = disp_max puts the largest byte value next to invalid pixels.  Unaligned
     caller buffers and a width that is no multiple of 32 exercise the edges of the widening code."""
     monkeypatch.setenv("ELAS_B200_NARROW_D2", mode)
-    W, H, dmax = 629, 120, 255
+    W, H, dmax = 629, 121, 255      # an odd pixel count: the frames of a group sit at odd multiples of 2 bytes
     L, R = _shifted_pair(W, H, 255, 5)
     p = checkers.stereomapper(dmax)
     _, O1, O2 = oracle.process(L, R, p)

@@ -1,0 +1,82 @@
+"""Randomised differential test of the CUDA path against the CPU oracle: random image sizes, disparity ranges and
+parameter blocks (ROBOTICS family, MIDDLEBURY preset, subsampling, odd grid sizes, lattice steps, thresholds), single
+frames and batches over frame groups.  Every stage of the single-frame run and the final maps of the batch run are
+compared bit for bit.  Usage: python tools/fuzz_parity.py [cases] [seed]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import checkers, elas_b200, synth
+
+STAGES = ["desc1", "desc2", "dcan_raw", "dcan", "support", "tri1", "tri2", "grid1", "grid2", "D1_raw", "D2_raw", "D1_lr", "D2_lr",
+          "D1_seg", "D1_gap", "D1_mean", "D1", "D2"]
+
+
+def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub", "odd"), max_w=720, max_h=280):
+    """Runs `cases` random cases; returns the list of (description, differing stages)."""
+    rng = np.random.default_rng(seed)
+    oracle = checkers.OracleElas()
+    failures = []
+    bad = 0
+    t0 = time.time()
+    for case in range(cases):
+        dmax = int(rng.choice([31, 47, 63, 95, 100, 127, 200, 255]))
+        W = int(rng.integers(max(96, dmax + 40), max(max_w, dmax + 60))); H = int(rng.integers(64, max_h))
+        kind = rng.choice(list(kinds))
+        p = checkers.stereomapper(dmax) if kind in ("stereomapper", "sub", "odd") else checkers.demo(dmax) if kind == "demo" else checkers.middlebury().copy(disp_max=dmax)
+        over = {}
+        if kind == "sub": over["subsampling"] = 1
+        if kind == "odd":
+            over.update(grid_size=int(rng.choice([10, 15, 16, 20, 24, 25])), candidate_stepsize=int(rng.choice([4, 5, 6, 7])),
+                        speckle_size=int(rng.choice([20, 100, 200, 400])), lr_threshold=int(rng.choice([1, 2])),
+                        ipol_gap_width=int(rng.choice([0, 1, 3, 7])), match_texture=int(rng.choice([0, 1, 30])),
+                        support_texture=int(rng.choice([5, 10, 30])), incon_min_support=int(rng.choice([3, 5, 8])),
+                        filter_adaptive_mean=int(rng.integers(0, 2)), postprocess_only_left=int(rng.integers(0, 2)))
+            if rng.random() < 0.3: over["disp_min"] = int(rng.integers(1, 6))
+            if rng.random() < 0.3: over["sradius"] = 3.0
+        p = p.copy(**over)
+        H = max(H, 2 * p.grid_size + 8)
+        L, R, _ = synth.synthetic_pair(W, H, dmax, seed=int(rng.integers(0, 1 << 30)))
+        if rng.random() < 0.2:                                        # a textureless band / noise to provoke holes and speckles
+            L = L.copy(); L[H // 3: H // 3 + 12] = 128
+        tag = f"case {case}: {W}x{H} d{dmax} {kind} {over}"
+        try:
+            rc_o, O1, O2, st_o = oracle.run_stages(L, R, p)
+            pp = elas_b200.Params.from_buffer_copy(bytes(p))
+            e = elas_b200.ElasB200(pp, W, H, n_slots=2, n_workers=2, frames_per_group=int(rng.choice([1, 2, 3, 8])))
+            try:
+                rc, D1, D2 = e.process(L, R, capture=True)
+                diffs = []
+                if rc != rc_o: diffs.append(f"rc {rc} vs {rc_o}")
+                if rc_o == 0:
+                    for k in STAGES:
+                        a = e.stage(k); b = st_o.get(k)
+                        if a is None or b is None: continue
+                        if a.shape != b.shape or not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+                            diffs.append(k)
+                            if a.shape == b.shape and k.endswith("_raw"):
+                                aa, bb = a.reshape(D1.shape), b.reshape(D1.shape)
+                                w = np.argwhere(aa != bb)
+                                print(f"   {k}: {len(w)} pixels differ; first:", [(int(v), int(u), float(aa[v, u]), float(bb[v, u])) for v, u in w[:6]], flush=True)
+                    if not (np.array_equal(D1.view(np.uint32), O1.view(np.uint32)) and np.array_equal(D2.view(np.uint32), O2.view(np.uint32))): diffs.append("final")
+                    n = int(rng.integers(1, 7))
+                    for rep in range(2):
+                        st, B1, B2 = e.process_batch([L] * n, [R] * n)
+                        for i in range(n):
+                            if st[i] != 0 or not (np.array_equal(B1[i].view(np.uint32), O1.view(np.uint32)) and np.array_equal(B2[i].view(np.uint32), O2.view(np.uint32))):
+                                diffs.append(f"batch rep {rep} frame {i}/{n}")
+                        n = int(rng.integers(1, 7))
+            finally:
+                e.close()
+        except Exception as ex:                                       # unsupported combinations must be refused cleanly, not crash
+            diffs = [f"exception {type(ex).__name__}: {ex}"]
+        if diffs:
+            bad += 1
+            failures.append((tag, diffs))
+            print("DIFF", tag, "->", diffs[:6], flush=True)
+    print(f"fuzz: {cases} cases, {bad} with differences, {time.time() - t0:.0f} s", flush=True)
+    return failures
+
+
+if __name__ == "__main__":
+    run_cases(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
