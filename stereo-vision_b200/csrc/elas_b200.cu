@@ -1210,12 +1210,14 @@ int32_t elas_b200_fuse(elas_b200_ctx* c, int32_t slot, const elas_b200_view* vie
     Group& s = *c->groups[slot];
     const int W = c->g.W, H = c->g.H;
     const size_t n = (size_t)W * H;
-    // device layout: [prev I D X Y Z | cur I D X Y Z | points_prev 4n | points_curr 4n | work ints | 2 counts]
-    const size_t floats = 18 * n, ints = fuse_work_ints(W, H) + 2;
+    // device layout: [prev I D X Y Z | cur I D X Y Z | points_prev 4n | points_curr 4n | work ints | 2 counts]; planes are
+    // np = n rounded up to 4 floats apart so that the point lists (float4 stores) stay 16-byte aligned
+    const size_t np = (n + 3) & ~(size_t)3;
+    const size_t floats = 18 * np, ints = fuse_work_ints(W, H) + 2;
     if (!s.d_fuse) CK(cudaMalloc(&s.d_fuse, (floats + ints) * 4));
     float* pm[5]; float* cm[5];
-    for (int k = 0; k < 5; k++) { pm[k] = s.d_fuse + (size_t)k * n; cm[k] = s.d_fuse + (size_t)(5 + k) * n; }
-    float* d_pp = s.d_fuse + 10 * n; float* d_pc = s.d_fuse + 14 * n;
+    for (int k = 0; k < 5; k++) { pm[k] = s.d_fuse + (size_t)k * np; cm[k] = s.d_fuse + (size_t)(5 + k) * np; }
+    float* d_pp = s.d_fuse + 10 * np; float* d_pc = s.d_fuse + 14 * np;
     int32_t* work = reinterpret_cast<int32_t*>(s.d_fuse + floats);
     int32_t* d_counts = work + fuse_work_ints(W, H);
     float* const user_prev[5] = {has_prev ? prev->I : nullptr, has_prev ? prev->D : nullptr, has_prev ? prev->X : nullptr,

@@ -50,6 +50,14 @@ class Map3D(C.Structure):
     _fields_ = [("I", C.c_void_p), ("D", C.c_void_p), ("X", C.c_void_p), ("Y", C.c_void_p), ("Z", C.c_void_p)]
 
 
+def _image(a):
+    """A uint8 image as the C ABI takes it: unit column stride, any row pitch >= width (bytes_per_line = strides[0]);
+    views into wider rows are passed as they are, anything else is copied."""
+    if isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim == 2 and a.strides[1] == 1 and a.strides[0] >= a.shape[1]:
+        return a
+    return np.ascontiguousarray(a, np.uint8)
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -168,8 +176,9 @@ _STAGE_DTYPES = {
 def process(I1, I2, params):
     """The synchronous drop-in call elas_b200_process (what Elas::process binds)."""
     lib = load_library()
-    I1 = np.ascontiguousarray(I1, np.uint8)
-    I2 = np.ascontiguousarray(I2, np.uint8)
+    I1, I2 = _image(I1), _image(I2)
+    if I1.strides[0] != I2.strides[0]:
+        I1, I2 = np.ascontiguousarray(I1), np.ascontiguousarray(I2)
     H, W = I1.shape
     shape = (H // 2, W // 2) if params.subsampling else (H, W)
     D1 = np.full(shape, -77.0, np.float32)
@@ -231,8 +240,9 @@ class ElasB200:
             pass
 
     def process(self, I1, I2, slot=0, capture=False):
-        I1 = np.ascontiguousarray(I1, np.uint8)
-        I2 = np.ascontiguousarray(I2, np.uint8)
+        I1, I2 = _image(I1), _image(I2)
+        if I1.strides[0] != I2.strides[0]:
+            I1, I2 = np.ascontiguousarray(I1), np.ascontiguousarray(I2)
         assert I1.shape == (self.H, self.W) and I2.shape == I1.shape
         D1 = np.full(self.shape, -77.0, np.float32)
         D2 = np.full(self.shape, -77.0, np.float32)
@@ -324,8 +334,10 @@ class ElasB200:
         return list(status)
 
     def process_batch(self, lefts, rights):
-        lefts = [np.ascontiguousarray(a, np.uint8) for a in lefts]
-        rights = [np.ascontiguousarray(a, np.uint8) for a in rights]
+        lefts = [_image(a) for a in lefts]
+        rights = [_image(a) for a in rights]
+        if len({a.strides[0] for a in lefts + rights}) != 1:          # one bytes_per_line per call
+            lefts = [np.ascontiguousarray(a) for a in lefts]; rights = [np.ascontiguousarray(a) for a in rights]
         D1 = [np.full(self.shape, -77.0, np.float32) for _ in lefts]
         D2 = [np.full(self.shape, -77.0, np.float32) for _ in lefts]
         status = self.process_batch_ptrs([a.ctypes.data for a in lefts], [a.ctypes.data for a in rights],

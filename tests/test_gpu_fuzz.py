@@ -21,3 +21,8 @@ def test_fuzz_all_parameter_families():
 def test_fuzz_plane_radius_3():
     import fuzz_parity
     assert fuzz_parity.run_cases(16, seed=11, kinds=("middlebury",), max_w=700, max_h=200) == []
+
+
+def test_fuzz_view_fusion_and_filters():
+    import fuzz_view
+    assert fuzz_view.run_cases(12, seed=3) == []

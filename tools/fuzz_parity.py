@@ -1,7 +1,7 @@
 """Randomised differential test of the CUDA path against the CPU oracle: random image sizes, disparity ranges and
 parameter blocks (ROBOTICS family, MIDDLEBURY preset, subsampling, odd grid sizes, lattice steps, thresholds), single
 frames and batches over frame groups.  Every stage of the single-frame run and the final maps of the batch run are
-compared bit for bit.  Usage: python tools/fuzz_parity.py [cases] [seed]"""
+compared bit for bit.  Usage: python tools/fuzz_parity.py [cases] [seed] [max_w] [max_h]   (ELAS_B200_HOST_STAGE=1 forces the host mesh stage)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -34,14 +34,35 @@ def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub",
                         filter_adaptive_mean=int(rng.integers(0, 2)), postprocess_only_left=int(rng.integers(0, 2)))
             if rng.random() < 0.3: over["disp_min"] = int(rng.integers(1, 6))
             if rng.random() < 0.3: over["sradius"] = 3.0
+            if rng.random() < 0.25: over["sigma"] = float(rng.choice([0.6, 1.5, 2.0]))        # plane radius 2..6: the generic window
+            if rng.random() < 0.25: over.update(gamma=float(rng.choice([1.0, 5.0, 15.0])), beta=float(rng.choice([0.01, 0.05])))
+            if rng.random() < 0.2: over["filter_median"] = 1
+            if rng.random() < 0.2: over["support_threshold"] = float(rng.choice([0.7, 0.95]))
+            if rng.random() < 0.15: over["subsampling"] = 1
+            if rng.random() < 0.15: over["add_corners"] = 1
+            if rng.random() < 0.2: over["incon_window_size"] = int(rng.choice([3, 7]))
+            if rng.random() < 0.2: over["speckle_sim_threshold"] = float(rng.choice([0.5, 2.0]))
         p = p.copy(**over)
         H = max(H, 2 * p.grid_size + 8)
         L, R, _ = synth.synthetic_pair(W, H, dmax, seed=int(rng.integers(0, 1 << 30)))
         if rng.random() < 0.2:                                        # a textureless band / noise to provoke holes and speckles
             L = L.copy(); L[H // 3: H // 3 + 12] = 128
+        content = rng.random()
+        if content < 0.08:                                            # pure noise: hardly any support point survives
+            L = rng.integers(0, 256, (H, W), dtype=np.uint8); R = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        elif content < 0.14:                                          # the whole scene at (nearly) the largest disparity
+            tex = rng.integers(0, 256, (H, W + dmax), dtype=np.uint8)
+            R = tex[:, dmax:].copy(); L = tex[:, 1:W + 1].copy() if rng.random() < 0.5 else tex[:, :W].copy()
+        elif content < 0.2:                                           # salt noise on the right image: speckles and failed L/R checks
+            R = R.copy(); m = rng.random((H, W)) < 0.05; R[m] = rng.integers(0, 256, int(m.sum()), dtype=np.uint8)
+        if rng.random() < 0.3:                                        # the caller's rows are wider than the image (stereothread.cpp:111)
+            pitch = W + int(rng.integers(1, 40))
+            Lp = rng.integers(0, 256, (H, pitch), dtype=np.uint8); Rp = rng.integers(0, 256, (H, pitch), dtype=np.uint8)
+            Lp[:, :W] = L; Rp[:, :W] = R
+            L, R = Lp[:, :W], Rp[:, :W]                                # views with strides[0] = pitch
         tag = f"case {case}: {W}x{H} d{dmax} {kind} {over}"
         try:
-            rc_o, O1, O2, st_o = oracle.run_stages(L, R, p)
+            rc_o, O1, O2, st_o = oracle.run_stages(np.ascontiguousarray(L), np.ascontiguousarray(R), p)
             pp = elas_b200.Params.from_buffer_copy(bytes(p))
             e = elas_b200.ElasB200(pp, W, H, n_slots=2, n_workers=2, frames_per_group=int(rng.choice([1, 2, 3, 8])))
             try:
@@ -79,4 +100,6 @@ def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub",
 
 
 if __name__ == "__main__":
-    run_cases(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    # python tools/fuzz_parity.py [cases] [seed] [max_w] [max_h]
+    a = [int(x) for x in sys.argv[1:]]
+    run_cases(a[0] if len(a) > 0 else 40, a[1] if len(a) > 1 else 1, max_w=a[2] if len(a) > 2 else 720, max_h=a[3] if len(a) > 3 else 280)
