@@ -87,6 +87,34 @@ def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub",
                             if st[i] != 0 or not (np.array_equal(B1[i].view(np.uint32), O1.view(np.uint32)) and np.array_equal(B2[i].view(np.uint32), O2.view(np.uint32))):
                                 diffs.append(f"batch rep {rep} frame {i}/{n}")
                         n = int(rng.integers(1, 7))
+                    if rng.random() < 0.35:
+                        # a batch of DIFFERENT frames (one of them blank), in random order, through host or device buffers
+                        Lc, Rc = np.ascontiguousarray(L), np.ascontiguousarray(R)
+                        L2, R2, _ = synth.synthetic_pair(W, H, dmax, seed=int(rng.integers(0, 1 << 30)))
+                        blank = np.full((H, W), 77, np.uint8)
+                        frames = [(Lc, Rc, rc_o, O1, O2)]
+                        rc2, P1, P2 = oracle.process(L2, R2, p)
+                        frames.append((L2, R2, rc2, P1, P2))
+                        # a blank frame: fewer than 3 support points (rc 1, maps -10) -- unless add_corners invents six (elas.cpp:283-318)
+                        rc3, Q1, Q2 = oracle.process(blank, blank, p)
+                        frames.append((blank, blank, rc3, Q1, Q2) if rc3 == 0 else (blank, blank, 1, np.full_like(O1, -10), np.full_like(O2, -10)))
+                        order = [int(x) for x in rng.integers(0, 3, int(rng.integers(2, 12)))]
+                        if rng.random() < 0.5:
+                            import torch
+                            dI = torch.stack([torch.stack([torch.from_numpy(frames[k][0]), torch.from_numpy(frames[k][1])]) for k in order]).cuda()
+                            dD = torch.full((len(order), 2) + O1.shape, -77.0, dtype=torch.float32, device="cuda")
+                            st = e.process_batch_ptrs([dI[i, 0].data_ptr() for i in range(len(order))], [dI[i, 1].data_ptr() for i in range(len(order))],
+                                                      [dD[i, 0].data_ptr() for i in range(len(order))], [dD[i, 1].data_ptr() for i in range(len(order))], W, device=True)
+                            torch.cuda.synchronize()
+                            outs = dD.cpu().numpy(); B1 = [outs[i, 0] for i in range(len(order))]; B2 = [outs[i, 1] for i in range(len(order))]
+                            how = "device"
+                        else:
+                            st, B1, B2 = e.process_batch([frames[k][0] for k in order], [frames[k][1] for k in order])
+                            how = "host"
+                        for i, k in enumerate(order):
+                            want_rc = frames[k][2]
+                            if st[i] != want_rc or not (np.array_equal(B1[i].view(np.uint32), frames[k][3].view(np.uint32)) and np.array_equal(B2[i].view(np.uint32), frames[k][4].view(np.uint32))):
+                                diffs.append(f"mixed {how} batch frame {i} (kind {k}) of {order}: status {st[i]} vs {want_rc}")
             finally:
                 e.close()
         except Exception as ex:                                       # unsupported combinations must be refused cleanly, not crash
