@@ -55,10 +55,11 @@ def algorithmic_bytes_matching(w, h, dmax, grid_size=20):
     return 72 * w * h + 8 * gw * gh * (dmax + 2)
 
 
-def ncu_traffic_k7(which=None):
+def ncu_traffic_k7(which=None, frames_per_launch=None):
     """DRAM bytes per launch of the matching kernel from the committed ncu --set full captures
-    (which = None: the 1242x375 workload; "bandwidth_config": 4096x2160)."""
-    path = os.path.join(ROOT, "profiles", "r01_k7_traffic.json")
+    (which = None: the 1242x375 workload; "bandwidth_config": 4096x2160), scaled to the frames a launch of this run
+    processes (the captures are per launch of `frames_per_launch` frames)."""
+    path = os.path.join(ROOT, "profiles", "r02_k7_traffic.json")
     if not os.path.exists(path):
         return None
     rec = json.load(open(path))
@@ -66,7 +67,9 @@ def ncu_traffic_k7(which=None):
         rec = rec.get(which)
         if not rec:
             return None
-    return int(rec["dram_bytes_read_per_launch"]) + int(rec["dram_bytes_write_per_launch"])
+    total = int(rec["dram_bytes_read_per_launch"]) + int(rec["dram_bytes_write_per_launch"])
+    captured = int(rec.get("frames_per_launch", 1))
+    return total if not frames_per_launch else int(round(total * frames_per_launch / captured))
 
 
 def measured_hbm_peak():
@@ -480,7 +483,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_matching (K7, left+right, one launch per frame group)", "frames_per_launch": k7_frames,
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic_k7(),
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic_k7(frames_per_launch=k7_frames) if args.config == "K" else None,
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
