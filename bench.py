@@ -34,9 +34,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "stereo-vision_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+# 32 hardware work queues instead of 8 (read at CUDA context creation, i.e. before torch touches the device): the frame
+# groups' launch chains run on separate streams and must not queue behind each other's long single-CTA kernels
+# (libelas_b200.so sets the same default when it is loaded first, elas_b200.cu)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 # BASELINE.json configs: K = configs[1] (the metric's configuration, default), HD = configs[2], 4K = configs[4] geometry
-CONFIGS = {"K": (1242, 375, 255, 512, 8), "HD": (1920, 1080, 128, 128, 2), "4K": (4096, 2160, 256, 32, 1)}
+CONFIGS = {"K": (1242, 375, 255, 512, 8), "HD": (1920, 1080, 128, 256, 2), "4K": (4096, 2160, 256, 64, 1)}
 W, H, DMAX = CONFIGS["K"][:3]
 WORKLOAD = f"synthetic {W}x{H} random-texture stereo pairs, d_max={DMAX}, stereomapper parameter set"
 METRIC = "stereo pairs/sec @1242x375 d_max=255"
@@ -251,7 +255,7 @@ def main():
     # The whole frame runs on the GPU, so a worker only enqueues launch chains and collects results (the end-to-end
     # path also widens D2 from int16 on the host): a few per GPU, one core per rank stays free for the main thread
     workers = args.workers or max(1, min(8, share - 1))
-    slots = args.slots or max(2, min(24, 3 * workers))
+    slots = args.slots or max(2, min(32, 4 * workers))
     B = args.batch or CONFIGS[args.config][3]
     args.distinct = min(args.distinct, B)
     bpl = W + 15 - (W - 1) % 16

@@ -849,6 +849,14 @@ uint64_t g_cache_tick = 0;
 
 }  // namespace
 
+// Frame groups run their launch chains on separate streams, and a chain holds kernels that run for a long time on
+// one or two CTAs (the mesh stage).  With the default of 8 hardware work queues, streams share queues and a chain that
+// waits for such a kernel blocks the streams queued behind it (4096x2160: 530 -> 910 pairs/s with 32 queues; 1242x375
+// end to end: 12.1 k -> 13.1 k).  The variable is read when the CUDA context is created: the library sets it when it is
+// loaded unless the host application has chosen a value; a host that initialises CUDA before loading the library
+// should export CUDA_DEVICE_MAX_CONNECTIONS=32 itself (bench.py does).
+__attribute__((constructor)) static void elas_b200_more_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 extern "C" {
 
 void elas_b200_default_params(elas_b200_params* p, int32_t setting)
@@ -931,18 +939,10 @@ int32_t elas_b200_create_grouped(elas_b200_ctx** out, int32_t device, const elas
     // warp each (FrameHeader::ovf_from), so this is a performance knob, not a limit.
     c->unit_cap = c->tri_cap + 4 * ((width + 31) / 32) * ((height + kRasterBandRows - 1) / kRasterBandRows) + 64;
     c->mesh_device = mesh_on_device(g, *p);
-    {
-        // A lattice that fits one CTA's shared memory (up to ~1920x1080) is filtered and triangulated on the GPU in
-        // tens to hundreds of microseconds.  Beyond that the single-CTA kernels work out of L2 and take milliseconds:
-        // still the better choice when few host threads serve this GPU (8 GPUs on one host), but with a core per
-        // worker to spare the host stage keeps up and leaves the SMs to the bandwidth kernels.
-        int cores = (int)std::thread::hardware_concurrency();
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
-        const int workers_hint = n_workers > 0 ? n_workers : cores;
-        const bool big_lattice = lattice_work_ints(g) * 4 > (size_t)1 << 20 || (size_t)g.Wc * g.Hc > 60000;
-        if (c->mesh_device && big_lattice && workers_hint >= 8) c->mesh_device = false;
-    }
+    // Lattices that do not fit one CTA's shared memory (beyond ~1500x800) are filtered and triangulated out of L2 by the
+    // same single-CTA kernels: milliseconds instead of tens of microseconds per frame, but many frame groups run them
+    // side by side (32 hardware queues, see the constructor below) and no host core is needed -- measured at 1920x1080:
+    // 4.6 k pairs/s against 3.6 k with the host stage on 15 cores; at 4096x2160: 0.92 k against 0.95 k.
     // ELAS_B200_HOST_STAGE=1 forces the host stage, =0 the device mesh stage wherever the parameters allow it
     if (const char* e = std::getenv("ELAS_B200_HOST_STAGE")) c->mesh_device = std::atoi(e) ? false : mesh_on_device(g, *p);
     // both SAD kernels stage their descriptor strips (segment + disparity range) in shared memory: at most
