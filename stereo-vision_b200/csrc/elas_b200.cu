@@ -323,16 +323,18 @@ std::vector<uint8_t> expand_grid(const FrameGeom& g, const std::vector<uint8_t>&
 
 // what kind of memory a caller's pointer is (launch errors are checked where the launches are issued, so
 // clearing the error of a failed query here cannot swallow one)
-struct PtrKind { bool pageable, device, mapped_host; void* device_alias; };
+struct PtrKind { bool pageable, device, mapped_host, device_alias_only; void* device_alias; };
 PtrKind classify(const void* ptr, int device)
 {
-    PtrKind k{false, false, false, nullptr};
+    PtrKind k{false, false, false, false, nullptr};
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); k.pageable = true; return k; }
     k.pageable = attr.type == cudaMemoryTypeUnregistered;
     // only memory of THIS device is written in place by the kernels; anything else takes the copy path
     k.device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.device == device;
     k.mapped_host = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+    // device or managed memory that is NOT this device's: reachable by copies only, and not CPU-addressable for sure
+    k.device_alias_only = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && !k.device;
     k.device_alias = attr.devicePointer;
     return k;
 }
@@ -591,9 +593,12 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         for (int k = 0; k < 2; k++) {
             float* user = k ? s.io[f].D2 : s.io[f].D1;
             if (!user) continue;                     // batch calls may leave D2 out (stereomapper never reads it)
+            // device memory of any GPU (this one is written in place by the fused tail, others and the unfused chain
+            // are reached by copies): never handed to the CPU-side widening
+            const bool on_device = s.io[f].device_io || classify(user, c->device).device || classify(user, c->device).device_alias_only;
             direct[k][f] = fused_post && (s.io[f].device_io || classify(user, c->device).device);
             if (k == 1 && direct[k][f]) any_direct_d2 = true;
-            if (direct[k][f]) all_host = false;
+            if (on_device) all_host = false;
         }
     // Copy path, D2 final after the L/R check: its values are raw integer disparities or -10, so it crosses
     // PCIe as int16 (half the bytes) and the worker widens it into the caller's float map.

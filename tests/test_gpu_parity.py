@@ -506,3 +506,33 @@ def test_narrowed_right_map_beyond_a_byte(oracle):
     finally:
         e.close()
     assert st == [0, 0] and bits_equal(D1[1], O1) and bits_equal(D2[1], O2)
+
+
+def test_device_buffers_through_the_unfused_tail(oracle):
+    """Device-resident maps with a parameter set that runs the unfused post-processing chain (median): the maps are
+    reached by device-to-device copies -- in particular the right map must not take the narrowed host path, whose
+    CPU-side widening cannot write device memory."""
+    torch = pytest.importorskip("torch")
+    W, H, dmax = 512, 188, 100
+    p = checkers.stereomapper(dmax).copy(filter_median=1)
+    L, R, _ = synth.synthetic_pair(W, H, dmax, 81)
+    _, O1, O2 = oracle.process(L, R, p)
+    n = 5
+    dI = torch.stack([torch.stack([torch.from_numpy(L), torch.from_numpy(R)]) for _ in range(n)]).cuda()
+    dD = torch.full((n, 2, H, W), -77.0, dtype=torch.float32, device="cuda")
+    e = elas_b200.ElasB200(as_product_params(p), W, H, n_slots=2, n_workers=2, frames_per_group=3)
+    try:
+        st = e.process_batch_ptrs([dI[i, 0].data_ptr() for i in range(n)], [dI[i, 1].data_ptr() for i in range(n)],
+                                  [dD[i, 0].data_ptr() for i in range(n)], [dD[i, 1].data_ptr() for i in range(n)], W, device=True)
+        torch.cuda.synchronize()
+        # the same buffers through the HOST entry point (pointer classification instead of the device flag)
+        dD2 = torch.full((n, 2, H, W), -77.0, dtype=torch.float32, device="cuda")
+        st2 = e.process_batch_ptrs([dI[i, 0].data_ptr() for i in range(n)], [dI[i, 1].data_ptr() for i in range(n)],
+                                   [dD2[i, 0].data_ptr() for i in range(n)], [dD2[i, 1].data_ptr() for i in range(n)], W, device=False)
+        torch.cuda.synchronize()
+    finally:
+        e.close()
+    assert st == [0] * n and st2 == [0] * n
+    for out in (dD.cpu().numpy(), dD2.cpu().numpy()):
+        for i in range(n):
+            assert bits_equal(out[i, 0], O1) and bits_equal(out[i, 1], O2), f"frame {i}"

@@ -61,6 +61,7 @@ def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub",
             Lp[:, :W] = L; Rp[:, :W] = R
             L, R = Lp[:, :W], Rp[:, :W]                                # views with strides[0] = pitch
         tag = f"case {case}: {W}x{H} d{dmax} {kind} {over}"
+        if os.environ.get("FUZZ_VERBOSE"): print("RUN", tag, "pitch", L.strides[0], flush=True)
         try:
             rc_o, O1, O2, st_o = oracle.run_stages(np.ascontiguousarray(L), np.ascontiguousarray(R), p)
             pp = elas_b200.Params.from_buffer_copy(bytes(p))
