@@ -109,6 +109,20 @@ def run_cases(cases, seed=1, kinds=("stereomapper", "demo", "middlebury", "sub",
                             torch.cuda.synchronize()
                             outs = dD.cpu().numpy(); B1 = [outs[i, 0] for i in range(len(order))]; B2 = [outs[i, 1] for i in range(len(order))]
                             how = "device"
+                        elif rng.random() < 0.5:
+                            # pinned host buffers, some frames without a right map (D2 == NULL)
+                            import torch
+                            hI = torch.stack([torch.stack([torch.from_numpy(frames[k][0]), torch.from_numpy(frames[k][1])]) for k in order]).pin_memory()
+                            hD = torch.full((len(order), 2) + O1.shape, -77.0, dtype=torch.float32).pin_memory()
+                            skip2 = [bool(rng.random() < 0.4) for _ in order]
+                            st = e.process_batch_ptrs([hI[i, 0].data_ptr() for i in range(len(order))], [hI[i, 1].data_ptr() for i in range(len(order))],
+                                                      [hD[i, 0].data_ptr() for i in range(len(order))],
+                                                      [0 if skip2[i] else hD[i, 1].data_ptr() for i in range(len(order))], W, device=False)
+                            outs = hD.numpy(); B1 = [outs[i, 0] for i in range(len(order))]
+                            B2 = [frames[k][4] if skip2[i] else outs[i, 1] for i, k in enumerate(order)]
+                            for i in range(len(order)):
+                                if skip2[i] and not (outs[i, 1] == -77.0).all(): diffs.append(f"mixed pinned batch frame {i}: a right map that was not asked for was written")
+                            how = "pinned"
                         else:
                             st, B1, B2 = e.process_batch([frames[k][0] for k in order], [frames[k][1] for k in order])
                             how = "host"
