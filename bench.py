@@ -431,11 +431,11 @@ def main():
 
     # the bandwidth-ceiling configuration (BASELINE.json configs[4] geometry, one GPU): its working set
     # (683 MB algorithmic) does not fit L2, so this is the honest HBM-roofline point of the same kernel
-    roof_4k = roof_hd = None
+    roof_4k = roof_hd = roof_k16 = None
     if rank == 0 and world == 1 and not args.no_4k and args.config == "K":
-        def roof_point(Wx, Hx, Dx):
+        def roof_point(Wx, Hx, Dx, frames=0):
             Lx, Rx, _ = synth.synthetic_pair(Wx, Hx, Dx, seed=0)
-            ex = elas_b200.ElasB200(elas_b200.stereomapper(Dx), Wx, Hx, n_slots=1, device=local_rank, frames_per_group=0)
+            ex = elas_b200.ElasB200(elas_b200.stereomapper(Dx), Wx, Hx, n_slots=1, device=local_rank, frames_per_group=frames)
             nfx = ex.frames_per_group
             ex.process_batch([Lx] * nfx, [Rx] * nfx)
             msx, nf = ex.time_matching(iters=20, flush_l2=True, per_frame=False)
@@ -447,6 +447,10 @@ def main():
                     "frames_per_launch": nf, "ms_per_launch": round(msx, 5)}
         roof_hd = roof_point(1920, 1080, 128)       # BASELINE.json configs[2] geometry
         roof_4k = roof_point(4096, 2160, 256)       # BASELINE.json configs[4] geometry
+        # the same kernel on the metric's workload with 16 frames per launch (20 waves of CTAs instead of 10): what
+        # the wave quantisation of a launch costs; the pipeline keeps 8 (same pairs/s, finer-grained copies)
+        roof_k16 = roof_point(W, H, DMAX, frames=16)
+        roof_k16["note"] = "K with 16 frames per launch (opt-in frames_per_group=16); the pipeline and `roofline` use 8"
         roof_4k["traffic"] = ncu_traffic_k7("bandwidth_config")
 
     (launches,) = sharding.sum_over_ranks([launches], dev)      # whole job
@@ -491,7 +495,7 @@ def main():
                          "algorithmic_bytes_per_launch": b_match, "ms_per_launch": round(k7_ms, 5),
                          "peak_source": peak_src},
             "roofline_bandwidth_config": roof_4k,
-            "roofline_hd_config": roof_hd,
+            "roofline_hd_config": roof_hd, "roofline_16_frames_per_launch": roof_k16,
             "view_kernels": view, "matcher_filters": filters,
             "drop_in_call": drop_in,
             "cpu_baseline": cpu,

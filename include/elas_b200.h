@@ -98,8 +98,8 @@ int32_t elas_b200_create(elas_b200_ctx** out, int32_t device, const elas_b200_pa
  * (e.g. 2x) and the GPU stays fed while every worker runs host stages. */
 int32_t elas_b200_create_ex(elas_b200_ctx** out, int32_t device, const elas_b200_params* p,
                             int32_t width, int32_t height, int32_t n_slots, int32_t n_workers);
-/* Frame groups: a context owns n_groups groups of frames_per_group frames each (at most 8; 0 = chosen from the
- * frame size).  The frames of a group share one chain of kernel launches -- every kernel takes the frame as a
+/* Frame groups: a context owns n_groups groups of frames_per_group frames each (at most 16; 0 = chosen from the
+ * frame size: 8 500 000 / (width * height), between 1 and 8).  The frames of a group share one chain of kernel launches -- every kernel takes the frame as a
  * grid dimension -- so small frames still fill the GPU and the launch cost per frame shrinks.  The whole path of
  * a frame runs on the device (for the parameter sets the device mesh stage covers, which include both presets'
  * ROBOTICS family; others use the host stage of section 3), so n_workers host threads only enqueue chains and

@@ -99,7 +99,7 @@ __host__ __device__ inline int map_pitch(const FrameGeom& g) { return map_pitch_
 // ---- kernel launchers (one translation unit each) --------------------------------------------
 // Every launcher takes the pointers of FRAME 0 of a frame group, the group's strides and the number of frames
 // batched into the launch (a grid dimension): one launch chain serves up to kMaxGroupFrames frames.
-constexpr int kMaxGroupFrames = 8;
+constexpr int kMaxGroupFrames = 16;
 struct OutTable { float* p[kMaxGroupFrames]; };      // where each frame's finished map goes (group buffer or the caller's)
 OutTable out_table(float* base, size_t stride, int n_frames);
 

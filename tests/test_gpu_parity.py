@@ -536,3 +536,19 @@ def test_device_buffers_through_the_unfused_tail(oracle):
     for out in (dD.cpu().numpy(), dD2.cpu().numpy()):
         for i in range(n):
             assert bits_equal(out[i, 0], O1) and bits_equal(out[i, 1], O2), f"frame {i}"
+
+
+def test_sixteen_frames_per_chain(oracle):
+    """The largest frame group (opt-in, frames_per_group = 16): 21 frames = one full chain and a tail of 5."""
+    p = checkers.stereomapper(63)
+    pairs = [synth.synthetic_pair(320, 120, 63, s)[:2] for s in (91, 92, 93)]
+    want = [oracle.process(L, R, p) for L, R in pairs]
+    e = elas_b200.ElasB200(as_product_params(p), 320, 120, n_slots=1, n_workers=1, frames_per_group=16)
+    try:
+        assert e.frames_per_group == 16
+        for n in (21, 16, 3):
+            status, D1, D2 = e.process_batch([pairs[i % 3][0] for i in range(n)], [pairs[i % 3][1] for i in range(n)])
+            for i in range(n):
+                assert status[i] == 0 and bits_equal(D1[i], want[i % 3][1]) and bits_equal(D2[i], want[i % 3][2]), f"batch of {n}, frame {i}"
+    finally:
+        e.close()
