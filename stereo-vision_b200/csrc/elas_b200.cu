@@ -708,8 +708,13 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
 int32_t finish_group(elas_b200_ctx* c, Group& s, int32_t* status_out)
 {
     const long long t0 = now_ns();
-    CK(cudaEventSynchronize(s.ev_out));
-    CK(cudaGetLastError());
+    cudaError_t waited = cudaEventSynchronize(s.ev_out);
+    if (waited == cudaSuccess) waited = cudaGetLastError();
+    if (waited != cudaSuccess) {
+        // the chain failed: nothing landed, nothing to widen (the callers' maps keep whatever they held)
+        std::fill(s.expand_D2.begin(), s.expand_D2.end(), nullptr);
+        CK(waited);
+    }
     const long long t1 = now_ns();
     c->ns_wait += t1 - t0; c->frames += s.n;
     const size_t ND = (size_t)c->g.Dw * c->g.Dh;
