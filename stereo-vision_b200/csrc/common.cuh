@@ -2,6 +2,7 @@
 // Vocabulary follows the reference (libelas/src/elas.{h,cpp}): descriptors, candidate lattice,
 // support points, triangles, disparity planes, candidate grid, disparity maps.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -104,7 +105,10 @@ struct OutTable { float* p[kMaxGroupFrames]; };      // where each frame's finis
 OutTable out_table(float* base, size_t stride, int n_frames);
 
 // K1  Sobel + descriptor, both images (filter.cpp:408-416, descriptor.cpp:48-121)
-void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const uint8_t* img2,
+// (the image tiles arrive by tensor-map TMA: tm1 / tm2 describe the group's two image buffers as [frames][H][bpl] uint8
+// with the box descriptor_tile_box() = {columns, rows}; elas_b200.cu encodes them once per group)
+void descriptor_tile_box(int box[2]);
+void launch_descriptor(const FrameGeom& g, int half, const CUtensorMap& tm1, const CUtensorMap& tm2,
                        uint4* desc1, uint4* desc2, const GroupStrides& st, int n_frames, cudaStream_t s);
 // K2  support matching on the candidate lattice, forward + reverse (elas.cpp:322-445, :471-493)
 void launch_support(const FrameGeom& g, const elas_b200_params& p, const uint4* desc1,

@@ -75,6 +75,7 @@ struct Group {
     cudaEvent_t ev_out = nullptr;              // the group's maps and headers are in the caller's / pinned buffers
     // device, [cap] frames each (strides: elas_b200_ctx::st)
     uint8_t* d_img[2] = {nullptr, nullptr};
+    CUtensorMap tm_img[2];                     // d_img[k] as a [frames][H][bpl] uint8 tensor for K1's tile loads (TMA)
     uint4* d_desc[2] = {nullptr, nullptr};
     int16_t* d_dcan_raw = nullptr;             // K2's candidate lattice
     int16_t* d_dcan = nullptr;                 // after the lattice filters
@@ -226,6 +227,37 @@ void free_group(Group& s)
 // ints of one frame's host-path tables: [support | tri1 | tri2 | units]
 size_t table_ints(const elas_b200_ctx* c) { return 3 * ((size_t)c->support_cap + 2 * (size_t)c->tri_cap) + 2 * (size_t)c->unit_cap + 8; }
 
+// Tensor map of a group's image buffer for k_descriptor: dims (column, row, frame), box = one image tile of one frame.
+// cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime so that the library keeps
+// linking against cudart only.
+int32_t encode_image_tensor_map(CUtensorMap* tm, uint8_t* base, int bpl, int H, int frames, size_t frame_stride)
+{
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return ELAS_B200_E_CUDA;
+        encode = reinterpret_cast<Encode>(fn);
+    }
+    int box[2];
+    descriptor_tile_box(box);
+    const cuuint64_t dims[3] = {(cuuint64_t)bpl, (cuuint64_t)H, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)bpl, (cuuint64_t)frame_stride};          // bytes; bpl is a multiple of 16
+    const cuuint32_t boxdim[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, boxdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        std::fprintf(stderr, "elas_b200: cuTensorMapEncodeTiled failed with %d (bpl %d, H %d, frames %d)\n", (int)r, bpl, H, frames);
+        return ELAS_B200_E_CUDA;
+    }
+    return ELAS_B200_OK;
+}
+
 int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
 {
     const FrameGeom& g = c->g;
@@ -241,6 +273,7 @@ int32_t alloc_group(elas_b200_ctx* c, Group& s, int cap)
     for (int k = 0; k < 2; k++) {
         CK(cudaMalloc(&s.d_img[k], n * st.img));
         CK(cudaMemset(s.d_img[k], 0, n * st.img));                          // padding columns stay 0 (elas.cpp:42-43)
+        if (int32_t rc = encode_image_tensor_map(&s.tm_img[k], s.d_img[k], c->g.bpl, c->g.H, cap, st.img)) return rc;
         CK(cudaMallocHost(&s.h_img[k], n * st.img));
         std::memset(s.h_img[k], 0, n * st.img);
         CK(cudaMalloc(&s.d_desc[k], n * st.desc * 16));
@@ -496,7 +529,7 @@ int32_t submit_group(elas_b200_ctx* c, Group& s)
         if (int32_t rc = copy_image_in(c, s.d_img[1] + (size_t)f * gs.img, io.I2, io.bytes_per_line, st, io.device_io ? nullptr : s.h_img[1] + (size_t)f * gs.img)) return rc;
     }
     mark(c, s, "copy_in");
-    launch_descriptor(g, p.subsampling, s.d_img[0], s.d_img[1], s.d_desc[0], s.d_desc[1], gs, n, st);
+    launch_descriptor(g, p.subsampling, s.tm_img[0], s.tm_img[1], s.d_desc[0], s.d_desc[1], gs, n, st);
     mark(c, s, "descriptor");
     launch_support(g, p, s.d_desc[0], s.d_desc[1], s.d_dcan_raw, gs, n, st);
     mark(c, s, "support");

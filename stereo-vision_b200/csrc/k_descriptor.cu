@@ -4,8 +4,10 @@
 // convolve_101_row_3x3_16bit :227-267 + convolve_121_row_3x3_16bit :176-222) followed by
 // Descriptor::createDescriptor (descriptor.cpp:48-121).  The reference materialises two int16 and
 // two uint8 planes per image; here one CTA stages a 64x16 pixel tile (+3 halo) of the uint8 image in
-// shared memory, derives du/dv for the tile (+2 / +1 halo) in shared memory and writes each
-// pixel's 16 descriptor bytes with a single 16-byte store.  HBM traffic: 1 B/px in, 16 B/px out.
+// shared memory -- ONE tensor-map TMA copy (cp.async.bulk.tensor.3d: column, row, frame of the group's image
+// buffer; the halo outside the image arrives as zeros, no bounds tests) -- derives du/dv for the tile
+// (+2 / +1 halo) in shared memory and writes each pixel's 16 descriptor bytes with a single 16-byte store.
+// HBM traffic: 1 B/px in, 16 B/px out.
 //
 // Both stages work on groups of four horizontally adjacent pixels per thread: the Sobel stage shares
 // the column sums S = I(v-1)+2I(v)+I(v+1) and T = I(v-1)-I(v+1) between neighbours (6 columns for 4
@@ -21,7 +23,8 @@ namespace elasb {
 namespace {
 
 constexpr int TW = 64, TH = 16;            // output tile
-constexpr int IW = TW + 12, IH = TH + 6;   // image tile: cols u0-4 .. u0+TW+7 (word aligned), rows v0-3 .. v0+TH+2
+constexpr int IW = TW + 32, IH = TH + 6;   // image tile: cols u0-16 .. u0+TW+15 (a TMA box starts and ends on 16-byte boundaries of the row), rows v0-3 .. v0+TH+2
+constexpr int IX = 16;                     // tile column of image column u0
 constexpr int GW = (TW + 4 + 3) / 4;       // du/dv groups of four columns per row: cols u0-2 .. u0-2+4*GW-1
 constexpr int UP = 4 * GW + 4;             // du/dv tile pitch in bytes (cols u0-2 ..), a multiple of 4, plus one spare word
 constexpr int UH = TH + 4;                 // du rows v0-2 .. v0+TH+1; dv is kept for the same rows (v0-1 .. v0+TH used)
@@ -43,38 +46,56 @@ __device__ __forceinline__ Win load_win(const uint8_t* row, int idx)      // idx
     return w;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(256)
-k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint8_t* __restrict__ img2,
-             uint4* __restrict__ desc1, uint4* __restrict__ desc2, size_t img_stride, size_t desc_stride)
+k_descriptor(FrameGeom g, int half, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+             uint4* __restrict__ desc1, uint4* __restrict__ desc2, size_t desc_stride)
 {
-    __shared__ __align__(16) uint8_t sI[IH][IW];
+    __shared__ __align__(128) uint8_t sI[IH][IW];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) uint8_t sU[UH][UP];
     __shared__ __align__(16) uint8_t sV[UH][UP];
     __shared__ uint4 sO[TH][TW];               // finished descriptors, 16-byte chunks XOR-swizzled within 128-byte lines
 
     // blockIdx.z = 2 * frame + image
-    const uint8_t* __restrict__ img = ((blockIdx.z & 1) ? img2 : img1) + (size_t)(blockIdx.z >> 1) * img_stride;
     uint4* __restrict__ desc = ((blockIdx.z & 1) ? desc2 : desc1) + (size_t)(blockIdx.z >> 1) * desc_stride;
     const int u0 = blockIdx.x * TW, v0 = blockIdx.y * TH;
     const int tid = threadIdx.x;
 
-    // stage the image tile, one aligned 32-bit word per load; outside the padded image = 0
-    for (int i = tid; i < IH * (IW / 4); i += 256) {
-        const int r = i / (IW / 4), cw = i - r * (IW / 4);
-        const int v = v0 - 3 + r, u = u0 - 4 + 4 * cw;
-        uint32_t w = 0;
-        if (v >= 0 && v < g.H && u >= 0 && u < g.bpl)
-            w = *reinterpret_cast<const uint32_t*>(img + (size_t)v * g.bpl + u);
-        *reinterpret_cast<uint32_t*>(&sI[r][4 * cw]) = w;
+    // stage the image tile: one TMA tensor copy of the box [u0-16, u0+80) x [v0-3, v0+19) x {frame} (the innermost start
+    // coordinate must be a multiple of 16 bytes: tools/micro/tma_tile_probe.cu); whatever lies
+    // outside the padded image [0, bpl) x [0, H) is filled with zeros by the copy engine
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(IH * IW) : "memory");
+        // the descriptor must be addressed where it lies in the kernel's parameter space (no pointer select: that would
+        // make the compiler copy the map into local memory, which the TMA unit cannot read)
+        if (blockIdx.z & 1)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(&sI[0][0])), "l"(&tm2), "r"(u0 - IX), "r"(v0 - 3), "r"((int)(blockIdx.z >> 1)), "r"(smem_u32(&bar)) : "memory");
+        else
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(&sI[0][0])), "l"(&tm1), "r"(u0 - IX), "r"(v0 - 3), "r"((int)(blockIdx.z >> 1)), "r"(smem_u32(&bar)) : "memory");
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
 
     // du(u,v) = sat8(((S(u-1,v) - S(u+1,v)) >> 2) + 128),  S = I(v-1) + 2 I(v) + I(v+1)
     // dv(u,v) = sat8(((T(u-1,v) + 2 T(u,v) + T(u+1,v)) >> 2) + 128),  T = I(v-1) - I(v+1)
     // one item = four columns u0-2+4q .. +3 of row v0-2+r: six columns of S and T
     for (int i = tid; i < UH * GW; i += 256) {
         const int r = i / GW, q = i - r * GW;
-        const int ir = r + 1, ic = 4 * q + 1;          // column u0-2+4q-1 sits at sI column (u0-3+4q) - (u0-4)
+        const int ir = r + 1, ic = 4 * q + IX - 3;     // column u0-2+4q-1 sits at sI column (u0-3+4q) - (u0-IX)
         int S[6], T[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) {
@@ -145,12 +166,14 @@ k_descriptor(FrameGeom g, int half, const uint8_t* __restrict__ img1, const uint
 
 }  // namespace
 
-void launch_descriptor(const FrameGeom& g, int half, const uint8_t* img1, const uint8_t* img2,
+void descriptor_tile_box(int box[2]) { box[0] = IW; box[1] = IH; }
+
+void launch_descriptor(const FrameGeom& g, int half, const CUtensorMap& tm1, const CUtensorMap& tm2,
                        uint4* desc1, uint4* desc2, const GroupStrides& st, int n_frames, cudaStream_t s)
 {
     dim3 grid((g.W + TW - 1) / TW, (g.H + TH - 1) / TH, 2 * n_frames);
     ELASB_PREPARE_KERNEL(k_descriptor);
-    k_descriptor<<<grid, 256, 0, s>>>(g, half, img1, img2, desc1, desc2, st.img, st.desc);
+    k_descriptor<<<grid, 256, 0, s>>>(g, half, tm1, tm2, desc1, desc2, st.desc);
     count_launch();
 }
 
