@@ -25,15 +25,16 @@ namespace {
 // 4 * 16 * 255 < 2^15 and d below 2^12 (checked at context creation).
 constexpr int kStripPad = 12;         // addressable entries before and after every staged strip (see match_point)
 
-struct Best { unsigned key; int e2; };
-constexpr unsigned kNoKey = (32767u << 16) | 0xFFFFu;     // nothing evaluated: e1 = 32767 (elas.cpp:378-381)
+// Both the best and the second best are kept as KEYS: keys are unique (distinct d), ordering by key is ordering by
+// (energy, d), so the energy of the second-smallest key is the second order statistic of the energies.
+struct Best { unsigned key, key2; };
+constexpr unsigned kNoKey = (32767u << 16) | 0xFFFFu;     // nothing evaluated: e1 = e2 = 32767 (elas.cpp:378-381)
 
 __device__ __forceinline__ void scan_update(Best& b, int sum, int d)
 {
     const unsigned key = ((unsigned)sum << 16) | (unsigned)d;
-    const unsigned loser = max(b.key, key);               // the one that does not become / stay the best
+    b.key2 = min(b.key2, max(b.key, key));                // the one that does not become / stay the best
     b.key = min(b.key, key);
-    b.e2 = min(b.e2, (int)(loser >> 16));
 }
 
 // Warp-wide (best energy, its disparity, second-best energy) with two REDUX reductions: the best key is
@@ -43,8 +44,8 @@ __device__ __forceinline__ void scan_update(Best& b, int sum, int d)
 __device__ __forceinline__ void warp_merge(const Best& b, int& e1, int& d1, int& e2)
 {
     const unsigned best = __reduce_min_sync(0xffffffffu, b.key);
-    const unsigned mine = b.key == best ? (unsigned)b.e2 : (b.key >> 16);
-    e2 = (int)__reduce_min_sync(0xffffffffu, mine);
+    const unsigned mine = b.key == best ? b.key2 : b.key;
+    e2 = (int)(__reduce_min_sync(0xffffffffu, mine) >> 16);
     e1 = (int)(best >> 16);
     d1 = best == kNoKey ? -1 : (int)(best & 0xFFFFu);
 }
@@ -92,7 +93,7 @@ __device__ __forceinline__ int match_point(const FrameGeom& g, const elas_b200_p
 
     const int sgn = right_image ? 1 : -1;                 // warped column = u + sgn * d
     const int lane_off = 12 * (lane >> 2) + (lane & 3);
-    Best b = {kNoKey, 32767};                                                        // :378-381
+    Best b = {kNoKey, kNoKey};                                                       // :378-381
     for (int d0 = dmin + lane_off; d0 <= dmax; d0 += 96) {                           // :396-429
         // the four columns X_j = (u + sgn*d0) + sgn*(4j - 2), j = 0..3, as strip indices; the disparities d0+4 and
         // d0+8 may lie past dmax: they are computed but not counted, their columns (at most 10 beyond the staged
